@@ -1,0 +1,136 @@
+/* lsw.h -- C ABI of the B200 batched Smith-Waterman seeding engine (liblsw.so).
+ *
+ * This is the drop-in boundary for the hot path of jackwadden/lamprey's seed stage.
+ * The reference reaches that path through a PYTHON MODULE boundary, not an FFI:
+ *
+ *   /root/reference/lamprey.py:14-16     sys.path.insert(0, './lib'); import swalign
+ *   /root/reference/lamprey.py:1860-1865 swalign.NucleotideScoringMatrix(2, -1); swalign.LocalAlignment(scoring)
+ *   /root/reference/lamprey.py:563       aligner.align(str(seq), primer)          (ref = read slice, query = primer)
+ *   /root/reference/lamprey.py:596-645   findPrimerAlignments   (greedy left/right recursion around the best hit)
+ *   /root/reference/lamprey.py:699-733   findAllPrimerAlignments (T, Tc, every schema entry fwd + rc; stable sort)
+ *
+ * so the entry points below are what a replacement `swalign` module (lib/swalign.py in this
+ * repo; binding stub in INTEGRATION.md) binds through ctypes.  Plain pointers and sizes only;
+ * the caller owns every host buffer, the library owns device memory inside the context.
+ * All functions return 0 on success and a negative LSW_E_* code on failure; the message is
+ * available from lsw_last_error().  There is NO CPU fallback: without a CUDA device
+ * lsw_create() fails with LSW_E_CUDA.
+ *
+ * A context is single-threaded (the reference creates one aligner per forked worker,
+ * lamprey.py:1886, and calls it synchronously); CUDA is initialised in lsw_create(), never
+ * at library load, so a forked child may create its own context.
+ */
+#ifndef LSW_H
+#define LSW_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSW_OK            0
+#define LSW_E_CUDA       -1   /* no device / CUDA runtime or launch failure            */
+#define LSW_E_ARG        -2   /* bad argument (NULL, negative size, out-of-range index) */
+#define LSW_E_UNSUPPORTED -3  /* scoring / query the kernels do not implement           */
+#define LSW_E_OVERFLOW   -4   /* caller buffer too small; *n_out / *cigar_used = needed */
+#define LSW_E_STATE      -5   /* call order (e.g. align before set_queries)             */
+#define LSW_E_INTERNAL   -6   /* an internal invariant failed (reported, never silent)  */
+
+#define LSW_MAX_QUERY_LEN 63  /* rows a query may have (kernels keep all rows in registers) */
+
+typedef struct lsw_ctx lsw_ctx;
+
+/* One local alignment request: schema sequence `query` against read[start:end).
+ * Replaces one swalign.LocalAlignment.align(ref, query) call (lamprey.py:563). */
+typedef struct {
+    int32_t read;      /* index into the uploaded read batch        */
+    int32_t start;     /* slice start on the read (0-based)         */
+    int32_t end;       /* slice end, exclusive                      */
+    int32_t query;     /* index into the sequences of lsw_set_queries */
+} lsw_task;
+
+/* Fields of swalign.Alignment that LAMPrey consumes (lamprey.py:564-566, 672-694).
+ * Positions are relative to the SLICE, 0-based, ends exclusive, exactly as swalign reports. */
+typedef struct {
+    int32_t score;
+    int32_t q_pos, q_end;
+    int32_t r_pos, r_end;
+    int32_t matches, mismatches;   /* identity = matches / (matches + mismatches), 0 if both 0 */
+    int32_t n_cigar;               /* number of (count, op) runs                             */
+    int64_t cigar_off;             /* offset of the first run in the caller's cigar buffer     */
+} lsw_result;
+
+/* One seed hit of findPrimerAlignments (lamprey.py:138-161 Alignment + the swalign fields behind it).
+ * start/end are READ coordinates (already shifted, lamprey.py:637-640). */
+typedef struct {
+    int32_t read;
+    int32_t start, end;
+    int16_t query;                 /* index into the sequences of lsw_set_queries */
+    int16_t depth;                 /* recursion depth at which the hit was found  */
+    int16_t matches, mismatches;
+    int16_t score;
+    int16_t q_pos, q_end;
+    int16_t reserved;
+    int32_t reserved2;
+} lsw_hit;                         /* 32 bytes */
+
+typedef struct {
+    int64_t tasks;        /* align() invocations the reference would have made            */
+    int64_t cells;        /* sum over those of len(slice) * len(query)  (the CUPS unit)   */
+    int64_t top_tasks;    /* round-0 (whole read) invocations                            */
+    int64_t top_cells;
+    int64_t traced;       /* tasks that needed a traceback (score could pass threshold)   */
+    int64_t hits;
+    int32_t rounds;       /* recursion depth reached + 1                                  */
+    int32_t reserved;
+    float   ms_score;     /* device time in the score kernels (CUDA events, own stream)   */
+    float   ms_trace;     /* device time in the traceback kernels                         */
+    float   ms_other;     /* compaction, sorting, bookkeeping kernels                     */
+    float   ms_total;     /* device time of the whole call                                */
+    int64_t score_launches, trace_launches, other_launches;
+    int64_t steps;        /* lane-steps (columns incl. dead padding) the score kernels ran */
+} lsw_counters;
+
+/* cigar runs are (count << 2) | op with op 1 = 'M', 2 = 'I', 3 = 'D' */
+
+int  lsw_create(int device, lsw_ctx** out);
+void lsw_destroy(lsw_ctx* ctx);
+const char* lsw_last_error(const lsw_ctx* ctx);      /* ctx may be NULL: error of the last failed lsw_create */
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*; NULL = the context's own stream). */
+int lsw_set_stream(lsw_ctx* ctx, void* cuda_stream);
+
+/* swalign.NucleotideScoringMatrix(match, mismatch) + LocalAlignment(gap_penalty, gap_extension_penalty).
+ * Supported: match > 0, mismatch <= 0, gap == gap_ext < 0, match*LSW_MAX_QUERY_LEN + |gap| <= 127. */
+int lsw_set_scoring(lsw_ctx* ctx, int match, int mismatch, int gap, int gap_ext);
+
+/* The schema sequences (already in search order; reverse complements supplied by the caller).
+ * ASCII, upper-cased by the library; must be ACGT only and 1..LSW_MAX_QUERY_LEN long. */
+int lsw_set_queries(lsw_ctx* ctx, int n, const uint8_t* concat, const int32_t* offs /* n+1 */);
+
+/* Host -> device copy of a read batch (ASCII, any bytes; non-ACGT never matches) and device-side
+ * re-coding.  offs has n+1 entries.  Replaces the per-read str(seq) handed to align(). */
+int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_t* offs);
+
+/* Batched align(): n_tasks independent alignments, results in task order.  cigar_buf may be NULL
+ * (no CIGARs wanted).  *cigar_used is the number of runs produced; LSW_E_OVERFLOW if > cigar_cap. */
+int lsw_align_tasks(lsw_ctx* ctx, int64_t n_tasks, const lsw_task* tasks, lsw_result* out,
+                    uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used);
+
+/* findAllPrimerAlignments for every uploaded read: all queries, greedy recursion on the device.
+ * Hits are returned sorted by (read, start, query) -- the order lamprey.py:722's stable sort
+ * produces.  Device-resident variant: results stay on the device until lsw_fetch_hits(). */
+int lsw_find_all(lsw_ctx* ctx, double identity_threshold, int64_t* n_hits, lsw_counters* counters);
+int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out);
+
+/* Integer-pipe roofline microbenchmark: ops/s of independent chains of one
+ * instruction mix on every SM.  mode: see lamprey_b200/csrc/intpeak.cuh.  Returns lane-ops per second. */
+int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per_s, float* ms);
+
+int lsw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
