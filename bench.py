@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- seeding throughput of the B200 engine on BASELINE.json's synthetic workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--workload NAME] [--thr T]
+    python bench.py --impl reference ...        # the reference arm: CPU (Cython) swalign seeding
+
+One "step" = one pass of the hot path (findAllPrimerAlignments for every read: all 46 schema
+sequences, greedy recursion included) over one batch of synthetic reads.  At N=1 the workload is
+BASELINE.json configs[2]: 10^6 ONT-like concatemer reads, 2 kb mean, 8 % error, H3.3 schema.
+With N GPUs every rank seeds its own batch of R reads (weak scaling, no data-path collective --
+reads are independent units; only timings and counts are reduced).
+
+Printed JSON line (rank 0): metric reads/s (whole job), plus GCUPS, roofline (integer ALU bound,
+SURVEY.md section 8d), cpu_baseline (Cython swalign on the host cores, N=1 only), e2e (host
+buffers -> hits on the host through the C ABI, H2D/D2H inside the timed region), clocks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCHEMA = os.path.join(ROOT, "tests", "golden", "H3.3_set1.primers")
+ALG_OPS_PER_CELL = 6          # int32-lane ops per DP cell (algorithmic)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def gather_max_and_sum(t_local, sums, device="cuda"):
+    """max over ranks of a time, sum over ranks of counters (the only cross-rank traffic)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return (t_local,) + tuple(sums)
+    t = torch.tensor([t_local], dtype=torch.float64, device=device)
+    s = torch.tensor(list(sums), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return (float(t[0]),) + tuple(int(round(v)) for v in s.tolist())
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle's Cython build ("Cython swalign", README.md:18-25 of the reference) driven by
+# the restated findAllPrimerAlignments, one process per host core (lamprey.py:2182-2196).
+# ---------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(schema_path):
+    import importlib.util
+    from oracle import build_cython
+    out = build_cython.build()
+    mods = {}
+    for name in ("swalign_cy", "seeding_cy"):
+        so = [f for f in os.listdir(out) if f.startswith(name) and f.endswith(".so")][0]
+        spec = importlib.util.spec_from_file_location(name, os.path.join(out, so))
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    _CPU["sw"] = mods["swalign_cy"].LocalAlignment(mods["swalign_cy"].NucleotideScoringMatrix(2, -1))
+    _CPU["seed"] = mods["seeding_cy"]
+    _CPU["ps"] = mods["seeding_cy"].PrimerSet(schema_path)
+
+
+def _cpu_seed(args):
+    read, thr = args
+    st = _CPU["seed"].Stats()
+    hits, _ = _CPU["seed"].find_all_primer_alignments(_CPU["sw"], read, _CPU["ps"], thr, st)
+    return len(hits), st.calls, st.cells
+
+
+def cpu_seed_sample(reads, thr, cores, pool=None):
+    """-> (seconds, hits, calls, cells) for seeding `reads` on `cores` processes."""
+    import multiprocessing as mp
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(SCHEMA,))
+        pool.map(_cpu_seed, [("ACGT" * 8, thr)] * cores)        # start-up (imports) outside the timing
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_seed, [(r, thr) for r in reads], chunksize=1)
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close()
+        pool.join()
+    return dt, sum(r[0] for r in res), sum(r[1] for r in res), sum(r[2] for r in res)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([f.strip() for f in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_reads(args, rank, world, workers):
+    from lamprey_b200 import synth
+    kw = dict(synth.CONFIGS[args.workload])
+    kw["seed"] = kw["seed"] + 1000 * rank            # every rank seeds its own batch (weak scaling)
+    return synth.generate(args.reads, workers=workers, **kw)
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    from lamprey_b200 import synth
+    cores = os.cpu_count() or 1
+    sample = max(cores, 8)
+    kw = dict(synth.CONFIGS[args.workload])
+    concat, offs = synth.generate(sample * (args.steps + args.warmup), chunk=sample, **kw)
+    reads = synth.reads_as_strings(concat, offs)
+    import multiprocessing as mp
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(SCHEMA,))
+    pool.map(_cpu_seed, [("ACGT" * 8, args.thr)] * cores)
+    k = 0
+    for _ in range(args.warmup):
+        cpu_seed_sample(reads[k:k + sample], args.thr, cores, pool)
+        k += sample
+    t = cells = 0
+    for _ in range(args.steps):
+        dt, _, _, c = cpu_seed_sample(reads[k:k + sample], args.thr, cores, pool)
+        t += dt
+        cells += c
+        k += sample
+    pool.close()
+    pool.join()
+    value = sample * args.steps / t
+    line = {"impl": "reference", "metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "python-int",
+            "data": "synthetic", "gcups": cells / t / 1e9,
+            "config": {"workload": args.workload, "schema": "H3.3_set1 (46 sequences)", "threshold": args.thr,
+                       "reads_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                             "sample": "%d reads of %s per step, Cython build of oracle/swalign_ref.py + "
+                                       "seeding_ref.py, one process per core" % (sample, args.workload)},
+            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1000000, help="reads per GPU per step")
+    ap.add_argument("--workload", default="synth_2kb_8pct")
+    ap.add_argument("--thr", type=float, default=0.70)          # lamprey.py:2293 default
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, local_rank, world = dist_env()
+    cores = os.cpu_count() or 1
+    workers = max(1, cores // max(1, world))
+
+    # ---- everything that forks happens before CUDA is touched -------------------------------
+    concat, offs = workload_reads(args, rank, world, workers)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from lamprey_b200 import synth
+        # ~2 s per 2 kb read per core for the Cython port: size the sample for about --cpu-seconds
+        per_read = 2.2 * (np.diff(offs).mean() / 2000.0) ** 1.0
+        sample = int(max(cores, min(len(offs) - 1, cores * args.cpu_seconds / per_read)))
+        reads = synth.reads_as_strings(concat[:offs[sample]], offs[:sample + 1])
+        dt, hits_cpu, calls_cpu, cells_cpu = cpu_seed_sample(reads, args.thr, cores)
+        cpu_baseline = {"value": sample / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                        "gcups": cells_cpu / dt / 1e9, "seconds": dt,
+                        "sample": "first %d reads of the workload, Cython build of oracle/swalign_ref.py + "
+                                  "seeding_ref.py (README.md:18-25 recipe), one process per core" % sample,
+                        "_hits": hits_cpu, "_calls": calls_cpu, "_cells": cells_cpu, "_n": sample}
+
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from lamprey_b200 import _native, seeding
+
+    eng = _native.Engine(local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_scoring(2, -1, -1, -1)
+    ps = seeding.PrimerSet(SCHEMA)
+    seqs = [s for _, s in ps.sequences()]
+    eng.set_queries(seqs)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # pinned host buffers: the reference-facing call takes host memory
+    h_ascii = torch.empty(len(concat), dtype=torch.uint8, pin_memory=True)
+    h_ascii.numpy()[:] = concat
+    h_offs = torch.empty(len(offs), dtype=torch.int64, pin_memory=True)
+    h_offs.numpy()[:] = offs
+    ascii_np, offs_np = h_ascii.numpy(), h_offs.numpy()
+
+    # integer roofline of this box (not in MEASURED_PEAKS.json)
+    peak = {}
+    if rank == 0:
+        for mode, name in ((0, "viaddmnmx_s16x2"), (1, "vimnmx3_s16x2"), (2, "iadd"), (3, "imad"), (4, "k1_mix"),
+                           (5, "k1_mix_imad"), (6, "lop3")):
+            ops, _ = eng.measure_int_peak(mode, 20000)
+            peak[name] = ops / 1e9
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    eng.upload_reads(ascii_np, offs_np)
+    n_hits = 0
+    for _ in range(args.warmup):
+        n_hits = eng.find_all(args.thr, fetch=False)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc = dict(ms_score=0.0, ms_trace=0.0, ms_other=0.0, ms_total=0.0, launches=0, score_launches=0)
+    e0.record(stream)
+    for _ in range(args.steps):
+        n_hits = eng.find_all(args.thr, fetch=False)
+        c = eng.last_counters
+        for k in ("ms_score", "ms_trace", "ms_other", "ms_total"):
+            acc[k] += c[k]
+        acc["launches"] += c["score_launches"] + c["trace_launches"] + c["other_launches"]
+        acc["score_launches"] += c["score_launches"]
+    e1.record(stream)
+    barrier()
+    t_value = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.stop() if sampler else None
+    cnt = dict(eng.last_counters)
+    t_value, reads_total, cells_total, hits_total = gather_max_and_sum(
+        t_value, [args.reads * args.steps, cnt["cells"] * args.steps, n_hits * args.steps])
+
+    # parity spot check against the CPU baseline's own sample (same reads, same threshold)
+    parity = None
+    if cpu_baseline is not None:
+        n = cpu_baseline.pop("_n")
+        eng.upload_reads(ascii_np[:offs_np[n]], offs_np[:n + 1])
+        sub = eng.find_all(args.thr)
+        c2 = eng.last_counters
+        parity = {"reads": n, "hits_match": int(len(sub)) == cpu_baseline.pop("_hits"),
+                  "calls_match": c2["tasks"] == cpu_baseline.pop("_calls"),
+                  "cells_match": c2["cells"] == cpu_baseline.pop("_cells")}
+        eng.upload_reads(ascii_np, offs_np)
+
+    # ---- e2e: host buffers in, hits on the host out, every step --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_hits = torch.empty(max(1, int(n_hits * 1.05) + 1024) * 32, dtype=torch.uint8, pin_memory=True)
+        hits_np = h_hits.numpy().view(_native.HIT_DT)
+
+        def e2e_step():
+            eng.upload_reads(ascii_np, offs_np)                     # H2D of this step's reads
+            n = eng.find_all(args.thr, fetch=False)
+            return len(eng.fetch_hits(out=hits_np))                 # D2H of this step's hits
+
+        for _ in range(max(1, args.warmup - 2)):
+            got = e2e_step()
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            got = e2e_step()
+        e1.record(stream)
+        barrier()
+        t_e2e = e0.elapsed_time(e1) / 1e3
+        t_e2e, reads_e2e = gather_max_and_sum(t_e2e, [args.reads * args.steps])
+        e2e = {"value": reads_e2e / t_e2e, "unit": "reads/s",
+               "h2d_bytes_per_step": int(ascii_np.nbytes + offs_np.nbytes), "d2h_bytes_per_step": int(got * 32),
+               "ms_per_step": 1e3 * t_e2e / args.steps}
+
+    if rank == 0:
+        gcups = cells_total / t_value / 1e9
+        score_s = acc["ms_score"] / 1e3
+        k1_gcups = cnt["cells"] * args.steps / score_s / 1e9 if score_s > 0 else None
+        peak_ops = max(peak.get("viaddmnmx_s16x2", 0.0), peak.get("iadd", 0.0))    # G packed-lane ops / s
+        # one packed (s16x2) instruction lane updates 2 cells' worth of one algorithmic op
+        peak_gcups = peak_ops * 2.0 / ALG_OPS_PER_CELL if peak_ops else None
+        roofline = {"bound": "int_alu", "kernel": "k_score<NR> (K1: DP fill + arg-max)",
+                    "achieved": k1_gcups, "peak": peak_gcups, "unit": "GCUPS",
+                    "frac": (k1_gcups / peak_gcups) if (k1_gcups and peak_gcups) else None,
+                    "traffic": None,
+                    "peak_source": "lsw_measure_int_peak on this box (MEASURED_PEAKS.json has no integer rate): "
+                                   "VIADDMNMX.S16x2 lane-ops/s x 2 cells / %d algorithmic ops per cell" % ALG_OPS_PER_CELL,
+                    "int_peak_glaneops": peak, "launches": acc["score_launches"],
+                    "avg_launch_ms": acc["ms_score"] / max(1, acc["score_launches"]),
+                    "k1_share_of_step": acc["ms_score"] / max(1e-9, acc["ms_total"]),
+                    "lane_step_efficiency": cnt["cells"] / max(1, cnt["steps"])}
+        line = {"metric": "reads_per_sec", "value": reads_total / t_value, "unit": "reads/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16x2",
+                "data": "synthetic", "gcups": gcups, "gcups_top_level": cnt["top_cells"] * args.steps * world / t_value / 1e9,
+                "config": {"workload": args.workload, "reads_per_gpu": args.reads, "mean_len": float(np.diff(offs).mean()),
+                           "schema": "H3.3_set1 (46 sequences, 1140 rows)", "threshold": args.thr,
+                           "l2": "inputs larger than L2 (%.2f GB of read codes + task lists per step)" % (len(concat) / 1e9),
+                           "tasks_per_step": cnt["tasks"], "cells_per_step": cnt["cells"], "hits_per_step": n_hits,
+                           "rounds": cnt["rounds"]},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+                "gpu_launches": acc["launches"],
+                "breakdown_ms_per_step": {k: acc[k] / args.steps for k in ("ms_score", "ms_trace", "ms_other", "ms_total")},
+                "parity_vs_cpu_sample": parity}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

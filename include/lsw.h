@@ -102,7 +102,7 @@ const char* lsw_last_error(const lsw_ctx* ctx);      /* ctx may be NULL: error o
 int lsw_set_stream(lsw_ctx* ctx, void* cuda_stream);
 
 /* swalign.NucleotideScoringMatrix(match, mismatch) + LocalAlignment(gap_penalty, gap_extension_penalty).
- * Supported: match > 0, mismatch <= 0, gap == gap_ext < 0, match*LSW_MAX_QUERY_LEN + |gap| <= 127. */
+ * Supported: match > 0, mismatch < 0, gap == gap_ext < 0, match*LSW_MAX_QUERY_LEN + |gap| <= 127. */
 int lsw_set_scoring(lsw_ctx* ctx, int match, int mismatch, int gap, int gap_ext);
 
 /* The schema sequences (already in search order; reverse complements supplied by the caller).
@@ -121,6 +121,7 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n_tasks, const lsw_task* tasks, lsw_re
 /* findAllPrimerAlignments for every uploaded read: all queries, greedy recursion on the device.
  * Hits are returned sorted by (read, start, query) -- the order lamprey.py:722's stable sort
  * produces.  Device-resident variant: results stay on the device until lsw_fetch_hits(). */
+int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap);   /* 0 = default (total bases / 8 + 4096) */
 int lsw_find_all(lsw_ctx* ctx, double identity_threshold, int64_t* n_hits, lsw_counters* counters);
 int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out);
 

@@ -1,0 +1,807 @@
+// lsw.cu -- host side of liblsw.so: the C ABI declared in include/lsw.h.
+//
+// Drop-in boundary for the seed stage of jackwadden/lamprey:
+//   lsw_align_tasks  <->  swalign.LocalAlignment.align(ref, query)        (/root/reference/lamprey.py:563)
+//   lsw_find_all     <->  findAllPrimerAlignments / findPrimerAlignments  (/root/reference/lamprey.py:596-645, 699-733)
+// The recursion of findPrimerAlignments runs on the device as level-synchronous rounds:
+//   round k:  K1 (score + arg-max of every task)  ->  K2 (traceback, hit test, left/right children)
+//             ->  scan + scatter of the children into the task list of round k+1.
+// No CPU fallback exists: every entry point needs the CUDA device the context was created on.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <thrust/iterator/transform_iterator.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lsw.h"
+#include "lsw_common.cuh"
+#include "lsw_score.cuh"
+#include "lsw_trace.cuh"
+#include "intpeak.cuh"
+#include "lsw_host.hpp"
+
+using namespace lsw;
+
+namespace {
+
+std::string g_create_error;
+
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct TaskBuf {
+    DevBuf read, a, b, seq, orig;
+    cudaError_t ensure(size_t n, bool with_orig) {
+        cudaError_t e;
+        if ((e = read.ensure(n * 4)) != cudaSuccess) return e;
+        if ((e = a.ensure(n * 4)) != cudaSuccess) return e;
+        if ((e = b.ensure(n * 4)) != cudaSuccess) return e;
+        if ((e = seq.ensure(n * 2)) != cudaSuccess) return e;
+        if (with_orig && (e = orig.ensure(n * 4)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    TaskArrays view() const {
+        TaskArrays t;
+        t.read = read.as<int32_t>(); t.a = a.as<int32_t>(); t.b = b.as<int32_t>();
+        t.seq = seq.as<int16_t>(); t.orig = orig.as<int32_t>();
+        return t;
+    }
+    void release() { read.release(); a.release(); b.release(); seq.release(); orig.release(); }
+};
+
+struct Timed { cudaEvent_t e0, e1; int kind; };
+
+}  // namespace
+
+struct lsw_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    int num_sms = 0;
+
+    int match = 2, mismatch = -1, g = 1;
+    int nseq = 0;
+    std::vector<int32_t> qlen;
+    std::vector<uint8_t> qcodes;
+    std::vector<int32_t> class_of;
+    std::vector<int32_t> class_seqs[NCLASS];
+    DevBuf d_qcodes, d_qlen, d_class_seqs[NCLASS], d_cand_ok;
+
+    int64_t n_reads = 0, total_bases = 0, codes_bytes = 0;
+    std::vector<int64_t> h_roff;
+    std::vector<int32_t> h_rlen;
+    DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen;
+
+    TaskBuf tb[2], child;
+    DevBuf d_res, d_seg[2], d_head, d_cand[NCLASS], d_ncand, d_counters, d_child_flag, d_pos,
+           d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_nhits, d_keys[2], d_vals[2], d_err,
+           d_results, d_cigar, d_ncigar;
+    int64_t hit_cap_user = 0;
+    int64_t n_hits = 0;
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char buf_[512];                                                                   \
+            snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call,            \
+                     cudaGetErrorString(e_));                                                 \
+            ctx->err = buf_;                                                                  \
+            return LSW_E_CUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+int fail(lsw_ctx* ctx, int code, const char* msg) { ctx->err = msg; return code; }
+
+// ---- small kernels ----------------------------------------------------------------------
+
+// ASCII -> read codes (A,C,G,T -> 0..3 after upper-casing, anything else -> 4), one warp per read,
+// each read written at a 16-byte aligned offset.
+__global__ void k_encode_reads(const uint8_t* __restrict__ ascii, const int64_t* __restrict__ offs_in,
+                               const int64_t* __restrict__ roff, uint8_t* __restrict__ codes, int64_t n_reads) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n_reads; i += nwarps) {
+        const int64_t s = offs_in[i], len = offs_in[i + 1] - s, d = roff[i];
+        const int64_t padded = roff[i + 1] - d;
+        for (int64_t j = lane; j < padded; j += 32) {
+            const uint8_t code = j < len ? encode_base(ascii[s + j]) : (uint8_t)CODE_OTHER;
+            codes[d + j] = code;
+        }
+    }
+}
+
+// Round 0 of findAllPrimerAlignments: every sequence against every whole read.
+__global__ void k_init_tasks(TaskArrays t, const int32_t* __restrict__ rlen, int64_t n_reads, int nseq) {
+    const int64_t n = n_reads * nseq;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int s = (int)(i / n_reads);
+        const int64_t r = i - (int64_t)s * n_reads;
+        t.read[i] = (int32_t)r; t.a[i] = 0; t.b[i] = rlen[r]; t.seq[i] = (int16_t)s;
+    }
+}
+
+struct FlagToInt {
+    __host__ __device__ int32_t operator()(const uint8_t& f) const { return (int32_t)f; }
+};
+
+// children of round k (slots 2t, 2t+1) -> dense task list of round k+1; order is preserved, so the
+// tasks of one sequence stay contiguous and seg_next[s] = pos[2 * seg[s]].
+__global__ void k_scatter_children(TaskArrays child, const uint8_t* __restrict__ flag, const int32_t* __restrict__ pos,
+                                   int64_t n2, TaskArrays next, const int64_t* __restrict__ seg, int64_t* __restrict__ seg_next,
+                                   int nseq) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid <= nseq) {
+        const int64_t j = 2 * seg[gid];
+        seg_next[gid] = pos[j < n2 ? j : n2];
+    }
+    for (int64_t j = gid; j < n2; j += (int64_t)gridDim.x * blockDim.x) {
+        if (flag[j]) {
+            const int32_t d = pos[j];
+            next.read[d] = child.read[j]; next.a[d] = child.a[j]; next.b[d] = child.b[j]; next.seq[d] = child.seq[j];
+        }
+    }
+}
+
+// sort key of a hit: (read, start, query) -- the order lamprey.py:722's stable sort yields
+__global__ void k_hit_keys(const lsw_hit* __restrict__ hits, int64_t n, unsigned long long* __restrict__ keys,
+                           uint32_t* __restrict__ vals) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const lsw_hit h = hits[i];
+        keys[i] = ((unsigned long long)(uint32_t)h.read << 35) | ((unsigned long long)(uint32_t)h.start << 8) |
+                  (unsigned long long)(uint16_t)h.query;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void k_gather_hits(const lsw_hit* __restrict__ hits, const uint32_t* __restrict__ vals, int64_t n,
+                              lsw_hit* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4* src = reinterpret_cast<const int4*>(hits + vals[i]);
+        int4* dst = reinterpret_cast<int4*>(out + i);
+        dst[0] = src[0]; dst[1] = src[1];
+    }
+}
+
+// ---- helpers -----------------------------------------------------------------------------
+
+int grid_for(int64_t n, int threads, int cap_blocks) {
+    int64_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > cap_blocks) b = cap_blocks;
+    return (int)b;
+}
+
+cudaEvent_t next_event(lsw_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+struct Span {      // times a region of the stream into one of the lsw_counters buckets
+    lsw_ctx* ctx; Timed t;
+    Span(lsw_ctx* c, int kind) : ctx(c) {
+        t.kind = kind; t.e0 = next_event(c); t.e1 = next_event(c);
+        if (t.e0) cudaEventRecord(t.e0, c->stream);
+    }
+    ~Span() { if (t.e1) { cudaEventRecord(t.e1, ctx->stream); ctx->timed.push_back(t); } }
+};
+
+template <int NR>
+int launch_score(lsw_ctx* ctx, const ScoreParams& P, int64_t n_class_tasks) {
+    const size_t smem = score_smem_bytes<NR>();
+    CK(cudaFuncSetAttribute(k_score<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score<NR>, SCORE_WARPS * 32, smem));
+    if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "score kernel does not fit on an SM");
+    const int64_t lanes_needed = (n_class_tasks + 1) / 2;
+    const int blocks = grid_for(lanes_needed, SCORE_WARPS * 32, ctx->num_sms * occ);
+    k_score<NR><<<blocks, SCORE_WARPS * 32, smem, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    return LSW_OK;
+}
+
+int launch_score_class(lsw_ctx* ctx, int c, const ScoreParams& P, int64_t n) {
+    switch (CLASS_NR[c]) {
+        case 16: return launch_score<16>(ctx, P, n);
+        case 24: return launch_score<24>(ctx, P, n);
+        case 32: return launch_score<32>(ctx, P, n);
+        case 48: return launch_score<48>(ctx, P, n);
+        default: return launch_score<64>(ctx, P, n);
+    }
+}
+
+template <int NR>
+int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<NR>, TRACE_THREADS, 0));
+    if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
+    const int blocks = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * occ);
+    const int64_t threads = (int64_t)blocks * TRACE_THREADS;
+    const int64_t W = trace_window(qmax, ctx->match, ctx->g);
+    CK(ctx->d_scratch.ensure((size_t)threads * (size_t)W * (NR / 16) * 4));
+    P.scratch = ctx->d_scratch.as<uint32_t>();
+    P.scratch_stride = threads;
+    k_trace<NR><<<blocks, TRACE_THREADS, 0, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    return LSW_OK;
+}
+
+int launch_trace_class(lsw_ctx* ctx, int c, const TraceParams& P, int64_t n, int qmax) {
+    switch (CLASS_NR2[c]) {
+        case 16: return launch_trace<16>(ctx, P, n, qmax);
+        case 32: return launch_trace<32>(ctx, P, n, qmax);
+        case 48: return launch_trace<48>(ctx, P, n, qmax);
+        default: return launch_trace<64>(ctx, P, n, qmax);
+    }
+}
+
+void fill_score_params(lsw_ctx* ctx, ScoreParams& P, const TaskBuf& cur, int segi) {
+    P.codes = ctx->d_codes.as<uint8_t>();
+    P.roff = ctx->d_roff.as<int64_t>();
+    P.t = cur.view();
+    P.seg = ctx->d_seg[segi].as<int64_t>();
+    P.head = ctx->d_head.as<unsigned long long>();
+    P.res = ctx->d_res.as<int2>();
+    P.qcodes = ctx->d_qcodes.as<uint8_t>();
+    P.qlen = ctx->d_qlen.as<int32_t>();
+    P.cand_ok = ctx->d_cand_ok.as<uint8_t>();
+    P.counters = ctx->d_counters.as<unsigned long long>();
+    P.s_match = SC * (ctx->match + ctx->g);
+    P.s_mis = SC * (ctx->mismatch + ctx->g);
+    P.g = ctx->g;
+}
+
+void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {
+    memset(&T, 0, sizeof T);
+    T.codes = ctx->d_codes.as<uint8_t>();
+    T.roff = ctx->d_roff.as<int64_t>();
+    T.t = cur.view();
+    T.res = ctx->d_res.as<int2>();
+    T.qcodes = ctx->d_qcodes.as<uint8_t>();
+    T.qlen = ctx->d_qlen.as<int32_t>();
+    T.match = ctx->match; T.mismatch = ctx->mismatch; T.g = ctx->g;
+    T.errflag = ctx->d_err.as<int32_t>();
+}
+
+// Runs K1 then K2 for every class over the task list `cur` (segments h_seg on the host).
+int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int64_t>& h_seg, int64_t n,
+              TraceParams Tbase, lsw_counters* cnt) {
+    CK(ctx->d_res.ensure((size_t)n * sizeof(int2)));
+    CK(ctx->d_head.ensure((size_t)ctx->nseq * 8));
+    CK(ctx->d_ncand.ensure(NCLASS * 8));
+    CK(cudaMemsetAsync(ctx->d_head.p, 0, (size_t)ctx->nseq * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ncand.p, 0, NCLASS * 8, ctx->stream));
+    int64_t ncls[NCLASS];
+    int qmax[NCLASS];
+    for (int c = 0; c < NCLASS; c++) {
+        ncls[c] = 0; qmax[c] = 0;
+        for (int s : ctx->class_seqs[c]) { ncls[c] += h_seg[s + 1] - h_seg[s]; qmax[c] = std::max(qmax[c], ctx->qlen[s]); }
+        if (ncls[c]) CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4));
+    }
+    ScoreParams P;
+    fill_score_params(ctx, P, cur, segi);
+    {
+        Span sp(ctx, 0);
+        for (int c = 0; c < NCLASS; c++) {
+            if (!ncls[c]) continue;
+            P.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
+            P.n_class_seqs = (int)ctx->class_seqs[c].size();
+            P.cand = ctx->d_cand[c].as<uint32_t>();
+            P.ncand = ctx->d_ncand.as<unsigned long long>() + c;
+            int rc = launch_score_class(ctx, c, P, ncls[c]);
+            if (rc) return rc;
+            if (cnt) cnt->score_launches++;
+        }
+    }
+    {
+        Span sp(ctx, 1);
+        for (int c = 0; c < NCLASS; c++) {
+            if (!ncls[c]) continue;
+            TraceParams T = Tbase;
+            T.res = ctx->d_res.as<int2>();
+            T.cand = ctx->d_cand[c].as<uint32_t>();
+            T.ncand = ctx->d_ncand.as<unsigned long long>() + c;
+            int rc = launch_trace_class(ctx, c, T, ncls[c], qmax[c]);
+            if (rc) return rc;
+            if (cnt) cnt->trace_launches++;
+        }
+    }
+    return LSW_OK;
+}
+
+void collect_times(lsw_ctx* ctx, lsw_counters* cnt) {
+    for (const Timed& t : ctx->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) != cudaSuccess) continue;
+        if (t.kind == 0) cnt->ms_score += ms;
+        else if (t.kind == 1) cnt->ms_trace += ms;
+        else if (t.kind == 2) cnt->ms_other += ms;
+        else cnt->ms_total += ms;
+    }
+    ctx->timed.clear();
+    ctx->ev_used = 0;
+}
+
+}  // namespace
+
+// ================================ C ABI ====================================================
+
+extern "C" {
+
+int lsw_version(void) { return 1; }
+
+const char* lsw_last_error(const lsw_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int lsw_create(int device, lsw_ctx** out) {
+    if (!out) { g_create_error = "lsw_create: out is NULL"; return LSW_E_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("lsw_create: no CUDA device (") + cudaGetErrorString(e) +
+                         "); this engine has no CPU fallback";
+        return LSW_E_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "lsw_create: device index out of range"; return LSW_E_ARG; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return LSW_E_CUDA; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return LSW_E_CUDA; }
+    if (prop.major < 10) {
+        g_create_error = "lsw_create: kernels are built for sm_100a (B200) only";
+        return LSW_E_CUDA;
+    }
+    lsw_ctx* ctx = new lsw_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); delete ctx; return LSW_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return LSW_OK;
+}
+
+void lsw_destroy(lsw_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_qcodes, &ctx->d_qlen, &ctx->d_cand_ok, &ctx->d_ascii, &ctx->d_offs_in, &ctx->d_codes,
+                      &ctx->d_roff, &ctx->d_rlen, &ctx->d_res, &ctx->d_seg[0], &ctx->d_seg[1], &ctx->d_head,
+                      &ctx->d_ncand, &ctx->d_counters, &ctx->d_child_flag, &ctx->d_pos, &ctx->d_cubtemp,
+                      &ctx->d_scratch, &ctx->d_hits, &ctx->d_hits_sorted, &ctx->d_nhits, &ctx->d_keys[0],
+                      &ctx->d_keys[1], &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_err, &ctx->d_results,
+                      &ctx->d_cigar, &ctx->d_ncigar};
+    for (DevBuf* b : bufs) b->release();
+    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); }
+    ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release();
+    for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int lsw_set_stream(lsw_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return LSW_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return LSW_OK;
+}
+
+int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap) {
+    if (!ctx || cap < 0) return LSW_E_ARG;
+    ctx->hit_cap_user = cap;
+    return LSW_OK;
+}
+
+int lsw_set_scoring(lsw_ctx* ctx, int match, int mismatch, int gap, int gap_ext) {
+    if (!ctx) return LSW_E_ARG;
+    if (gap != gap_ext)
+        return fail(ctx, LSW_E_UNSUPPORTED, "gap_penalty != gap_extension_penalty is not implemented (LAMPrey uses -1/-1)");
+    // mismatch must be strictly negative: K1 lets a lane run a few dead columns past a slice end and
+    // relies on every move through them costing at least 1, so that they can never tie the arg-max.
+    if (match <= 0 || mismatch >= 0 || gap >= 0)
+        return fail(ctx, LSW_E_UNSUPPORTED, "need match > 0, mismatch < 0, gap < 0");
+    if (match * LSW_MAX_QUERY_LEN - gap > 127 && match * 1 - gap > 127)
+        return fail(ctx, LSW_E_UNSUPPORTED, "scores do not fit the packed 8.8 fixed-point cells");
+    ctx->match = match; ctx->mismatch = mismatch; ctx->g = -gap;
+    // queries set earlier must still fit
+    for (int s = 0; s < ctx->nseq; s++)
+        if (ctx->match * ctx->qlen[s] + ctx->g > 127)
+            return fail(ctx, LSW_E_UNSUPPORTED, "match * len(query) + |gap| must be <= 127 for the packed cells");
+    return LSW_OK;
+}
+
+int lsw_set_queries(lsw_ctx* ctx, int n, const uint8_t* concat, const int32_t* offs) {
+    if (!ctx || n <= 0 || n > 255 || !concat || !offs) return ctx ? fail(ctx, LSW_E_ARG, "lsw_set_queries: bad argument (1..255 sequences)") : LSW_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int32_t> qlen(n), class_of(n);
+    std::vector<uint8_t> qcodes((size_t)n * QSTRIDE, 0xFF);
+    for (int s = 0; s < n; s++) {
+        const int len = offs[s + 1] - offs[s];
+        if (len < 1 || len > LSW_MAX_QUERY_LEN)
+            return fail(ctx, LSW_E_UNSUPPORTED, "query length must be 1..63 (all rows are kept in registers)");
+        if (ctx->match * len + ctx->g > 127)
+            return fail(ctx, LSW_E_UNSUPPORTED, "match * len(query) + |gap| must be <= 127 for the packed cells");
+        qlen[s] = len;
+        for (int j = 0; j < len; j++) {
+            const int code = encode_base(concat[offs[s] + j]) < CODE_OTHER ? (int)encode_base(concat[offs[s] + j]) : -1;
+            if (code < 0)
+                return fail(ctx, LSW_E_UNSUPPORTED, "queries must be ACGT only (swalign would match a non-ACGT query character against the same character in a read)");
+            qcodes[(size_t)s * QSTRIDE + j] = (uint8_t)code;
+        }
+        int c = 0;
+        while (CLASS_NR[c] < len) c++;
+        class_of[s] = c;
+    }
+    ctx->nseq = n; ctx->qlen = qlen; ctx->qcodes = qcodes; ctx->class_of = class_of;
+    for (int c = 0; c < NCLASS; c++) ctx->class_seqs[c].clear();
+    for (int s = 0; s < n; s++) ctx->class_seqs[class_of[s]].push_back(s);
+    CK(ctx->d_qcodes.ensure(qcodes.size()));
+    CK(ctx->d_qlen.ensure((size_t)n * 4));
+    CK(cudaMemcpyAsync(ctx->d_qcodes.p, qcodes.data(), qcodes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_qlen.p, qlen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    for (int c = 0; c < NCLASS; c++) {
+        if (ctx->class_seqs[c].empty()) continue;
+        CK(ctx->d_class_seqs[c].ensure(ctx->class_seqs[c].size() * 4));
+        CK(cudaMemcpyAsync(ctx->d_class_seqs[c].p, ctx->class_seqs[c].data(), ctx->class_seqs[c].size() * 4,
+                           cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LSW_OK;
+}
+
+int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_t* offs) {
+    if (!ctx || n < 0 || !offs || (n > 0 && !ascii && offs[n] > offs[0])) return ctx ? fail(ctx, LSW_E_ARG, "lsw_upload_reads: bad argument") : LSW_E_ARG;
+    if (n >= (1ll << 26)) return fail(ctx, LSW_E_ARG, "at most 2^26 - 1 reads per batch");
+    CK(cudaSetDevice(ctx->device));
+    ctx->h_roff.assign((size_t)n + 1, 0);
+    ctx->h_rlen.assign((size_t)n, 0);
+    int64_t d = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t len = offs[i + 1] - offs[i];
+        if (len < 0 || len >= (1ll << 27)) return fail(ctx, LSW_E_ARG, "read length must be in [0, 2^27)");
+        ctx->h_roff[i] = d;
+        ctx->h_rlen[i] = (int32_t)len;
+        d += (len + 15) & ~15ll;
+    }
+    ctx->h_roff[n] = d;
+    ctx->n_reads = n;
+    ctx->total_bases = n ? offs[n] - offs[0] : 0;
+    ctx->codes_bytes = d + 256;             // K1 reads whole 64-byte blocks past a slice end
+    const int64_t in_bytes = ctx->total_bases;
+    CK(ctx->d_ascii.ensure((size_t)std::max<int64_t>(in_bytes, 1)));
+    CK(ctx->d_offs_in.ensure((size_t)(n + 1) * 8));
+    CK(ctx->d_roff.ensure((size_t)(n + 1) * 8));
+    CK(ctx->d_rlen.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CK(ctx->d_codes.ensure((size_t)ctx->codes_bytes));
+    if (in_bytes) CK(cudaMemcpyAsync(ctx->d_ascii.p, ascii + offs[0], (size_t)in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int64_t> rel((size_t)n + 1);
+    for (int64_t i = 0; i <= n; i++) rel[i] = offs[i] - offs[0];
+    CK(cudaMemcpyAsync(ctx->d_offs_in.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_roff.p, ctx->h_roff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) CK(cudaMemcpyAsync(ctx->d_rlen.p, ctx->h_rlen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_codes.as<uint8_t>() + d, CODE_OTHER, 256, ctx->stream));
+    if (n) {
+        const int blocks = grid_for(n * 32, 256, ctx->num_sms * 16);
+        k_encode_reads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ascii.as<uint8_t>(), ctx->d_offs_in.as<int64_t>(),
+                                                        ctx->d_roff.as<int64_t>(), ctx->d_codes.as<uint8_t>(), n);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));      // `rel` and the caller's buffers may go away
+    return LSW_OK;
+}
+
+int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counters) {
+    if (!ctx) return LSW_E_ARG;
+    if (!(thr > 0.0)) return fail(ctx, LSW_E_ARG, "identity_threshold must be > 0 (the reference recurses forever otherwise)");
+    if (ctx->nseq <= 0) return fail(ctx, LSW_E_STATE, "lsw_set_queries has not been called");
+    CK(cudaSetDevice(ctx->device));
+    lsw_counters cnt;
+    memset(&cnt, 0, sizeof cnt);
+    ctx->timed.clear(); ctx->ev_used = 0;
+    ctx->n_hits = 0;
+    if (n_hits) *n_hits = 0;
+    const int64_t n0 = ctx->n_reads * ctx->nseq;
+    if (n0 >= (1ll << 30)) return fail(ctx, LSW_E_ARG, "reads x sequences must stay below 2^30 tasks per batch");
+    if (n0 == 0) { if (counters) *counters = cnt; return LSW_OK; }
+
+    std::vector<uint8_t> tab;
+    build_cand_ok(ctx->nseq, ctx->qlen.data(), ctx->match, ctx->mismatch, ctx->g, thr, false, tab);
+    CK(ctx->d_cand_ok.ensure(tab.size()));
+    CK(cudaMemcpyAsync(ctx->d_cand_ok.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+
+    int64_t hit_cap = ctx->hit_cap_user > 0 ? ctx->hit_cap_user : ctx->total_bases / 8 + 4096;
+    CK(ctx->d_hits.ensure((size_t)hit_cap * sizeof(lsw_hit)));
+    CK(ctx->d_nhits.ensure(8));
+    CK(ctx->d_counters.ensure(32));
+    CK(ctx->d_err.ensure(4));
+    CK(cudaMemsetAsync(ctx->d_nhits.p, 0, 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 32, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_err.p, 0, 4, ctx->stream));
+    CK(ctx->d_seg[0].ensure((size_t)(ctx->nseq + 1) * 8));
+    CK(ctx->d_seg[1].ensure((size_t)(ctx->nseq + 1) * 8));
+
+    Timed tt; tt.kind = 3; tt.e0 = next_event(ctx); tt.e1 = next_event(ctx);
+    if (tt.e0) cudaEventRecord(tt.e0, ctx->stream);
+    std::vector<int64_t> h_seg((size_t)ctx->nseq + 1);
+    for (int s = 0; s <= ctx->nseq; s++) h_seg[s] = (int64_t)s * ctx->n_reads;
+    CK(cudaMemcpyAsync(ctx->d_seg[0].p, h_seg.data(), h_seg.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int cur = 0;
+    CK(ctx->tb[0].ensure((size_t)n0, false));
+    {
+        Span sp(ctx, 2);
+        k_init_tasks<<<grid_for(n0, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+            ctx->tb[0].view(), ctx->d_rlen.as<int32_t>(), ctx->n_reads, ctx->nseq);
+        CK(cudaGetLastError());
+        cnt.other_launches++;
+    }
+
+    int64_t n = n0;
+    int round = 0;
+    int rc = LSW_OK;
+    unsigned long long h_nhits = 0;
+    while (n > 0) {
+        const int64_t n2 = 2 * n;
+        rc = ctx->child.ensure((size_t)n2, false) == cudaSuccess ? LSW_OK : LSW_E_CUDA;
+        if (rc) { ctx->err = "out of device memory (child tasks)"; break; }
+        CK(ctx->d_child_flag.ensure((size_t)n2 + 1));
+        CK(ctx->d_pos.ensure((size_t)(n2 + 1) * 4));
+        CK(cudaMemsetAsync(ctx->d_child_flag.p, 0, (size_t)n2 + 1, ctx->stream));
+
+        TraceParams T;
+        fill_trace_params(ctx, T, ctx->tb[cur]);
+        T.mode = 0; T.thr = thr; T.round = round;
+        T.hits = ctx->d_hits.p; T.hits_cap = hit_cap; T.nhits = ctx->d_nhits.as<unsigned long long>();
+        T.child_flag = ctx->d_child_flag.as<uint8_t>();
+        T.child = ctx->child.view();
+        rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt);
+        if (rc) break;
+
+        {
+            Span sp(ctx, 2);
+            auto it = thrust::make_transform_iterator((const uint8_t*)ctx->d_child_flag.as<uint8_t>(), FlagToInt());
+            size_t tmp = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, ctx->d_pos.as<int32_t>(), (int)(n2 + 1), ctx->stream));
+            CK(ctx->d_cubtemp.ensure(tmp));
+            CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtemp.p, tmp, it, ctx->d_pos.as<int32_t>(), (int)(n2 + 1), ctx->stream));
+            cnt.other_launches += 2;
+        }
+        // total children (pos[n2]) decides whether the preallocated next list is large enough
+        int32_t total_next = 0;
+        CK(cudaMemcpyAsync(&total_next, ctx->d_pos.as<int32_t>() + n2, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(ctx->tb[cur ^ 1].ensure((size_t)std::max<int32_t>(total_next, 1), false));
+        {
+            Span sp(ctx, 2);
+            k_scatter_children<<<grid_for(n2, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+                ctx->child.view(), ctx->d_child_flag.as<uint8_t>(), ctx->d_pos.as<int32_t>(), n2,
+                ctx->tb[cur ^ 1].view(), ctx->d_seg[cur].as<int64_t>(), ctx->d_seg[cur ^ 1].as<int64_t>(), ctx->nseq);
+            CK(cudaGetLastError());
+            cnt.other_launches++;
+        }
+        CK(cudaMemcpyAsync(h_seg.data(), ctx->d_seg[cur ^ 1].p, h_seg.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&h_nhits, ctx->d_nhits.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (round == 0) { cnt.top_tasks = n; }
+        cur ^= 1;
+        n = total_next;
+        round++;
+        if (round > 30000) { rc = fail(ctx, LSW_E_INTERNAL, "recursion did not terminate"); break; }
+    }
+    if (rc) return rc;
+    cnt.rounds = round;
+
+    // work counters and the internal-invariant flag
+    unsigned long long h_cnt[4] = {0, 0, 0, 0};
+    int32_t h_err = 0;
+    CK(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&h_err, ctx->d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cnt.tasks = (int64_t)h_cnt[0]; cnt.cells = (int64_t)h_cnt[1]; cnt.steps = (int64_t)h_cnt[2];
+    cnt.top_cells = 0;
+    {
+        int64_t sumq = 0;
+        for (int s = 0; s < ctx->nseq; s++) sumq += ctx->qlen[s];
+        cnt.top_cells = sumq * ctx->total_bases;
+    }
+    cnt.hits = (int64_t)h_nhits;
+    if (h_err) return fail(ctx, LSW_E_INTERNAL, "traceback window bound violated");
+    if ((int64_t)h_nhits > hit_cap) {
+        ctx->n_hits = 0;
+        if (n_hits) *n_hits = (int64_t)h_nhits;
+        if (counters) *counters = cnt;
+        return fail(ctx, LSW_E_OVERFLOW, "hit buffer too small; call lsw_set_hit_capacity(*n_hits) and retry");
+    }
+
+    // order hits by (read, start, query)
+    const int64_t nh = (int64_t)h_nhits;
+    if (nh > 0) {
+        Span sp(ctx, 2);
+        CK(ctx->d_keys[0].ensure((size_t)nh * 8)); CK(ctx->d_keys[1].ensure((size_t)nh * 8));
+        CK(ctx->d_vals[0].ensure((size_t)nh * 4)); CK(ctx->d_vals[1].ensure((size_t)nh * 4));
+        CK(ctx->d_hits_sorted.ensure((size_t)nh * sizeof(lsw_hit)));
+        k_hit_keys<<<grid_for(nh, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+            ctx->d_hits.as<lsw_hit>(), nh, ctx->d_keys[0].as<unsigned long long>(), ctx->d_vals[0].as<uint32_t>());
+        CK(cudaGetLastError());
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_keys[0].as<unsigned long long>(), ctx->d_keys[1].as<unsigned long long>(),
+                                           ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>(), (int)nh, 0, 61, ctx->stream));
+        CK(ctx->d_cubtemp.ensure(tmp));
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtemp.p, tmp, ctx->d_keys[0].as<unsigned long long>(), ctx->d_keys[1].as<unsigned long long>(),
+                                           ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>(), (int)nh, 0, 61, ctx->stream));
+        k_gather_hits<<<grid_for(nh, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+            ctx->d_hits.as<lsw_hit>(), ctx->d_vals[1].as<uint32_t>(), nh, ctx->d_hits_sorted.as<lsw_hit>());
+        CK(cudaGetLastError());
+        cnt.other_launches += 3;
+    }
+    if (tt.e1) { cudaEventRecord(tt.e1, ctx->stream); ctx->timed.push_back(tt); }
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_times(ctx, &cnt);
+    ctx->n_hits = nh;
+    if (n_hits) *n_hits = nh;
+    if (counters) *counters = cnt;
+    return LSW_OK;
+}
+
+int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out) {
+    if (!ctx) return LSW_E_ARG;
+    if (n_out) *n_out = ctx->n_hits;
+    if (ctx->n_hits > cap) return fail(ctx, LSW_E_OVERFLOW, "lsw_fetch_hits: caller buffer too small");
+    if (ctx->n_hits == 0) return LSW_OK;
+    if (!out) return fail(ctx, LSW_E_ARG, "lsw_fetch_hits: out is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->d_hits_sorted.p, (size_t)ctx->n_hits * sizeof(lsw_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LSW_OK;
+}
+
+int lsw_align_tasks(lsw_ctx* ctx, int64_t n, const lsw_task* tasks, lsw_result* out,
+                    uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used) {
+    if (!ctx) return LSW_E_ARG;
+    if (n < 0 || (n > 0 && (!tasks || !out))) return fail(ctx, LSW_E_ARG, "lsw_align_tasks: bad argument");
+    if (ctx->nseq <= 0) return fail(ctx, LSW_E_STATE, "lsw_set_queries has not been called");
+    if (n >= (1ll << 30)) return fail(ctx, LSW_E_ARG, "at most 2^30 - 1 tasks per call");
+    if (cigar_used) *cigar_used = 0;
+    if (n == 0) return LSW_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->timed.clear(); ctx->ev_used = 0;
+
+    // group by sequence (K1 serves one sequence per warp): counting sort on the host
+    std::vector<int64_t> h_seg((size_t)ctx->nseq + 1, 0);
+    for (int64_t i = 0; i < n; i++) {
+        const lsw_task& t = tasks[i];
+        if (t.query < 0 || t.query >= ctx->nseq || t.read < 0 || t.read >= ctx->n_reads || t.start < 0 ||
+            t.end < t.start || t.end > ctx->h_rlen[t.read])
+            return fail(ctx, LSW_E_ARG, "lsw_align_tasks: task out of range");
+        h_seg[t.query + 1]++;
+    }
+    for (int s = 0; s < ctx->nseq; s++) h_seg[s + 1] += h_seg[s];
+    std::vector<int32_t> hr(n), ha(n), hb(n), ho(n);
+    std::vector<int16_t> hs(n);
+    {
+        std::vector<int64_t> fill(h_seg.begin(), h_seg.end() - 1);
+        for (int64_t i = 0; i < n; i++) {
+            const lsw_task& t = tasks[i];
+            const int64_t d = fill[t.query]++;
+            hr[d] = t.read; ha[d] = t.start; hb[d] = t.end; hs[d] = (int16_t)t.query; ho[d] = (int32_t)i;
+        }
+    }
+    TaskBuf& cur = ctx->tb[0];
+    CK(cur.ensure((size_t)n, true));
+    CK(cudaMemcpyAsync(cur.read.p, hr.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(cur.a.p, ha.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(cur.b.p, hb.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(cur.seq.p, hs.data(), (size_t)n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(cur.orig.p, ho.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_seg[0].ensure(h_seg.size() * 8));
+    CK(cudaMemcpyAsync(ctx->d_seg[0].p, h_seg.data(), h_seg.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+    std::vector<uint8_t> tab;
+    build_cand_ok(ctx->nseq, ctx->qlen.data(), ctx->match, ctx->mismatch, ctx->g, 0.0, true, tab);          // every task gets a traceback
+    CK(ctx->d_cand_ok.ensure(tab.size()));
+    CK(cudaMemcpyAsync(ctx->d_cand_ok.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_counters.ensure(32)); CK(ctx->d_err.ensure(4)); CK(ctx->d_ncigar.ensure(8));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 32, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_err.p, 0, 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ncigar.p, 0, 8, ctx->stream));
+    CK(ctx->d_results.ensure((size_t)n * sizeof(lsw_result)));
+    const bool want_cigar = cigar_buf != nullptr && cigar_cap > 0;
+    if (want_cigar) CK(ctx->d_cigar.ensure((size_t)cigar_cap * 4));
+
+    TraceParams T;
+    fill_trace_params(ctx, T, cur);
+    T.mode = 1;
+    T.results = ctx->d_results.p;
+    T.cigar = want_cigar ? ctx->d_cigar.as<uint32_t>() : nullptr;
+    T.cigar_cap = want_cigar ? cigar_cap : 0;
+    T.ncigar = ctx->d_ncigar.as<unsigned long long>();
+    int rc = run_round(ctx, cur, 0, h_seg, n, T, nullptr);
+    if (rc) return rc;
+
+    unsigned long long h_ncig = 0;
+    int32_t h_err = 0;
+    CK(cudaMemcpyAsync(out, ctx->d_results.p, (size_t)n * sizeof(lsw_result), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&h_ncig, ctx->d_ncigar.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&h_err, ctx->d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->timed.clear(); ctx->ev_used = 0;
+    if (h_err) return fail(ctx, LSW_E_INTERNAL, "traceback window bound violated");
+    if (cigar_used) *cigar_used = (int64_t)h_ncig;
+    if (want_cigar) {
+        if ((int64_t)h_ncig > cigar_cap) return fail(ctx, LSW_E_OVERFLOW, "cigar buffer too small; *cigar_used runs are needed");
+        if (h_ncig) {
+            CK(cudaMemcpyAsync(cigar_buf, ctx->d_cigar.p, (size_t)h_ncig * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return LSW_OK;
+}
+
+int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per_s, float* ms_out) {
+    if (!ctx || !lane_ops_per_s || iters <= 0) return LSW_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->num_sms * 8;
+    DevBuf out, in;
+    CK(out.ensure((size_t)threads * blocks * 4));
+    CK(in.ensure(64));
+    const uint32_t h_in[8] = {0x00030002u, 0x00010001u, 0x01000100u, 0x00100020u, 0x00000000u, 0, 0, 0};
+    CK(cudaMemcpyAsync(in.p, h_in, sizeof h_in, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(e0, ctx->stream));
+#define LSW_IP(M) case M: k_intpeak<M><<<blocks, threads, 0, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters, 1u); break;
+        switch (mode) {
+            LSW_IP(0) LSW_IP(1) LSW_IP(2) LSW_IP(3) LSW_IP(4) LSW_IP(5) LSW_IP(6) LSW_IP(7) LSW_IP(8)
+            default: cudaEventDestroy(e0); cudaEventDestroy(e1); out.release(); in.release();
+                     return fail(ctx, LSW_E_ARG, "lsw_measure_int_peak: unknown mode");
+        }
+#undef LSW_IP
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    out.release(); in.release();
+    const double ops = (double)threads * blocks * (double)iters * intpeak_ops_per_iter(mode);
+    *lane_ops_per_s = ops / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return LSW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// lsw_common.cuh -- shared definitions for the B200 Smith-Waterman seeding kernels.
+//
+// Everything here is written so that the per-lane logic can ALSO be compiled for the host
+// (nvcc host pass) and driven one lane at a time by csrc/lsw_emu.cu.  That emulation is test
+// infrastructure (tests/test_emu.py checks the kernel logic against the oracle without a GPU);
+// the product library (lsw.cu) never runs it.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define LSW_HD __host__ __device__ __forceinline__
+
+namespace lsw {
+
+constexpr int SC_SHIFT   = 8;          // DP values are scaled by 256 inside an s16 half ...
+constexpr int SC         = 1 << SC_SHIFT;   // ... so the low byte can carry the step index of the arg-max key
+constexpr int BLOCK_STEPS = 64;        // columns a lane advances between two task-switch points
+constexpr int MAXQ       = 63;         // LSW_MAX_QUERY_LEN
+constexpr int QSTRIDE    = 64;         // bytes per query in the device query-code table
+constexpr int CODE_OTHER = 4;          // read code of any byte that is not A/C/G/T (never matches)
+constexpr int NCODE      = 5;
+constexpr int NIDX       = NCODE * NCODE;   // (code of low-half task, code of high-half task)
+
+// ---- packed s16x2 DPX primitives (VIADDMNMX.S16x2 / VIMNMX3.S16x2 on sm_100a) ------------
+LSW_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) {       // max(a + b, c) per s16 half
+    return __viaddmax_s16x2(a, b, c);
+}
+LSW_HD uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) {        // max(a, b, c) per s16 half
+    return __vimax3_s16x2(a, b, c);
+}
+LSW_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t s = (sel >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)((v >> (8 * (s & 7))) & 0xFF);
+        if (s & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+#endif
+}
+
+// swalign upper-cases both strings and compares raw characters: A/C/G/T in
+// either case get codes 0..3, every other byte gets CODE_OTHER and never matches an ACGT query.
+LSW_HD uint8_t encode_base(uint8_t ch) {
+    if (ch >= 'a' && ch <= 'z') ch = (uint8_t)(ch - 32);
+    return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : (uint8_t)CODE_OTHER;
+}
+
+LSW_HD unsigned long long atomic_add_ull(unsigned long long* p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    const unsigned long long o = *p; *p += v; return o;    // host emulation is single-threaded
+#endif
+}
+LSW_HD void atomicExch_or_store(int32_t* p, int32_t v) { *p = v; }   // benign race: any writer stores the same flag
+
+// ---- task / result records shared by host and device -------------------------------------
+struct TaskArrays {           // struct-of-arrays task list of one recursion round
+    int32_t* read;            // read index in the uploaded batch
+    int32_t* a;               // slice start on the read
+    int32_t* b;               // slice end (exclusive)
+    int16_t* seq;             // schema sequence index
+    int32_t* orig;            // align_tasks(): caller's task index (results are written there); else unused
+};
+
+struct ScoreParams {
+    const uint8_t*  codes;    // read codes, one byte per base, every read 16-byte aligned
+    const int64_t*  roff;     // [n_reads + 1] byte offset of each read in codes
+    TaskArrays      t;
+    const int64_t*  seg;      // [n_seq + 1] tasks of sequence s are [seg[s], seg[s+1])
+    unsigned long long* head; // [n_seq] next unclaimed task of each sequence (relative to seg[s])
+    int2*           res;      // [n_tasks] x = score | (max_row << 16), y = max_col (1-based DP coords)
+    const uint8_t*  qcodes;   // [n_seq][QSTRIDE] 0..3
+    const int32_t*  qlen;     // [n_seq]
+    const int32_t*  class_seqs; // sequences served by this launch (same register-row class)
+    int             n_class_seqs;
+    const uint8_t*  cand_ok;  // [n_seq][128] 1 if a task with that score can still pass the hit test
+    uint32_t*       cand;     // out: tasks that need a traceback
+    unsigned long long* ncand;
+    unsigned long long* counters;   // [0] += tasks, [1] += cells, [2] += lane steps
+    int32_t s_match;          // SC * (match + |gap|)
+    int32_t s_mis;            // SC * (mismatch + |gap|)
+    int32_t g;                // |gap|
+};
+
+struct TraceParams {
+    const uint8_t*  codes;
+    const int64_t*  roff;
+    TaskArrays      t;
+    const int2*     res;
+    const uint8_t*  qcodes;
+    const int32_t*  qlen;
+    const uint32_t* cand;
+    const unsigned long long* ncand;
+    uint32_t*       scratch;      // direction bits, [window col][word][thread]
+    int64_t         scratch_stride;   // threads in the launch
+    int32_t match, mismatch, g;
+    int32_t mode;             // 0 = find_all (hit test, children), 1 = align_tasks (result records, CIGAR)
+    double  thr;
+    int32_t round;
+    // mode 0 outputs
+    void*   hits;             // lsw_hit[]
+    int64_t hits_cap;
+    unsigned long long* nhits;
+    uint8_t*  child_flag;     // [2 * n_tasks]
+    TaskArrays child;         // [2 * n_tasks]
+    // mode 1 outputs
+    void*   results;          // lsw_result[] indexed by t.orig
+    uint32_t* cigar;
+    int64_t cigar_cap;
+    unsigned long long* ncigar;
+    int32_t* errflag;
+};
+
+}  // namespace lsw

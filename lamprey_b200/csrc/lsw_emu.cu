@@ -1,0 +1,246 @@
+// lsw_emu.cu -- TEST INFRASTRUCTURE: runs the per-lane logic of the CUDA kernels on the host.
+//
+// The kernels' lane code (ScoreLane<NR> in lsw_score.cuh, trace_task<NR> in lsw_trace.cuh) is
+// __host__ __device__.  This file drives it one lane at a time with host loops in place of the
+// kernel launches, the scan and the scatter, so tests/test_emu.py can check the exact
+// arithmetic (packed DPX recurrence, arg-max fold, task switching, windowed traceback, hit test,
+// recursion rounds) against the oracle in the build container, which has no GPU.
+// It is built into its own library (liblsw_emu.so) and is never loaded by the product path:
+// lamprey_b200 only opens liblsw.so and fails loudly without a CUDA device.
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/lsw.h"
+#include "lsw_common.cuh"
+#include "lsw_score.cuh"
+#include "lsw_trace.cuh"
+#include "lsw_host.hpp"
+
+using namespace lsw;
+
+namespace {
+
+struct Emu {
+    int match, mismatch, g;
+    int nseq;
+    std::vector<int32_t> qlen, class_of;
+    std::vector<uint8_t> qcodes;
+    std::vector<uint8_t> codes;
+    std::vector<int64_t> roff;
+    std::vector<int32_t> rlen;
+    // task list
+    std::vector<int32_t> t_read, t_a, t_b, t_orig;
+    std::vector<int16_t> t_seq;
+    std::vector<int64_t> seg;
+    std::vector<int2> res;
+    std::vector<uint8_t> cand_ok;
+    unsigned long long counters[4];
+};
+
+bool setup(Emu& E, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
+           const int32_t* qoffs, int match, int mismatch, int gap) {
+    if (match <= 0 || mismatch >= 0 || gap >= 0) return false;
+    E.match = match; E.mismatch = mismatch; E.g = -gap; E.nseq = nseq;
+    E.qlen.resize(nseq); E.class_of.resize(nseq);
+    E.qcodes.assign((size_t)nseq * QSTRIDE, 0xFF);
+    for (int s = 0; s < nseq; s++) {
+        const int len = qoffs[s + 1] - qoffs[s];
+        if (len < 1 || len > LSW_MAX_QUERY_LEN || match * len + E.g > 127) return false;
+        E.qlen[s] = len;
+        for (int j = 0; j < len; j++) {
+            const uint8_t c = encode_base(qconcat[qoffs[s] + j]);
+            if (c >= CODE_OTHER) return false;
+            E.qcodes[(size_t)s * QSTRIDE + j] = c;
+        }
+        int c = 0;
+        while (CLASS_NR[c] < len) c++;
+        E.class_of[s] = c;
+    }
+    E.roff.assign((size_t)n_reads + 1, 0);
+    E.rlen.assign((size_t)n_reads, 0);
+    int64_t d = 0;
+    for (int64_t i = 0; i < n_reads; i++) {
+        const int64_t len = offs[i + 1] - offs[i];
+        E.roff[i] = d; E.rlen[i] = (int32_t)len;
+        d += (len + 15) & ~15ll;
+    }
+    E.roff[n_reads] = d;
+    E.codes.assign((size_t)d + 256, CODE_OTHER);
+    for (int64_t i = 0; i < n_reads; i++)
+        for (int64_t j = 0; j < E.rlen[i]; j++) E.codes[E.roff[i] + j] = encode_base(ascii[offs[i] + j]);
+    memset(E.counters, 0, sizeof E.counters);
+    return true;
+}
+
+template <int NR>
+void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& cand) {
+    using Lane = ScoreLane<NR>;
+    static U4 keep_ge[17], keep_lt[17];
+    for (int n = 0; n <= 16; n++) make_keep_masks(keep_ge, keep_lt, n);
+    std::vector<U4> prof((size_t)NIDX * Lane::PROF_STRIDE);
+    const int Q = E.qlen[q];
+    Lane::build_profile(P, q, Q, reinterpret_cast<uint32_t*>(prof.data()), 0, 1);
+    Lane L;
+    L.n_tasks = L.n_cells = L.n_steps = 0;
+    L.init();
+    const long long cnt = E.seg[q + 1] - E.seg[q], base = E.seg[q];
+    long long head = 0;
+    bool exhausted = false;
+    for (;;) {
+        for (int h = 0; h < 2; h++) {
+            if (L.tid[h] >= 0 && L.rem[h] == 0) L.finish(P, h, q, Q, [&](int t) { cand.push_back((uint32_t)t); });
+            if (L.tid[h] < 0 && !exhausted) {
+                if (head < cnt) L.start(P, h, (int)(base + head++), Q);
+                else exhausted = true;
+            }
+        }
+        if (!(L.tid[0] >= 0 || L.tid[1] >= 0)) break;
+        L.run_block(P, prof.data(), keep_ge, keep_lt, Q);
+    }
+    E.counters[0] += L.n_tasks; E.counters[1] += L.n_cells; E.counters[2] += L.n_steps;
+}
+
+void emu_score_class(Emu& E, const ScoreParams& P, int c, int q, std::vector<uint32_t>& cand) {
+    switch (CLASS_NR[c]) {
+        case 16: emu_score_seq<16>(E, P, q, cand); break;
+        case 24: emu_score_seq<24>(E, P, q, cand); break;
+        case 32: emu_score_seq<32>(E, P, q, cand); break;
+        case 48: emu_score_seq<48>(E, P, q, cand); break;
+        default: emu_score_seq<64>(E, P, q, cand); break;
+    }
+}
+
+void emu_trace_class(const TraceParams& T, int c, int t) {
+    switch (CLASS_NR2[c]) {
+        case 16: trace_task<16>(T, t, 0); break;
+        case 32: trace_task<32>(T, t, 0); break;
+        case 48: trace_task<48>(T, t, 0); break;
+        default: trace_task<64>(T, t, 0); break;
+    }
+}
+
+TaskArrays view(Emu& E) {
+    TaskArrays t;
+    t.read = E.t_read.data(); t.a = E.t_a.data(); t.b = E.t_b.data(); t.seq = E.t_seq.data(); t.orig = E.t_orig.data();
+    return t;
+}
+
+// K1 + K2 over the current task list.  Tbase carries the mode-specific outputs.
+void emu_round(Emu& E, TraceParams T) {
+    const int64_t n = (int64_t)E.t_read.size();
+    E.res.assign((size_t)n, make_int2(0, 0));
+    ScoreParams P;
+    memset(&P, 0, sizeof P);
+    P.codes = E.codes.data(); P.roff = E.roff.data(); P.t = view(E); P.seg = E.seg.data();
+    P.res = E.res.data(); P.qcodes = E.qcodes.data(); P.qlen = E.qlen.data();
+    P.cand_ok = E.cand_ok.data();
+    P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g;
+    int qmax = 1;
+    for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
+    std::vector<uint32_t> scratch((size_t)trace_window(qmax, E.match, E.g) * 4 + 16);
+    T.codes = E.codes.data(); T.roff = E.roff.data(); T.t = view(E); T.res = E.res.data();
+    T.qcodes = E.qcodes.data(); T.qlen = E.qlen.data();
+    T.match = E.match; T.mismatch = E.mismatch; T.g = E.g;
+    T.scratch = scratch.data(); T.scratch_stride = 1;
+    for (int s = 0; s < E.nseq; s++) {
+        if (E.seg[s + 1] == E.seg[s]) continue;
+        std::vector<uint32_t> cand;
+        emu_score_class(E, P, E.class_of[s], s, cand);
+        for (uint32_t t : cand) emu_trace_class(T, E.class_of[s], (int)t);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
+                     const int32_t* qoffs, int match, int mismatch, int gap, double thr, lsw_hit* out, int64_t cap,
+                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds */) {
+    Emu E;
+    if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, match, mismatch, gap)) return LSW_E_UNSUPPORTED;
+    build_cand_ok(nseq, E.qlen.data(), match, mismatch, E.g, thr, false, E.cand_ok);
+    const int64_t n0 = n_reads * nseq;
+    E.t_read.resize(n0); E.t_a.resize(n0); E.t_b.resize(n0); E.t_seq.resize(n0);
+    E.seg.resize(nseq + 1);
+    for (int s = 0; s <= nseq; s++) E.seg[s] = (int64_t)s * n_reads;
+    for (int64_t i = 0; i < n0; i++) {
+        const int s = (int)(i / n_reads); const int64_t r = i - (int64_t)s * n_reads;
+        E.t_read[i] = (int32_t)r; E.t_a[i] = 0; E.t_b[i] = E.rlen[r]; E.t_seq[i] = (int16_t)s;
+    }
+    unsigned long long nhits = 0;
+    int32_t errflag = 0;
+    int round = 0;
+    while (!E.t_read.empty()) {
+        const int64_t n = (int64_t)E.t_read.size(), n2 = 2 * n;
+        std::vector<int32_t> c_read(n2), c_a(n2), c_b(n2);
+        std::vector<int16_t> c_seq(n2);
+        std::vector<uint8_t> flag(n2 + 1, 0);
+        TraceParams T;
+        memset(&T, 0, sizeof T);
+        T.mode = 0; T.thr = thr; T.round = round;
+        T.hits = out; T.hits_cap = cap; T.nhits = &nhits;
+        T.child_flag = flag.data();
+        T.child.read = c_read.data(); T.child.a = c_a.data(); T.child.b = c_b.data(); T.child.seq = c_seq.data();
+        T.errflag = &errflag;
+        emu_round(E, T);
+        // scan + scatter
+        std::vector<int32_t> nr, na, nb; std::vector<int16_t> ns;
+        std::vector<int64_t> nseg(nseq + 1, 0);
+        std::vector<int32_t> pos(n2 + 1, 0);
+        for (int64_t j = 0; j < n2; j++) pos[j + 1] = pos[j] + flag[j];
+        for (int s = 0; s <= nseq; s++) nseg[s] = pos[std::min<int64_t>(2 * E.seg[s], n2)];
+        for (int64_t j = 0; j < n2; j++)
+            if (flag[j]) { nr.push_back(c_read[j]); na.push_back(c_a[j]); nb.push_back(c_b[j]); ns.push_back(c_seq[j]); }
+        E.t_read.swap(nr); E.t_a.swap(na); E.t_b.swap(nb); E.t_seq.swap(ns); E.seg.swap(nseg);
+        round++;
+    }
+    if (errflag) return LSW_E_INTERNAL;
+    if (n_out) *n_out = (int64_t)nhits;
+    if (counters) { counters[0] = E.counters[0]; counters[1] = E.counters[1]; counters[2] = E.counters[2]; counters[3] = round; }
+    if ((int64_t)nhits > cap) return LSW_E_OVERFLOW;
+    // (read, start, query) order
+    std::sort(out, out + nhits, [](const lsw_hit& x, const lsw_hit& y) {
+        if (x.read != y.read) return x.read < y.read;
+        if (x.start != y.start) return x.start < y.start;
+        return x.query < y.query;
+    });
+    return LSW_OK;
+}
+
+int lsw_emu_align_tasks(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
+                        const int32_t* qoffs, int match, int mismatch, int gap, int64_t n, const lsw_task* tasks,
+                        lsw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used) {
+    Emu E;
+    if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, match, mismatch, gap)) return LSW_E_UNSUPPORTED;
+    build_cand_ok(nseq, E.qlen.data(), match, mismatch, E.g, 0.0, true, E.cand_ok);
+    E.seg.assign(nseq + 1, 0);
+    for (int64_t i = 0; i < n; i++) {
+        const lsw_task& t = tasks[i];
+        if (t.query < 0 || t.query >= nseq || t.read < 0 || t.read >= n_reads || t.start < 0 || t.end < t.start ||
+            t.end > E.rlen[t.read]) return LSW_E_ARG;
+        E.seg[t.query + 1]++;
+    }
+    for (int s = 0; s < nseq; s++) E.seg[s + 1] += E.seg[s];
+    E.t_read.resize(n); E.t_a.resize(n); E.t_b.resize(n); E.t_seq.resize(n); E.t_orig.resize(n);
+    std::vector<int64_t> fill(E.seg.begin(), E.seg.end() - 1);
+    for (int64_t i = 0; i < n; i++) {
+        const lsw_task& t = tasks[i];
+        const int64_t d = fill[t.query]++;
+        E.t_read[d] = t.read; E.t_a[d] = t.start; E.t_b[d] = t.end; E.t_seq[d] = (int16_t)t.query; E.t_orig[d] = (int32_t)i;
+    }
+    unsigned long long ncig = 0;
+    int32_t errflag = 0;
+    TraceParams T;
+    memset(&T, 0, sizeof T);
+    T.mode = 1; T.results = out; T.cigar = cigar_buf; T.cigar_cap = cigar_buf ? cigar_cap : 0; T.ncigar = &ncig;
+    T.errflag = &errflag;
+    if (n) emu_round(E, T);
+    if (errflag) return LSW_E_INTERNAL;
+    if (cigar_used) *cigar_used = (int64_t)ncig;
+    if (cigar_buf && (int64_t)ncig > cigar_cap) return LSW_E_OVERFLOW;
+    return LSW_OK;
+}
+
+}  // extern "C"

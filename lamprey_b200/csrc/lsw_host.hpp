@@ -1,0 +1,44 @@
+// lsw_host.hpp -- host-side pieces shared by the product library (lsw.cu) and the CPU emulation
+// of the kernels used by the tests (lsw_emu.cu).
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace lsw {
+
+constexpr int NCLASS = 5;
+static const int CLASS_NR[NCLASS] = {16, 24, 32, 48, 64};     // K1 register-row classes
+static const int CLASS_NR2[NCLASS] = {16, 32, 32, 48, 64};    // K2 rows (one op word per 16 rows)
+
+// cand_ok[s][score]: can a task of sequence s whose best local score is `score` still pass
+// findPrimerAlignments' test  identity >= thr and span >= len(primer) * thr  (lamprey.py:616-617)?
+// score = match*m + mismatch*mm + gap*(I+D) exactly (every cell on a traceback path satisfies
+// H == predecessor + step), identity = m / (m + mm + I + D), span <= m + mm + (I+D).  The table is a
+// NECESSARY condition evaluated with the same double arithmetic Python uses, so pruning is exact.
+inline void build_cand_ok(int nseq, const int32_t* qlen, int match, int mismatch, int g, double thr, bool all,
+                          std::vector<uint8_t>& tab) {
+    tab.assign((size_t)nseq * 128, 0);
+    for (int s = 0; s < nseq; s++) {
+        const int Q = qlen[s];
+        for (int score = 0; score < 128; score++) {
+            bool ok = false;
+            if (all) ok = true;
+            else if (score > 0) {
+                for (int m = 0; m <= Q && !ok; m++)
+                    for (int mm = 0; m + mm <= Q && !ok; mm++) {
+                        const int rest = match * m + mismatch * mm - score;   // = g * gaps
+                        if (rest < 0 || rest % g) continue;
+                        const int gaps = rest / g;
+                        const int x = mm + gaps, tot = m + x;
+                        if (tot <= 0) continue;
+                        const double identity = (double)m / (double)tot;
+                        if (identity >= thr && (double)(m + mm + gaps) >= (double)Q * thr) ok = true;
+                    }
+            }
+            tab[(size_t)s * 128 + score] = ok ? 1 : 0;
+        }
+    }
+}
+
+
+}  // namespace lsw

@@ -1,0 +1,312 @@
+// lsw_score.cuh -- K1: score + arg-max pass of swalign.LocalAlignment.align()
+//
+// Replaces the matrix fill and the `if val >= max_val` arg-max of the third-party align()
+// that /root/reference/lamprey.py:563 calls (semantics: SURVEY.md Appendix A.1 / A.3).
+// For LAMPrey's parameters gap_penalty == gap_extension_penalty, so the VALUE recurrence is
+// linear-gap Smith-Waterman,  H = max(0, D + s, L - g, U - g);  the (op, run) part of
+// swalign's cells only matters for the traceback (K2, lsw_trace.cuh).
+//
+// Layout of the computation (see DESIGN.md section "K1"):
+//  * one LANE owns two independent tasks at a time, one in each s16 half of every register
+//    (packed DPX: VIADDMNMX.S16x2 / VIMNMX3.S16x2).  All NR query rows of both tasks live in
+//    registers; the lane streams read columns.
+//  * all lanes of a WARP serve the same schema sequence, whose substitution profile
+//    (indexed by the pair of read codes of the two tasks) sits in shared memory.
+//  * values are scaled by 256 and biased by |gap| so that
+//        T     = max(Mold[r-1] + s'', Mold[r])              s'' = 256*(s + g)
+//        h     = max(T, Mnew[r-1], 256*g)                   h   = 256*(H + g)
+//        Mnew  = h - 256*g                                  (= 256*H, never borrows)
+//        K[r]  = max(K[r], h + step)                        arg-max key, step in the low byte
+//    i.e. 3 ALU-pipe DPX ops + 1 add per TWO cells.
+//  * every BLOCK_STEPS columns the lane folds K into its per-task best (value, row, column)
+//    with swalign's tie rule (last cell in row-major order wins: highest row, then highest
+//    column), retires finished tasks and claims new ones from the per-sequence queue.
+#pragma once
+#include "lsw_common.cuh"
+
+namespace lsw {
+
+struct U4 { uint32_t x, y, z, w; };
+
+template <int NR>
+struct ScoreLane {
+    static_assert(NR % 4 == 0 && NR <= 64, "rows are kept in registers, 4 per profile load");
+    static constexpr int PROF_STRIDE = NR / 4 + 1;      // uint4 per profile row (+1 pad: bank spread)
+
+    uint32_t M[NR];        // 256 * H of the previous column, two tasks packed
+    uint32_t K[NR];        // running max of (256*(H+g) + step) over the current block
+    int32_t  tid[2];       // task index, -1 = half idle
+    int64_t  pos[2];       // byte offset (16-aligned) in codes of step 0 of the next block
+    int32_t  begin[2];     // first live step of the next block (only the first block of a task is > 0)
+    int32_t  rem[2];       // live columns still to run
+    int32_t  cbase[2];     // DP column (1-based) of step 0 of the next block
+    uint32_t best[2];      // ((H+g) << 16) | (row << 8) | step of the best cell so far
+    int32_t  bestc[2];     // its DP column
+    int32_t  len[2];       // slice length
+    unsigned long long n_tasks, n_cells, n_steps;
+
+    LSW_HD void init() {
+#pragma unroll
+        for (int r = 0; r < NR; r++) { M[r] = 0; K[r] = 0; }
+        tid[0] = tid[1] = -1;
+        rem[0] = rem[1] = 0; begin[0] = begin[1] = 0;
+        pos[0] = pos[1] = 0; cbase[0] = cbase[1] = 0;
+        best[0] = best[1] = 0; bestc[0] = bestc[1] = 0; len[0] = len[1] = 0;
+    }
+
+    // Build the packed profile of sequence q for this warp: prof[idx][r/4] holds rows r..r+3 of
+    // (s''(code_lo, q[r]), s''(code_hi, q[r])).  `lane`/`nlanes` split the work.
+    static LSW_HD void build_profile(const ScoreParams& P, int q, int Q, uint32_t* prof32, int lane, int nlanes) {
+        const uint8_t* qc = P.qcodes + (size_t)q * QSTRIDE;
+        for (int e = lane; e < NIDX * NR; e += nlanes) {
+            const int idx = e / NR, r = e - idx * NR;
+            const int cl = idx / NCODE, ch = idx - cl * NCODE;
+            int lo = P.s_mis, hi = P.s_mis;
+            if (r < Q) {
+                const int qb = qc[r];
+                if (cl == qb) lo = P.s_match;      // CODE_OTHER (4) never equals a query code 0..3
+                if (ch == qb) hi = P.s_match;
+            }
+            prof32[idx * (PROF_STRIDE * 4) + r] = ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
+        }
+    }
+
+    // Start task `t` in half h.
+    LSW_HD void start(const ScoreParams& P, int h, int t, int Q) {
+        const int rd = P.t.read[t];
+        const int a = P.t.a[t], b = P.t.b[t];
+        const int64_t p0 = P.roff[rd] + a;
+        tid[h] = t;
+        len[h] = b - a;
+        rem[h] = b - a;
+        begin[h] = (int32_t)(p0 & 15);
+        pos[h] = p0 & ~(int64_t)15;
+        cbase[h] = 1 - begin[h];
+        best[h] = ((uint32_t)P.g << 16) | 0xFFFFu;     // nothing positive seen yet
+        bestc[h] = 0;
+        const uint32_t keep = h ? 0x0000FFFFu : 0xFFFF0000u;
+#pragma unroll
+        for (int r = 0; r < NR; r++) M[r] &= keep;     // zero boundary column for this half
+        n_tasks += 1;
+        n_cells += (unsigned long long)(b - a) * (unsigned long long)Q;
+    }
+
+    // Retire the task in half h: publish (score, max_row, max_col) and queue it for traceback.
+    template <class PushCand>
+    LSW_HD void finish(const ScoreParams& P, int h, int q, int Q, PushCand push) {
+        const int t = tid[h];
+        int score = (int)(best[h] >> 16) - P.g;
+        int row, col;
+        if (bestc[h] == 0) {            // no positive cell: swalign's `>=` leaves the last cell
+            score = 0;
+            row = len[h] > 0 ? Q : 0;
+            col = len[h] > 0 ? len[h] : 0;
+        } else {
+            row = (int)((best[h] >> 8) & 0xFF) + 1;
+            col = bestc[h];
+        }
+        P.res[t] = make_int2(score | (row << 16), col);
+        if (P.cand_ok[(size_t)q * 128 + score]) push(t);
+        tid[h] = -1;
+    }
+
+    // One DP column for both halves.  prow: profile row of this column's (code_lo, code_hi).
+    LSW_HD void column(const U4* prow, uint32_t tvec, uint32_t G2, uint32_t FLOOR2) {
+        uint32_t d = 0, u = 0;
+#pragma unroll
+        for (int r4 = 0; r4 < NR / 4; r4++) {
+            const U4 s = prow[r4];
+#define LSW_ROW(R, S)                                            \
+            {                                                    \
+                const uint32_t mold = M[R];                      \
+                const uint32_t T = addmax2(d, S, mold);          \
+                const uint32_t hh = max3_2(T, u, FLOOR2);        \
+                u = hh - G2;                                     \
+                M[R] = u;                                        \
+                K[R] = addmax2(hh, tvec, K[R]);                  \
+                d = mold;                                        \
+            }
+            LSW_ROW(r4 * 4 + 0, s.x)
+            LSW_ROW(r4 * 4 + 1, s.y)
+            LSW_ROW(r4 * 4 + 2, s.z)
+            LSW_ROW(r4 * 4 + 3, s.w)
+#undef LSW_ROW
+        }
+    }
+
+    // BLOCK_STEPS columns for both halves, then fold the block's arg-max into the task state.
+    // keep_ge[n]: bytes j >= n of a 16-byte chunk are live; keep_lt[n]: bytes j < n are live.
+    LSW_HD void run_block(const ScoreParams& P, const U4* prof, const U4* keep_ge, const U4* keep_lt, int Q) {
+        const uint32_t G2 = (uint32_t)(P.g * SC) * 0x00010001u;
+        const uint32_t FLOOR2 = G2;
+        int end[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            end[h] = 0;
+            if (tid[h] >= 0) { end[h] = begin[h] + rem[h]; if (end[h] > BLOCK_STEPS) end[h] = BLOCK_STEPS; }
+            else begin[h] = 0;
+        }
+#pragma unroll
+        for (int r = 0; r < NR; r++) K[r] = 0;
+
+        uint32_t tvec = 0;
+#pragma unroll 1
+        for (int k = 0; k < BLOCK_STEPS / 16; k++) {
+            U4 c[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                U4 v; v.x = v.y = v.z = v.w = 0;
+                if (tid[h] >= 0) v = *reinterpret_cast<const U4*>(P.codes + pos[h] + 16 * k);
+                int nl = begin[h] - 16 * k; nl = nl < 0 ? 0 : (nl > 16 ? 16 : nl);
+                int ne = end[h] - 16 * k;   ne = ne < 0 ? 0 : (ne > 16 ? 16 : ne);
+                const U4 kg = keep_ge[nl], kl = keep_lt[ne];
+                const uint32_t OTH = 0x01010101u * CODE_OTHER;
+                uint32_t kp;
+                kp = kg.x & kl.x; v.x = (v.x & kp) | (OTH & ~kp);
+                kp = kg.y & kl.y; v.y = (v.y & kp) | (OTH & ~kp);
+                kp = kg.z & kl.z; v.z = (v.z & kp) | (OTH & ~kp);
+                kp = kg.w & kl.w; v.w = (v.w & kp) | (OTH & ~kp);
+                c[h] = v;
+            }
+#pragma unroll 1
+            for (int w = 0; w < 4; w++) {
+                const uint32_t idx4 = c[0].x * NCODE + c[1].x;       // four (lo, hi) code pairs, bytes <= 24
+                c[0].x = c[0].y; c[0].y = c[0].z; c[0].z = c[0].w;
+                c[1].x = c[1].y; c[1].y = c[1].z; c[1].z = c[1].w;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t idx = (idx4 >> (8 * j)) & 0xFFu;
+                    column(prof + idx * PROF_STRIDE, tvec, G2, FLOOR2);
+                    tvec += 0x00010001u;
+                }
+            }
+        }
+
+        // fold: per half, lexicographic max of (H, row, step) over the rows of the query
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t bb = 0;
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                if (r < Q) {
+                    // bytes of K[r]: [step_lo, H_lo, step_hi, H_hi]  ->  [step, row, H, 0]
+                    const uint32_t key = prmt(K[r], (uint32_t)r, h ? 0x5342u : 0x5140u);
+                    bb = key > bb ? key : bb;
+                }
+            }
+            if (tid[h] >= 0) {
+                if ((bb >> 8) >= (best[h] >> 8)) {       // >= : a later block wins ties on (H, row)
+                    best[h] = bb;
+                    bestc[h] = cbase[h] + (int32_t)(bb & 0xFF);
+                }
+                rem[h] -= end[h] - begin[h];
+                begin[h] = 0;
+                pos[h] += BLOCK_STEPS;
+                cbase[h] += BLOCK_STEPS;
+            }
+        }
+        n_steps += BLOCK_STEPS;
+    }
+};
+
+// Live-byte masks of a 16-byte chunk, indexed by n in [0, 16].
+LSW_HD void make_keep_masks(U4* keep_ge, U4* keep_lt, int n) {
+    uint32_t ge[4], lt[4];
+    for (int w = 0; w < 4; w++) {
+        ge[w] = 0; lt[w] = 0;
+        for (int j = 0; j < 4; j++) {
+            const int byte = 4 * w + j;
+            if (byte >= n) ge[w] |= 0xFFu << (8 * j);
+            if (byte < n)  lt[w] |= 0xFFu << (8 * j);
+        }
+    }
+    keep_ge[n].x = ge[0]; keep_ge[n].y = ge[1]; keep_ge[n].z = ge[2]; keep_ge[n].w = ge[3];
+    keep_lt[n].x = lt[0]; keep_lt[n].y = lt[1]; keep_lt[n].z = lt[2]; keep_lt[n].w = lt[3];
+}
+
+#if defined(__CUDACC__)
+// ---- the kernel --------------------------------------------------------------------------
+// One launch serves every sequence of one register-row class.  Warps pick the sequence with
+// the most unclaimed tasks, build its profile in shared memory, and their lanes drain that
+// sequence's queue two tasks at a time until it is empty.
+constexpr int SCORE_WARPS = 4;
+
+template <int NR>
+__global__ void __launch_bounds__(SCORE_WARPS * 32)
+k_score(const ScoreParams P) {
+    using Lane = ScoreLane<NR>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    U4* keep_ge = reinterpret_cast<U4*>(smem_raw);
+    U4* keep_lt = keep_ge + 17;
+    U4* prof_all = keep_lt + 17;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    U4* prof = prof_all + (size_t)warp * NIDX * Lane::PROF_STRIDE;
+
+    if (threadIdx.x < 17) make_keep_masks(keep_ge, keep_lt, threadIdx.x);
+    __syncthreads();
+
+    Lane L;
+    L.n_tasks = L.n_cells = L.n_steps = 0;
+
+    for (;;) {
+        // choose the sequence of this class with the most unclaimed tasks
+        long long bestrem = 0; int bestq = -1;
+        for (int i = lane; i < P.n_class_seqs; i += 32) {
+            const int q = P.class_seqs[i];
+            const long long cnt = P.seg[q + 1] - P.seg[q];
+            const long long hd = (long long)*((volatile unsigned long long*)&P.head[q]);
+            const long long remq = cnt - (hd < cnt ? hd : cnt);
+            if (remq > bestrem) { bestrem = remq; bestq = q; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long orem = __shfl_xor_sync(0xFFFFFFFFu, bestrem, o);
+            const int oq = __shfl_xor_sync(0xFFFFFFFFu, bestq, o);
+            if (orem > bestrem || (orem == bestrem && oq > bestq)) { bestrem = orem; bestq = oq; }
+        }
+        if (bestq < 0) break;
+        const int q = bestq;
+        const int Q = P.qlen[q];
+        const long long cnt = P.seg[q + 1] - P.seg[q];
+        const long long base = P.seg[q];
+
+        __syncwarp();
+        Lane::build_profile(P, q, Q, reinterpret_cast<uint32_t*>(prof), lane, 32);
+        __syncwarp();
+
+        L.init();
+        bool exhausted = false;
+        for (;;) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (L.tid[h] >= 0 && L.rem[h] == 0)
+                    L.finish(P, h, q, Q, [&](int t) {
+                        const unsigned long long i = atomicAdd(P.ncand, 1ull);
+                        P.cand[i] = (uint32_t)t;
+                    });
+                if (L.tid[h] < 0 && !exhausted) {
+                    const unsigned long long i = atomicAdd(&P.head[q], 1ull);
+                    if ((long long)i < cnt) L.start(P, h, (int)(base + (long long)i), Q);
+                    else exhausted = true;
+                }
+            }
+            const bool active = (L.tid[0] >= 0) || (L.tid[1] >= 0);
+            if (!__any_sync(0xFFFFFFFFu, active)) break;
+            L.run_block(P, prof, keep_ge, keep_lt, Q);
+        }
+    }
+    // per-lane work counters -> global (one atomic per lane per launch)
+    if (L.n_tasks) {
+        atomicAdd(&P.counters[0], L.n_tasks);
+        atomicAdd(&P.counters[1], L.n_cells);
+    }
+    if (L.n_steps) atomicAdd(&P.counters[2], L.n_steps);
+}
+
+template <int NR>
+inline size_t score_smem_bytes() {
+    return sizeof(U4) * (34 + (size_t)SCORE_WARPS * NIDX * ScoreLane<NR>::PROF_STRIDE);
+}
+#endif  // __CUDACC__
+
+}  // namespace lsw

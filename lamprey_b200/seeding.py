@@ -1,0 +1,200 @@
+"""Host-side mirror of LAMPrey's seed stage, backed by the batched GPU engine.
+
+Mirrors, name for name and argument for argument (same ordering and error behaviour):
+
+* ``rc``                         /root/reference/lamprey.py:649-659
+* ``PrimerSet``                  /root/reference/lamprey.py:81-136
+* ``Alignment``                  /root/reference/lamprey.py:138-161
+* ``findPrimerAlignments``       /root/reference/lamprey.py:596-645   (--swalign branch)
+* ``findAllPrimerAlignments``    /root/reference/lamprey.py:699-733
+
+and adds the batched form the reference lacks: ``seed_reads(reads, primer_set, threshold)`` seeds a
+whole FASTQ in one device pass (recursion included) and returns a ``SeedBatch`` (struct of arrays;
+``batch[i]`` gives exactly what ``findAllPrimerAlignments`` returns for read ``i``).
+The arithmetic runs only in liblsw.so; nothing here computes an alignment on the CPU.
+"""
+import numpy as np
+
+from . import _native
+from ._native import HIT_DT
+
+_COMPLEMENT = {'A': 'T', 'C': 'G', 'G': 'C', 'T': 'A'}
+
+
+def rc(seq):
+    """Reverse complement; characters outside ACGT pass through unchanged."""
+    return ''.join(_COMPLEMENT.get(b, b) for b in reversed(seq))
+
+
+class PrimerSet(object):
+    """LAMP schema: ``<name> <sequence>`` lines, ``#`` comments, fwd/rev primer-order lines.
+    Names ending in ``c`` are stored reverse-complemented under the stripped name."""
+
+    def __init__(self, primer_set_filename=None, lines=None, verbose=False):
+        self.primer_dict = dict()
+        self.fwd_primer_order = ['F3', 'F2', 'F1', 'T', 'B1c', 'B2c', 'B3c']
+        self.rev_primer_order = ['B3', 'B2', 'B1', 'Tc', 'F1c', 'F2c', 'F3c']
+        if lines is None:
+            with open(primer_set_filename) as fp:
+                lines = fp.readlines()
+        for line in lines:
+            line = line.strip()
+            if not line or line.startswith("#"):
+                continue
+            fields = line.split(' ')
+            name = fields[0]
+            if name == 'fwd_primer_order':
+                self.fwd_primer_order = list(fields[1:])
+            elif name == 'rev_primer_order':
+                self.rev_primer_order = list(fields[1:])
+            elif name.endswith('c'):
+                self.primer_dict[name[:-1]] = rc(fields[1])
+            else:
+                self.primer_dict[name] = fields[1]
+        if verbose:                      # the reference prints both order lists on construction
+            print(self.fwd_primer_order)
+            print(self.rev_primer_order)
+
+    def sequences(self):
+        """[(name, sequence)] in the order findAllPrimerAlignments searches them:
+        T, Tc, then every other entry forward and reverse-complemented (lamprey.py:703-719)."""
+        out = [('T', self.primer_dict['T']), ('Tc', rc(self.primer_dict['T']))]
+        for name, seq in self.primer_dict.items():
+            if name != 'T':
+                out.append((name, seq))
+                out.append((name + 'c', rc(seq)))
+        return out
+
+
+class Alignment(object):
+    """Seed hit: [start, end) on the read, identity, schema sequence name."""
+
+    def __init__(self, start=0, end=0, identity=0.0, primer_name=''):
+        self.start = start
+        self.end = end
+        self.identity = identity
+        self.primer_name = primer_name
+
+    def __repr__(self):
+        return "{} at ({}, {}) identity: {}".format(self.primer_name, self.start, self.end, self.identity)
+
+    __str__ = __repr__
+
+    def __lt__(self, other):
+        return self.start < other.start
+
+    def __eq__(self, other):              # as in the reference: evaluates and returns None
+        self.start == other.start
+
+    __hash__ = object.__hash__
+
+
+def _read_arrays(reads):
+    """list of str/bytes, or (uint8 concat, int64 offsets) -> (concat, offsets)."""
+    if isinstance(reads, tuple) and len(reads) == 2 and isinstance(reads[0], np.ndarray):
+        return np.ascontiguousarray(reads[0], np.uint8), np.ascontiguousarray(reads[1], np.int64)
+    return _native.concat_sequences([str(r) for r in reads])
+
+
+class SeedBatch(object):
+    """Seeds of a read batch.  ``hits`` is a HIT_DT array ordered by (read, start, search order) --
+    the order lamprey.py:722's stable sort produces; ``offsets[i]:offsets[i+1]`` are read i's hits."""
+
+    def __init__(self, hits, n_reads, read_lengths, names, counters):
+        self.hits = hits
+        self.names = names
+        self.counters = counters
+        self.read_lengths = read_lengths
+        self.offsets = np.searchsorted(hits["read"], np.arange(n_reads + 1)).astype(np.int64)
+        tot = (hits["matches"].astype(np.int64) + hits["mismatches"])
+        self.identity = hits["matches"] / np.maximum(tot, 1)        # tot > 0 for every hit
+        covered = np.zeros(n_reads, np.int64)
+        np.add.at(covered, hits["read"], (hits["end"] - hits["start"]).astype(np.int64))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.coverage = covered / read_lengths.astype(np.float64)
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def alignments(self, i):
+        lo, hi = self.offsets[i], self.offsets[i + 1]
+        h = self.hits[lo:hi]
+        return [Alignment(int(x["start"]), int(x["end"]), float(self.identity[lo + k]), self.names[x["query"]])
+                for k, x in enumerate(h)]
+
+    def __getitem__(self, i):
+        """(sorted alignment list, coverage) -- findAllPrimerAlignments' return value for read i."""
+        if self.read_lengths[i] == 0:
+            raise ZeroDivisionError("float division by zero")      # lamprey.py:731 on an empty read
+        return self.alignments(i), float(self.coverage[i])
+
+
+def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None):
+    """findAllPrimerAlignments for every read of a batch in one device pass."""
+    from . import swalign as _sw
+    concat, offs = _read_arrays(reads)
+    pairs = primer_set.sequences()
+    names = [n for n, _ in pairs]
+    eng = engine or _sw.get_engine(device)
+    if aligner is not None:
+        eng.set_scoring(aligner.scoring_matrix.match, aligner.scoring_matrix.mismatch, aligner.gap_penalty,
+                        aligner.gap_extension_penalty)
+    else:
+        eng.set_scoring(2, -1, -1, -1)                  # initAligners, lamprey.py:1860-1865
+    eng.set_queries([s for _, s in pairs])
+    eng.upload_reads(concat, offs)
+    hits = eng.find_all(threshold)
+    return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters)
+
+
+def _preorder(hits, identity, name):
+    """Rebuild findPrimerAlignments' pre-order list from one sequence's hits sorted by start.
+    Hits of one sequence never overlap and each knows its recursion depth, so the recursion tree
+    is the Cartesian tree of (start-order, depth): root = the depth-minimum of a segment."""
+    out = []
+    stack = [(0, len(hits))]
+    while stack:
+        lo, hi = stack.pop()
+        if lo >= hi:
+            continue
+        k = lo + int(np.argmin(hits["depth"][lo:hi]))
+        out.append(Alignment(int(hits["start"][k]), int(hits["end"][k]), float(identity[k]), name))
+        stack.append((k + 1, hi))      # right is visited after left: push it first
+        stack.append((lo, k))
+    return out
+
+
+def findPrimerAlignments(aligner, seq, primer, primer_name, identity_threshold, args=None):
+    """Greedy best-hit + left/right recursion for ONE primer on ONE sequence; returns the same
+    pre-order list the reference builds.  ``args`` is accepted for signature compatibility
+    (the reference only reads ``args.swalign`` from it)."""
+    from . import swalign as _sw
+    eng = _sw.get_engine(getattr(aligner, "device", 0))
+    eng.set_scoring(aligner.scoring_matrix.match, aligner.scoring_matrix.mismatch, aligner.gap_penalty,
+                    aligner.gap_extension_penalty)
+    eng.set_queries([primer])
+    eng.upload_read_list([str(seq)])
+    hits = eng.find_all(identity_threshold)
+    tot = hits["matches"].astype(np.int64) + hits["mismatches"]
+    return _preorder(hits, hits["matches"] / np.maximum(tot, 1), primer_name)
+
+
+def findAllPrimerAlignments(aligner, seq, primers, identity_threshold, args=None):
+    """(stable-sorted hit list, coverage) for one read -- drop-in for lamprey.py:699-733."""
+    batch = seed_reads([str(seq)], primers, identity_threshold, aligner=aligner,
+                       device=getattr(aligner, "device", 0))
+    return batch[0]
+
+
+def shard_reads(offsets, world_size):
+    """Contiguous read ranges per rank, balanced by bases (the reference
+    deals reads round-robin over processes, lamprey.py:2182-2187).  -> [(lo, hi)] * world_size."""
+    offsets = np.asarray(offsets, np.int64)
+    n = len(offsets) - 1
+    total = offsets[-1] - offsets[0]
+    cuts = [0]
+    for r in range(1, world_size):
+        target = offsets[0] + (total * r) // world_size
+        cuts.append(int(min(n, max(cuts[-1], np.searchsorted(offsets, target, side="left")))))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]

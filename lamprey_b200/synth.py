@@ -1,0 +1,127 @@
+"""Synthetic ONT-like LAMP concatemer reads.
+
+A LAMP product is a concatemer of alternating forward / reverse-complement copies of the amplicon.
+Template of a read: optional ONT adapter (+ barcode) at the head, then copies of
+``amplicon + rc(amplicon)`` entered at a random phase, cut to the drawn length; then sequencing
+errors (substitution / insertion / deletion in equal parts) at the requested rate.
+Everything is vectorised numpy (``numpy.random.Generator(PCG64(seed))``), generated in chunks of
+reads so that 10^6 reads of 2 kb take seconds, not minutes.
+"""
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_GOLD = os.path.join(os.path.dirname(_HERE), "tests", "golden")
+
+_ACGT = np.frombuffer(b"ACGT", np.uint8)
+_COMP = np.zeros(256, np.uint8)
+for _a, _b in zip(b"ACGT", b"TGCA"):
+    _COMP[_a] = _b
+
+# the 141 bp F2..B2c stretch of the H3F3A target reference (data/references/H3F3A.fa[41:182]) and
+# the HIST1H3B target; read from the committed fixtures so the GPU box does not need /root/reference
+def _fasta(name):
+    with open(os.path.join(_GOLD, name)) as fp:
+        return "".join(l.strip() for l in fp if not l.startswith(">")).upper()
+
+
+def amplicon(schema="H33"):
+    if schema == "H33":
+        return _fasta("H3F3A.fa")[41:182]
+    return _fasta("HIST1H3B.fa")[200:380]
+
+
+ONT_RAP_TOP = "GGCGTCTGCTTGGGTGTTTAACCTTTTTTTTTTAATGTACTTCGTTCAGTTACGTATTGCT"
+
+
+def _rc_bytes(a):
+    return _COMP[a[::-1]]
+
+
+def draw_lengths(rng, n, kind="gamma", mean=2000, lo=200, hi=20000):
+    if kind == "gamma":
+        ln = rng.gamma(4.0, mean / 4.0, n)
+    else:
+        ln = rng.uniform(lo, hi, n)
+    return np.clip(ln, lo, hi).astype(np.int64)
+
+
+def _chunk(args):
+    (n, seed, ci, mean_len, error, schema, length_kind, min_len, max_len, adapter_p, heads) = args
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence([seed, ci])))
+    amp = np.frombuffer(amplicon(schema).encode(), np.uint8)
+    unit = np.concatenate([amp, _rc_bytes(amp)])
+    U = len(unit)
+    hl = max(len(h) for h in heads)
+    head_tab = np.zeros((len(heads), hl), np.uint8)
+    head_len = np.array([len(h) for h in heads], np.int64)
+    for k, h in enumerate(heads):
+        head_tab[k, :len(h)] = np.frombuffer(h, np.uint8)
+    L = draw_lengths(rng, n, length_kind, mean_len, min_len, max_len)
+    phase = rng.integers(0, U, n)
+    has_head = rng.random(n) < adapter_p
+    which = rng.integers(0, len(heads), n)
+    hlen = np.where(has_head, head_len[which], 0)
+    starts = np.zeros(n + 1, np.int64)
+    np.cumsum(L, out=starts[1:])
+    tot = int(starts[-1])
+    rid = np.repeat(np.arange(n, dtype=np.int32), L)
+    pos = np.arange(tot, dtype=np.int64) - starts[rid]
+    body = pos - hlen[rid]
+    tpl = unit[(phase[rid] + np.maximum(body, 0)) % U]
+    in_head = body < 0
+    if in_head.any():
+        tpl[in_head] = head_tab[which[rid[in_head]], pos[in_head]]
+    r = rng.random(tot, dtype=np.float32)
+    is_sub = r < error / 3
+    is_ins = (r >= error / 3) & (r < 2 * error / 3)
+    is_del = (r >= 2 * error / 3) & (r < error)
+    rnd = _ACGT[rng.integers(0, 4, tot, dtype=np.uint8)]
+    tpl = np.where(is_sub, rnd, tpl)
+    counts = np.ones(tot, np.uint8)
+    counts[is_ins] = 2
+    counts[is_del] = 0
+    out = np.repeat(tpl, counts)
+    ends = np.cumsum(counts, dtype=np.int64)
+    ins_at = ends[is_ins] - 1                       # the second copy of an inserted position is random
+    out[ins_at] = _ACGT[rng.integers(0, 4, len(ins_at), dtype=np.uint8)]
+    new_len = np.add.reduceat(counts.astype(np.int64), starts[:-1]) if tot else np.zeros(n, np.int64)
+    return out, new_len
+
+
+def generate(n_reads, seed=3, mean_len=2000, error=0.08, schema="H33", length_kind="gamma", min_len=200,
+             max_len=20000, adapter_p=0.5, heads=None, chunk=16384, workers=1):
+    """-> (uint8 ASCII concat, int64 offsets[n+1]).  heads: optional list of byte strings, one of which
+    (uniformly) replaces the ONT adapter at the read head (config 5 injects barcode + adapter).
+    Each chunk of reads has its own PCG64 stream seeded by (seed, chunk index), so the result does
+    not depend on `workers`.  workers > 1 forks a pool: call it BEFORE initialising CUDA."""
+    if heads is None:
+        heads = [ONT_RAP_TOP.encode()]
+    jobs = [(min(chunk, n_reads - c0), seed, ci, mean_len, error, schema, length_kind, min_len, max_len, adapter_p,
+             heads) for ci, c0 in enumerate(range(0, n_reads, chunk))]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            parts = pool.map(_chunk, jobs)
+    else:
+        parts = [_chunk(j) for j in jobs]
+    concat = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, np.uint8)
+    lens = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int64)
+    offs = np.zeros(n_reads + 1, np.int64)
+    np.cumsum(lens, out=offs[1:])
+    return concat, offs
+
+
+CONFIGS = {
+    # BASELINE.json configs[2..4] / SURVEY.md section 8d
+    "synth_2kb_8pct": dict(mean_len=2000, error=0.08, min_len=200, max_len=20000, seed=3, schema="H33"),
+    "synth_5kb_12pct": dict(mean_len=5000, error=0.12, min_len=500, max_len=50000, seed=4, schema="H33"),
+    "synth_20_50kb_12pct": dict(length_kind="uniform", min_len=20000, max_len=50000, error=0.12, seed=5,
+                                schema="H33", adapter_p=1.0),
+}
+
+
+def reads_as_strings(concat, offs):
+    b = concat.tobytes()
+    return [b[offs[i]:offs[i + 1]].decode("ascii") for i in range(len(offs) - 1)]

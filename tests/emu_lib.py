@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE: ctypes binding of liblsw_emu.so, the host emulation of the CUDA kernels'
+lane logic (lamprey_b200/csrc/lsw_emu.cu).  Lets the CPU test tier check the kernel arithmetic
+against the oracle.  Never used by the product path."""
+import ctypes
+import os
+
+import numpy as np
+
+from lamprey_b200._native import HIT_DT, RESULT_DT, TASK_DT, concat_sequences, _ptr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "lamprey_b200", "liblsw_emu.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(PATH)
+        _lib.lsw_emu_find_all.restype = ctypes.c_int
+        _lib.lsw_emu_align_tasks.restype = ctypes.c_int
+    return _lib
+
+
+def find_all(reads, seqs, thr, match=2, mismatch=-1, gap=-1):
+    rc_, ro = concat_sequences(reads)
+    qc, qo = concat_sequences(seqs)
+    qo = qo.astype(np.int32)
+    cap = max(1024, int(ro[-1]) // 4)
+    out = np.zeros(cap, HIT_DT)
+    n = ctypes.c_int64(0)
+    cnt = np.zeros(4, np.int64)
+    rc = lib().lsw_emu_find_all(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc),
+                                _ptr(qo), ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap),
+                                ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt))
+    if rc:
+        raise RuntimeError("lsw_emu_find_all rc=%d" % rc)
+    return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), steps=int(cnt[2]), rounds=int(cnt[3]))
+
+
+def align_tasks(reads, seqs, tasks, match=2, mismatch=-1, gap=-1):
+    rc_, ro = concat_sequences(reads)
+    qc, qo = concat_sequences(seqs)
+    qo = qo.astype(np.int32)
+    tasks = np.ascontiguousarray(tasks, dtype=TASK_DT)
+    out = np.zeros(len(tasks), RESULT_DT)
+    cap = max(64, 8 * len(tasks) + int(sum(t["end"] - t["start"] for t in tasks)))
+    cig = np.zeros(cap, np.uint32)
+    used = ctypes.c_int64(0)
+    rc = lib().lsw_emu_align_tasks(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc),
+                                   _ptr(qo), ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap),
+                                   ctypes.c_int64(len(tasks)), _ptr(tasks), _ptr(out), _ptr(cig), ctypes.c_int64(cap),
+                                   ctypes.byref(used))
+    if rc:
+        raise RuntimeError("lsw_emu_align_tasks rc=%d" % rc)
+    return out, cig[:used.value]

@@ -1,0 +1,124 @@
+"""Kernel lane logic, emulated on the host (liblsw_emu.so), against the oracle.  This is the same
+__host__ __device__ code the CUDA kernels run (ScoreLane<NR>, trace_task<NR>); the GPU tier
+(test_gpu_parity.py) repeats these checks through the real kernels and the C ABI."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import emu_lib
+from conftest import GOLD, load_reads, schema_path, load_seed_golden, hits_matrix
+from lamprey_b200._native import TASK_DT
+from oracle import seeding_ref, c_oracle
+
+_OPS = " MID"
+
+
+def _seqs(schema):
+    return [s for _, s in seeding_ref.PrimerSet(schema_path(schema)).sequences()]
+
+
+@pytest.mark.parametrize("reads_key,schema,thr", [("50", "H33", 0.70), ("50", "H33", 0.75), ("50", "H31", 0.70),
+                                                  ("50", "H31", 0.75), ("1k", "H33", 0.75), ("1k", "H31", 0.70)])
+def test_emu_find_all_vs_golden(reads_key, schema, thr):
+    gold = load_seed_golden(reads_key, schema, thr)
+    hits, cnt = emu_lib.find_all(load_reads(reads_key), _seqs(schema), thr)
+    assert np.array_equal(hits_matrix(hits), gold["hits"])
+    assert (cnt["tasks"], cnt["cells"]) == (int(gold["calls"]), int(gold["cells"]))
+
+
+def _check_tasks(reads, seqs, tasks, scoring=(2, -1, -1)):
+    res, cig = emu_lib.align_tasks(reads, seqs, tasks, *scoring)
+    for t, r in zip(tasks, res):
+        want = c_oracle.align(reads[t["read"]][t["start"]:t["end"]], seqs[t["query"]], scoring[0], scoring[1],
+                              scoring[2], scoring[2])
+        got_cigar = [(int(c) >> 2, _OPS[int(c) & 3]) for c in cig[r["cigar_off"]:r["cigar_off"] + r["n_cigar"]]]
+        got = dict(score=int(r["score"]), q_pos=int(r["q_pos"]), q_end=int(r["q_end"]), r_pos=int(r["r_pos"]),
+                   r_end=int(r["r_end"]), matches=int(r["matches"]), mismatches=int(r["mismatches"]), cigar=got_cigar)
+        assert got == want, (t, reads[t["read"]][t["start"]:t["end"]], seqs[t["query"]])
+
+
+def test_emu_align_vs_committed_vectors():
+    vecs = [v for v in json.load(open(os.path.join(GOLD, "align_vectors.json")))
+            if v["query"] and set(v["query"].upper()) <= set("ACGT")]
+    assert len(vecs) > 250
+    reads = [v["ref"] for v in vecs]
+    seqs = sorted(set(v["query"] for v in vecs))
+    tasks = np.zeros(len(vecs), TASK_DT)
+    for i, v in enumerate(vecs):
+        tasks[i] = (i, 0, len(v["ref"]), seqs.index(v["query"]))
+    res, cig = emu_lib.align_tasks(reads, seqs, tasks)
+    for v, r in zip(vecs, res):
+        cigar = "".join("%d%s" % (int(c) >> 2, _OPS[int(c) & 3]) for c in cig[r["cigar_off"]:r["cigar_off"] + r["n_cigar"]])
+        got = (r["score"], r["q_pos"], r["q_end"], r["r_pos"], r["r_end"], r["matches"], r["mismatches"], cigar)
+        assert got == tuple(v[k] for k in ("score", "q_pos", "q_end", "r_pos", "r_end", "matches", "mismatches", "cigar"))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_emu_align_random_tie_heavy(seed):
+    rng = random.Random(seed)
+    alpha = ["AC", "A", "ACG", "ACGT", "AT", "ACGT"][seed]
+    reads, seqs, tasks = [], [], []
+    for q in range(12):
+        seqs.append("".join(rng.choice(alpha) for _ in range(rng.choice([1, 2, 5, 15, 16, 17, 24, 25, 33, 48, 49, 63]))))
+    for i in range(40):
+        n = rng.choice([0, 1, 3, 15, 16, 17, 63, 64, 65, 127, 128, 129, 300, 700])
+        r = [rng.choice(alpha + ("N" if rng.random() < 0.2 else "")) for _ in range(n)]
+        if n > 80 and rng.random() < 0.7:         # plant noisy copies
+            for _ in range(3):
+                s = seqs[rng.randrange(len(seqs))]
+                p = rng.randrange(0, n - len(s))
+                for k, ch in enumerate(s):
+                    if rng.random() > 0.1:
+                        r[p + k] = ch
+        reads.append("".join(r).lower() if rng.random() < 0.1 else "".join(r))
+    for i, r in enumerate(reads):
+        for _ in range(6):
+            a = rng.randrange(0, len(r) + 1)
+            b = rng.randrange(a, len(r) + 1)
+            tasks.append((i, a, b, rng.randrange(len(seqs))))
+        tasks.append((i, 0, len(r), rng.randrange(len(seqs))))
+    _check_tasks(reads, seqs, np.array(tasks, dtype=TASK_DT))
+
+
+@pytest.mark.parametrize("scoring", [(1, -1, -1), (3, -2, -2), (2, -3, -1), (1, -2, -3), (2, -1, -2)])
+def test_emu_align_general_scoring(scoring):
+    rng = random.Random(sum(scoring) + 11)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(n)) for n in (8, 15, 20, 24, 31, 40)]
+    reads = []
+    for i in range(30):
+        n = rng.randrange(1, 400)
+        r = [rng.choice("ACGT") for _ in range(n)]
+        s = seqs[rng.randrange(len(seqs))]
+        if n > len(s) + 2:
+            p = rng.randrange(0, n - len(s))
+            for k, ch in enumerate(s):
+                if rng.random() > 0.15:
+                    r[p + k] = ch
+        reads.append("".join(r))
+    tasks = np.array([(i, 0, len(r), q) for i, r in enumerate(reads) for q in range(len(seqs))], dtype=TASK_DT)
+    _check_tasks(reads, seqs, tasks, scoring)
+
+
+def test_emu_find_all_edge_reads():
+    seqs = _seqs("H33")
+    reads = ["", "A", "ACGT" * 3, "N" * 100, seqs[0], seqs[0] * 7, (seqs[4] + "ACGTTGCA") * 30, "acgt" * 50 + seqs[9].lower()]
+    hits, cnt = emu_lib.find_all(reads, seqs, 0.7)
+    rows = []
+    calls = cells = 0
+    for i, r in enumerate(reads):
+        h, st = c_oracle.find_all(r, seqs, 0.7)
+        h = h[np.argsort(h["start"], kind="stable")]
+        calls += st["calls"]
+        cells += st["cells"]
+        rows += [(i, x["seq"], x["start"], x["end"], x["matches"], x["mismatches"], x["score"], x["q_pos"], x["q_end"],
+                  x["depth"]) for x in h]
+    assert np.array_equal(hits_matrix(hits), np.array(rows, np.int32).reshape(-1, 10))
+    assert (cnt["tasks"], cnt["cells"]) == (calls, cells)
+
+
+def test_emu_rejects_unsupported_scoring():
+    with pytest.raises(RuntimeError):
+        emu_lib.align_tasks(["ACGT"], ["ACG"], np.array([(0, 0, 4, 0)], dtype=TASK_DT), 2, 0, -1)

@@ -1,0 +1,228 @@
+"""Parity tests proper: the CUDA kernels, called through the C ABI (liblsw.so) and the drop-in
+Python surface, against the oracle and the committed golden fixtures.  Bit-exact: all outputs are
+integers (scores, coordinates, CIGAR runs, match counts); identity is derived in Python doubles."""
+import io
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, load_reads, schema_path, load_seed_golden, hits_matrix
+from lamprey_b200 import seeding, swalign, synth
+from lamprey_b200._native import TASK_DT
+from oracle import seeding_ref, c_oracle, swalign_ref
+
+pytestmark = pytest.mark.gpu
+_OPS = " MID"
+
+
+def _seqs(schema):
+    return [s for _, s in seeding_ref.PrimerSet(schema_path(schema)).sequences()]
+
+
+def test_readme_vector_through_dropin_surface():
+    sw = swalign.LocalAlignment(swalign.NucleotideScoringMatrix(2, -1))       # lamprey.py:1860-1865
+    a = sw.align('ACACACTA', 'AGCACACA')
+    assert (a.score, a.cigar_str, a.matches, a.mismatches) == (12, '1M1I5M1D1M', 7, 2)
+    assert (a.q_pos, a.q_end, a.r_pos, a.r_end) == (0, 8, 0, 8)
+    assert a.identity == 7 / 9
+    buf = io.StringIO()
+    a.dump(out=buf)
+    ref = io.StringIO()
+    swalign_ref.LocalAlignment(swalign_ref.NucleotideScoringMatrix(2, -1)).align('ACACACTA', 'AGCACACA').dump(out=ref)
+    assert buf.getvalue() == ref.getvalue()
+    z = sw.align('AAAA', 'CCCC')
+    assert (z.score, z.q_pos, z.q_end, z.r_pos, z.r_end, z.cigar, z.identity) == (0, 4, 4, 4, 4, [], 0)
+    e = sw.align('', 'ACGT')
+    assert (e.score, e.q_pos, e.r_pos, e.r_end) == (0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("reads_key,schema,thr", [("50", "H33", 0.70), ("50", "H33", 0.75), ("50", "H31", 0.70),
+                                                  ("50", "H31", 0.75), ("1k", "H33", 0.70), ("1k", "H33", 0.75),
+                                                  ("1k", "H31", 0.70), ("1k", "H31", 0.75)])
+def test_find_all_vs_golden(engine, reads_key, schema, thr):
+    gold = load_seed_golden(reads_key, schema, thr)
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(_seqs(schema))
+    engine.upload_read_list(load_reads(reads_key))
+    hits = engine.find_all(thr)
+    assert np.array_equal(hits_matrix(hits), gold["hits"])
+    c = engine.last_counters
+    assert (c["tasks"], c["cells"]) == (int(gold["calls"]), int(gold["cells"]))
+
+
+def test_seed_reads_dropin_matches_reference_function(engine):
+    reads = load_reads("50")
+    ps = seeding.PrimerSet(schema_path("H33"))
+    batch = seeding.seed_reads(reads, ps, 0.75)
+    gold = load_seed_golden("50", "H33", 0.75)
+    assert np.array_equal(batch.coverage, gold["coverage"])
+    al = swalign_ref.LocalAlignment(swalign_ref.NucleotideScoringMatrix(2, -1))
+    for i in (3, 11):
+        want, wcov = seeding_ref.find_all_primer_alignments(al, reads[i], seeding_ref.PrimerSet(schema_path("H33")), 0.75)
+        got, gcov = batch[i]
+        assert [(h.start, h.end, h.identity, h.primer_name) for h in got] == [h.astuple() for h in want]
+        assert gcov == wcov
+    # function-level drop-ins (same signatures as lamprey.py:596, 699)
+    sw = swalign.LocalAlignment(swalign.NucleotideScoringMatrix(2, -1))
+    got, cov = seeding.findAllPrimerAlignments(sw, reads[3], ps, 0.75, None)
+    want, wcov = seeding_ref.find_all_primer_alignments(al, reads[3], seeding_ref.PrimerSet(schema_path("H33")), 0.75)
+    assert [(h.start, h.end, h.identity, h.primer_name) for h in got] == [h.astuple() for h in want] and cov == wcov
+    t = ps.primer_dict["T"]
+    got = seeding.findPrimerAlignments(sw, reads[11], t, "T", 0.7, None)
+    want = seeding_ref.find_primer_alignments(al, reads[11], t, "T", 0.7)
+    assert [(h.start, h.end, h.identity) for h in got] == [(h.start, h.end, h.identity) for h in want]
+
+
+def _check_tasks(engine, reads, seqs, tasks, scoring=(2, -1, -1)):
+    engine.set_scoring(scoring[0], scoring[1], scoring[2], scoring[2])
+    engine.set_queries(seqs)
+    engine.upload_read_list(reads)
+    res, cig = engine.align_tasks(tasks)
+    for t, r in zip(tasks, res):
+        want = c_oracle.align(reads[t["read"]][t["start"]:t["end"]], seqs[t["query"]], scoring[0], scoring[1],
+                              scoring[2], scoring[2])
+        got_cigar = [(int(c) >> 2, _OPS[int(c) & 3]) for c in cig[r["cigar_off"]:r["cigar_off"] + r["n_cigar"]]]
+        got = dict(score=int(r["score"]), q_pos=int(r["q_pos"]), q_end=int(r["q_end"]), r_pos=int(r["r_pos"]),
+                   r_end=int(r["r_end"]), matches=int(r["matches"]), mismatches=int(r["mismatches"]), cigar=got_cigar)
+        assert got == want, (t, reads[t["read"]][t["start"]:t["end"]], seqs[t["query"]])
+
+
+def test_align_many_vs_committed_vectors(engine):
+    vecs = [v for v in json.load(open(os.path.join(GOLD, "align_vectors.json")))
+            if v["query"] and set(v["query"].upper()) <= set("ACGT")]
+    reads = [v["ref"] for v in vecs]
+    seqs = sorted(set(v["query"] for v in vecs))
+    iv = np.array([(i, 0, len(v["ref"]), seqs.index(v["query"])) for i, v in enumerate(vecs)])
+    batch = swalign.align_many(reads, seqs, iv)
+    for i, v in enumerate(vecs):
+        a = batch[i]
+        got = (a.score, a.q_pos, a.q_end, a.r_pos, a.r_end, a.matches, a.mismatches, a.cigar_str, a.identity)
+        assert got == tuple(v[k] for k in ("score", "q_pos", "q_end", "r_pos", "r_end", "matches", "mismatches",
+                                           "cigar", "identity"))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_align_random_tie_heavy(engine, seed):
+    rng = random.Random(seed)
+    alpha = ["AC", "A", "ACG", "ACGT", "AT", "ACGT"][seed]
+    seqs = ["".join(rng.choice(alpha) for _ in range(rng.choice([1, 2, 5, 15, 16, 17, 24, 25, 33, 48, 49, 63])))
+            for _ in range(12)]
+    reads, tasks = [], []
+    for i in range(60):
+        n = rng.choice([0, 1, 3, 15, 16, 17, 63, 64, 65, 127, 128, 129, 300, 700, 2500])
+        r = [rng.choice(alpha + ("N" if rng.random() < 0.2 else "")) for _ in range(n)]
+        if n > 80 and rng.random() < 0.7:
+            for _ in range(3):
+                s = seqs[rng.randrange(len(seqs))]
+                p = rng.randrange(0, n - len(s))
+                for k, ch in enumerate(s):
+                    if rng.random() > 0.1:
+                        r[p + k] = ch
+        reads.append("".join(r).lower() if rng.random() < 0.1 else "".join(r))
+    for i, r in enumerate(reads):
+        for _ in range(6):
+            a = rng.randrange(0, len(r) + 1)
+            b = rng.randrange(a, len(r) + 1)
+            tasks.append((i, a, b, rng.randrange(len(seqs))))
+        tasks.append((i, 0, len(r), rng.randrange(len(seqs))))
+    _check_tasks(engine, reads, seqs, np.array(tasks, dtype=TASK_DT))
+
+
+@pytest.mark.parametrize("scoring", [(1, -1, -1), (3, -2, -2), (2, -3, -1), (1, -2, -3), (2, -1, -2)])
+def test_align_general_scoring(engine, scoring):
+    rng = random.Random(sum(scoring) + 11)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(n)) for n in (8, 15, 20, 24, 31, 40)]
+    reads = []
+    for i in range(30):
+        n = rng.randrange(1, 400)
+        r = [rng.choice("ACGT") for _ in range(n)]
+        s = seqs[rng.randrange(len(seqs))]
+        if n > len(s) + 2:
+            p = rng.randrange(0, n - len(s))
+            for k, ch in enumerate(s):
+                if rng.random() > 0.15:
+                    r[p + k] = ch
+        reads.append("".join(r))
+    tasks = np.array([(i, 0, len(r), q) for i, r in enumerate(reads) for q in range(len(seqs))], dtype=TASK_DT)
+    _check_tasks(engine, reads, seqs, tasks, scoring)
+
+
+def test_find_all_edge_reads(engine):
+    seqs = _seqs("H33")
+    reads = ["", "A", "ACGT" * 3, "N" * 100, seqs[0], seqs[0] * 7, (seqs[4] + "ACGTTGCA") * 30, "acgt" * 50 + seqs[9].lower()]
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(seqs)
+    engine.upload_read_list(reads)
+    hits = engine.find_all(0.7)
+    rows = []
+    for i, r in enumerate(reads):
+        h, st = c_oracle.find_all(r, seqs, 0.7)
+        h = h[np.argsort(h["start"], kind="stable")]
+        rows += [(i, x["seq"], x["start"], x["end"], x["matches"], x["mismatches"], x["score"], x["q_pos"], x["q_end"],
+                  x["depth"]) for x in h]
+    assert np.array_equal(hits_matrix(hits), np.array(rows, np.int32).reshape(-1, 10))
+    with pytest.raises(ZeroDivisionError):
+        seeding.seed_reads(reads, seeding.PrimerSet(schema_path("H33")), 0.7)[0]     # empty read: lamprey.py:731
+
+
+@pytest.mark.parametrize("cfg,n,schema", [("synth_2kb_8pct", 96, "H33"), ("synth_5kb_12pct", 40, "H31"),
+                                          ("synth_20_50kb_12pct", 6, "H33")])
+def test_find_all_synthetic_vs_oracle(engine, cfg, n, schema):
+    # the BASELINE.json synthetic configs at sizes the C oracle finishes in seconds
+    kw = dict(synth.CONFIGS[cfg])
+    kw["schema"] = schema
+    concat, offs = synth.generate(n, **kw)
+    seqs = _seqs(schema)
+    if cfg == "synth_20_50kb_12pct":
+        seqs = seqs[:40]
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(seqs)
+    engine.upload_reads(concat, offs)
+    hits = engine.find_all(0.7)
+    reads = synth.reads_as_strings(concat, offs)
+    rows, calls, cells = [], 0, 0
+    for i, r in enumerate(reads):
+        h, st = c_oracle.find_all(r, seqs, 0.7)
+        h = h[np.argsort(h["start"], kind="stable")]
+        calls += st["calls"]
+        cells += st["cells"]
+        rows += [(i, x["seq"], x["start"], x["end"], x["matches"], x["mismatches"], x["score"], x["q_pos"], x["q_end"],
+                  x["depth"]) for x in h]
+    assert np.array_equal(hits_matrix(hits), np.array(rows, np.int32).reshape(-1, 10))
+    assert (engine.last_counters["tasks"], engine.last_counters["cells"]) == (calls, cells)
+
+
+def test_full_size_properties(engine):
+    # size-independent properties at a size the oracle cannot check directly (65536 reads, ~1.3e8 bases):
+    # (1) sharding invariance: seeding two halves separately gives the same hits as the whole batch;
+    # (2) hits of one (read, sequence) never overlap and lie inside the read;
+    # (3) every hit passes the reference predicate in Python doubles;
+    # (4) idempotence: a second pass returns identical bytes.
+    concat, offs = synth.generate(65536, workers=8, **synth.CONFIGS["synth_2kb_8pct"])
+    seqs = _seqs("H33")
+    qlen = np.array([len(s) for s in seqs])
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(seqs)
+    engine.upload_reads(concat, offs)
+    whole = engine.find_all(0.7)
+    again = engine.find_all(0.7)
+    assert whole.tobytes() == again.tobytes()
+    half = len(offs) // 2
+    engine.upload_reads(concat[:offs[half]], offs[:half + 1])
+    a = engine.find_all(0.7).copy()
+    engine.upload_reads(concat[offs[half]:], offs[half:] - offs[half])
+    b = engine.find_all(0.7).copy()
+    b["read"] += half
+    assert np.concatenate([a, b]).tobytes() == whole.tobytes()
+    lens = np.diff(offs)
+    assert (whole["start"] >= 0).all() and (whole["end"] <= lens[whole["read"]]).all() and (whole["start"] < whole["end"]).all()
+    order = np.lexsort((whole["start"], whole["query"], whole["read"]))
+    s = whole[order]
+    same = (s["read"][1:] == s["read"][:-1]) & (s["query"][1:] == s["query"][:-1])
+    assert (s["start"][1:][same] >= s["end"][:-1][same]).all()
+    m, x = whole["matches"].astype(np.int64), whole["mismatches"].astype(np.int64)
+    assert (m / (m + x) >= 0.7).all() and ((whole["end"] - whole["start"]) >= qlen[whole["query"]] * 0.7).all()
+    assert (whole["score"] == 2 * m - x).all()
