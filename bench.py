@@ -321,7 +321,7 @@ def main():
         gcups = cells_total / t_value / 1e9
         score_s = acc["ms_score"] / 1e3
         k1_gcups = cnt["cells"] * args.steps / score_s / 1e9 if score_s > 0 else None
-        peak_ops = max(peak.get("viaddmnmx_s16x2", 0.0), peak.get("iadd", 0.0))    # G packed-lane ops / s
+        peak_ops = peak.get("viaddmnmx_s16x2", 0.0)      # G lane-ops / s of the packed DPX instruction K1 is built from
         # one packed (s16x2) instruction lane updates 2 cells' worth of one algorithmic op
         peak_gcups = peak_ops * 2.0 / ALG_OPS_PER_CELL if peak_ops else None
         roofline = {"bound": "int_alu", "kernel": "k_score<NR> (K1: DP fill + arg-max)",

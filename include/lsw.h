@@ -90,6 +90,8 @@ typedef struct {
     float   ms_total;     /* device time of the whole call                                */
     int64_t score_launches, trace_launches, other_launches;
     int64_t steps;        /* lane-steps (columns incl. dead padding) the score kernels ran */
+    int64_t fallbacks;    /* traced tasks the short-window traceback could not prove exact and that
+                             were redone by the full-window kernel                              */
 } lsw_counters;
 
 /* cigar runs are (count << 2) | op with op 1 = 'M', 2 = 'I', 3 = 'D' */

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -93,6 +94,7 @@ struct lsw_ctx {
     DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen;
 
     TaskBuf tb[2], child;
+    DevBuf d_fallback[NCLASS], d_nfallback;
     DevBuf d_res, d_seg[2], d_head, d_cand[NCLASS], d_ncand, d_counters, d_child_flag, d_pos,
            d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_nhits, d_keys[2], d_vals[2], d_err,
            d_results, d_cigar, d_ncigar;
@@ -241,28 +243,41 @@ int launch_score_class(lsw_ctx* ctx, int c, const ScoreParams& P, int64_t n) {
     }
 }
 
-template <int NR>
+template <int NR, int NR2>
 int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
+    // short-window kernel over every candidate of the class
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<NR>, TRACE_THREADS, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_fast<NR>, TRACE_THREADS, 0));
     if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
     const int blocks = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * occ);
     const int64_t threads = (int64_t)blocks * TRACE_THREADS;
-    const int64_t W = trace_window(qmax, ctx->match, ctx->g);
-    CK(ctx->d_scratch.ensure((size_t)threads * (size_t)W * (NR / 16) * 4));
+    const int64_t Wf = trace_window_fast_max(qmax, ctx->match, ctx->g);
+    // full-window kernel over the (normally empty) fallback list
+    int occ2 = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_trace_full<NR2>, TRACE_THREADS, 0));
+    if (occ2 < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
+    const int blocks2 = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * std::min(occ2, 2));
+    const int64_t threads2 = (int64_t)blocks2 * TRACE_THREADS;
+    const int64_t W = trace_window_full(qmax, ctx->match, ctx->g);
+    const size_t need = std::max((size_t)threads * (size_t)Wf * (NR / 4) * 4, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
+    CK(ctx->d_scratch.ensure(need));
     P.scratch = ctx->d_scratch.as<uint32_t>();
     P.scratch_stride = threads;
-    k_trace<NR><<<blocks, TRACE_THREADS, 0, ctx->stream>>>(P);
+    k_trace_fast<NR><<<blocks, TRACE_THREADS, 0, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    P.scratch_stride = threads2;
+    k_trace_full<NR2><<<blocks2, TRACE_THREADS, 0, ctx->stream>>>(P);
     CK(cudaGetLastError());
     return LSW_OK;
 }
 
 int launch_trace_class(lsw_ctx* ctx, int c, const TraceParams& P, int64_t n, int qmax) {
-    switch (CLASS_NR2[c]) {
-        case 16: return launch_trace<16>(ctx, P, n, qmax);
-        case 32: return launch_trace<32>(ctx, P, n, qmax);
-        case 48: return launch_trace<48>(ctx, P, n, qmax);
-        default: return launch_trace<64>(ctx, P, n, qmax);
+    switch (CLASS_NR[c]) {
+        case 16: return launch_trace<16, 16>(ctx, P, n, qmax);
+        case 24: return launch_trace<24, 32>(ctx, P, n, qmax);
+        case 32: return launch_trace<32, 32>(ctx, P, n, qmax);
+        case 48: return launch_trace<48, 48>(ctx, P, n, qmax);
+        default: return launch_trace<64, 64>(ctx, P, n, qmax);
     }
 }
 
@@ -302,12 +317,14 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
     CK(ctx->d_ncand.ensure(NCLASS * 8));
     CK(cudaMemsetAsync(ctx->d_head.p, 0, (size_t)ctx->nseq * 8, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_ncand.p, 0, NCLASS * 8, ctx->stream));
+    CK(ctx->d_nfallback.ensure(NCLASS * 8));
+    CK(cudaMemsetAsync(ctx->d_nfallback.p, 0, NCLASS * 8, ctx->stream));
     int64_t ncls[NCLASS];
     int qmax[NCLASS];
     for (int c = 0; c < NCLASS; c++) {
         ncls[c] = 0; qmax[c] = 0;
         for (int s : ctx->class_seqs[c]) { ncls[c] += h_seg[s + 1] - h_seg[s]; qmax[c] = std::max(qmax[c], ctx->qlen[s]); }
-        if (ncls[c]) CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4));
+        if (ncls[c]) { CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4)); CK(ctx->d_fallback[c].ensure((size_t)ncls[c] * 4)); }
     }
     ScoreParams P;
     fill_score_params(ctx, P, cur, segi);
@@ -332,9 +349,11 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             T.res = ctx->d_res.as<int2>();
             T.cand = ctx->d_cand[c].as<uint32_t>();
             T.ncand = ctx->d_ncand.as<unsigned long long>() + c;
+            T.fallback = ctx->d_fallback[c].as<uint32_t>();
+            T.nfallback = ctx->d_nfallback.as<unsigned long long>() + c;
             int rc = launch_trace_class(ctx, c, T, ncls[c], qmax[c]);
             if (rc) return rc;
-            if (cnt) cnt->trace_launches++;
+            if (cnt) cnt->trace_launches += 2;
         }
     }
     return LSW_OK;
@@ -403,7 +422,8 @@ void lsw_destroy(lsw_ctx* ctx) {
                       &ctx->d_keys[1], &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_err, &ctx->d_results,
                       &ctx->d_cigar, &ctx->d_ncigar};
     for (DevBuf* b : bufs) b->release();
-    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); }
+    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); }
+    ctx->d_nfallback.release();
     ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -569,6 +589,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
 
     int64_t n = n0;
     int round = 0;
+    size_t dbg_from = 0;
     int rc = LSW_OK;
     unsigned long long h_nhits = 0;
     while (n > 0) {
@@ -612,7 +633,21 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         }
         CK(cudaMemcpyAsync(h_seg.data(), ctx->d_seg[cur ^ 1].p, h_seg.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(&h_nhits, ctx->d_nhits.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long h_nc[NCLASS], h_nf[NCLASS];
+        CK(cudaMemcpyAsync(h_nc, ctx->d_ncand.p, NCLASS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_nf, ctx->d_nfallback.p, NCLASS * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        for (int c = 0; c < NCLASS; c++) { cnt.traced += (int64_t)h_nc[c]; cnt.fallbacks += (int64_t)h_nf[c]; }
+        if (getenv("LSW_DEBUG")) {
+            float ms[3] = {0.f, 0.f, 0.f};
+            for (size_t k = dbg_from; k < ctx->timed.size(); k++) {
+                float m = 0.f;
+                if (ctx->timed[k].kind < 3 && cudaEventElapsedTime(&m, ctx->timed[k].e0, ctx->timed[k].e1) == cudaSuccess) ms[ctx->timed[k].kind] += m;
+            }
+            dbg_from = ctx->timed.size();
+            fprintf(stderr, "[lsw] round %d: tasks %lld -> children %d, hits so far %llu, score %.3f ms, trace %.3f ms, other %.3f ms\n",
+                    round, (long long)n, total_next, h_nhits, ms[0], ms[1], ms[2]);
+        }
         if (round == 0) { cnt.top_tasks = n; }
         cur ^= 1;
         n = total_next;

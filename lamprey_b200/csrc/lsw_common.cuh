@@ -98,6 +98,8 @@ struct TraceParams {
     const int32_t*  qlen;
     const uint32_t* cand;
     const unsigned long long* ncand;
+    uint32_t*       fallback;     // tasks the short-window kernel could not prove exact
+    unsigned long long* nfallback;
     uint32_t*       scratch;      // direction bits, [window col][word][thread]
     int64_t         scratch_stride;   // threads in the launch
     int32_t match, mismatch, g;

@@ -36,6 +36,8 @@ struct Emu {
     std::vector<int2> res;
     std::vector<uint8_t> cand_ok;
     unsigned long long counters[4];
+    unsigned long long fallbacks = 0;
+    bool force_full = false;
 };
 
 bool setup(Emu& E, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
@@ -111,12 +113,22 @@ void emu_score_class(Emu& E, const ScoreParams& P, int c, int q, std::vector<uin
     }
 }
 
-void emu_trace_class(const TraceParams& T, int c, int t) {
-    switch (CLASS_NR2[c]) {
-        case 16: trace_task<16>(T, t, 0); break;
-        case 32: trace_task<32>(T, t, 0); break;
-        case 48: trace_task<48>(T, t, 0); break;
-        default: trace_task<64>(T, t, 0); break;
+template <int NR, int NR2>
+void emu_trace_one(Emu& E, const TraceParams& T, int t) {
+    E.counters[3]++;
+    if (E.force_full || !trace_fast_task<NR>(T, t, 0)) {
+        E.fallbacks++;
+        trace_full_task<NR2>(T, t, 0);
+    }
+}
+
+void emu_trace_class(Emu& E, const TraceParams& T, int c, int t) {
+    switch (CLASS_NR[c]) {
+        case 16: emu_trace_one<16, 16>(E, T, t); break;
+        case 24: emu_trace_one<24, 32>(E, T, t); break;
+        case 32: emu_trace_one<32, 32>(E, T, t); break;
+        case 48: emu_trace_one<48, 48>(E, T, t); break;
+        default: emu_trace_one<64, 64>(E, T, t); break;
     }
 }
 
@@ -138,7 +150,7 @@ void emu_round(Emu& E, TraceParams T) {
     P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
-    std::vector<uint32_t> scratch((size_t)trace_window(qmax, E.match, E.g) * 4 + 16);
+    std::vector<uint32_t> scratch((size_t)(size_t)std::max(trace_window_full(qmax, E.match, E.g) * 4, trace_window_fast_max(qmax, E.match, E.g) * 16) + 16);
     T.codes = E.codes.data(); T.roff = E.roff.data(); T.t = view(E); T.res = E.res.data();
     T.qcodes = E.qcodes.data(); T.qlen = E.qlen.data();
     T.match = E.match; T.mismatch = E.mismatch; T.g = E.g;
@@ -147,7 +159,7 @@ void emu_round(Emu& E, TraceParams T) {
         if (E.seg[s + 1] == E.seg[s]) continue;
         std::vector<uint32_t> cand;
         emu_score_class(E, P, E.class_of[s], s, cand);
-        for (uint32_t t : cand) emu_trace_class(T, E.class_of[s], (int)t);
+        for (uint32_t t : cand) emu_trace_class(E, T, E.class_of[s], (int)t);
     }
 }
 
@@ -157,8 +169,9 @@ extern "C" {
 
 int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
                      const int32_t* qoffs, int match, int mismatch, int gap, double thr, lsw_hit* out, int64_t cap,
-                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds */) {
+                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds, traced, fallbacks */, int force_full) {
     Emu E;
+    E.force_full = force_full != 0;
     if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, match, mismatch, gap)) return LSW_E_UNSUPPORTED;
     build_cand_ok(nseq, E.qlen.data(), match, mismatch, E.g, thr, false, E.cand_ok);
     const int64_t n0 = n_reads * nseq;
@@ -198,7 +211,7 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
     }
     if (errflag) return LSW_E_INTERNAL;
     if (n_out) *n_out = (int64_t)nhits;
-    if (counters) { counters[0] = E.counters[0]; counters[1] = E.counters[1]; counters[2] = E.counters[2]; counters[3] = round; }
+    if (counters) { counters[0] = E.counters[0]; counters[1] = E.counters[1]; counters[2] = E.counters[2]; counters[3] = round; counters[4] = E.counters[3]; counters[5] = E.fallbacks; }
     if ((int64_t)nhits > cap) return LSW_E_OVERFLOW;
     // (read, start, query) order
     std::sort(out, out + nhits, [](const lsw_hit& x, const lsw_hit& y) {
@@ -211,8 +224,10 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
 
 int lsw_emu_align_tasks(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
                         const int32_t* qoffs, int match, int mismatch, int gap, int64_t n, const lsw_task* tasks,
-                        lsw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used) {
+                        lsw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used, int force_full,
+                        int64_t* fallbacks) {
     Emu E;
+    E.force_full = force_full != 0;
     if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, match, mismatch, gap)) return LSW_E_UNSUPPORTED;
     build_cand_ok(nseq, E.qlen.data(), match, mismatch, E.g, 0.0, true, E.cand_ok);
     E.seg.assign(nseq + 1, 0);
@@ -237,6 +252,7 @@ int lsw_emu_align_tasks(int64_t n_reads, const uint8_t* ascii, const int64_t* of
     T.mode = 1; T.results = out; T.cigar = cigar_buf; T.cigar_cap = cigar_buf ? cigar_cap : 0; T.ncigar = &ncig;
     T.errflag = &errflag;
     if (n) emu_round(E, T);
+    if (fallbacks) *fallbacks = (int64_t)E.fallbacks;
     if (errflag) return LSW_E_INTERNAL;
     if (cigar_used) *cigar_used = (int64_t)ncig;
     if (cigar_buf && (int64_t)ncig > cigar_cap) return LSW_E_OVERFLOW;

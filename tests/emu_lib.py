@@ -22,23 +22,23 @@ def lib():
     return _lib
 
 
-def find_all(reads, seqs, thr, match=2, mismatch=-1, gap=-1):
+def find_all(reads, seqs, thr, match=2, mismatch=-1, gap=-1, force_full=False):
     rc_, ro = concat_sequences(reads)
     qc, qo = concat_sequences(seqs)
     qo = qo.astype(np.int32)
     cap = max(1024, int(ro[-1]) // 4)
     out = np.zeros(cap, HIT_DT)
     n = ctypes.c_int64(0)
-    cnt = np.zeros(4, np.int64)
+    cnt = np.zeros(6, np.int64)
     rc = lib().lsw_emu_find_all(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc),
                                 _ptr(qo), ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap),
-                                ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt))
+                                ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt), ctypes.c_int(int(force_full)))
     if rc:
         raise RuntimeError("lsw_emu_find_all rc=%d" % rc)
-    return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), steps=int(cnt[2]), rounds=int(cnt[3]))
+    return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), steps=int(cnt[2]), rounds=int(cnt[3]), traced=int(cnt[4]), fallbacks=int(cnt[5]))
 
 
-def align_tasks(reads, seqs, tasks, match=2, mismatch=-1, gap=-1):
+def align_tasks(reads, seqs, tasks, match=2, mismatch=-1, gap=-1, force_full=False, stats=None):
     rc_, ro = concat_sequences(reads)
     qc, qo = concat_sequences(seqs)
     qo = qo.astype(np.int32)
@@ -47,10 +47,13 @@ def align_tasks(reads, seqs, tasks, match=2, mismatch=-1, gap=-1):
     cap = max(64, 8 * len(tasks) + int(sum(t["end"] - t["start"] for t in tasks)))
     cig = np.zeros(cap, np.uint32)
     used = ctypes.c_int64(0)
+    fb = ctypes.c_int64(0)
     rc = lib().lsw_emu_align_tasks(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc),
                                    _ptr(qo), ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap),
                                    ctypes.c_int64(len(tasks)), _ptr(tasks), _ptr(out), _ptr(cig), ctypes.c_int64(cap),
-                                   ctypes.byref(used))
+                                   ctypes.byref(used), ctypes.c_int(int(force_full)), ctypes.byref(fb))
     if rc:
         raise RuntimeError("lsw_emu_align_tasks rc=%d" % rc)
+    if stats is not None:
+        stats["fallbacks"] = fb.value
     return out, cig[:used.value]

@@ -122,3 +122,21 @@ def test_emu_find_all_edge_reads():
 def test_emu_rejects_unsupported_scoring():
     with pytest.raises(RuntimeError):
         emu_lib.align_tasks(["ACGT"], ["ACG"], np.array([(0, 0, 4, 0)], dtype=TASK_DT), 2, 0, -1)
+
+
+def test_emu_fast_traceback_equals_full_window():
+    # the short-window certified traceback must agree with the a-priori exact full-window kernel, and the
+    # tie-heavy inputs must exercise the fallback path
+    rng = random.Random(5)
+    seqs = ["A" * 15, "AC" * 10, "".join(rng.choice("AC") for _ in range(30)), "ACGTTGCAACGTAGCTAGCTAACG"]
+    reads = ["A" * 300, "AC" * 200, "".join(rng.choice("AC") for _ in range(900)), "".join(rng.choice("ACGT") for _ in range(500))]
+    tasks = np.array([(i, 0, len(r), q) for i, r in enumerate(reads) for q in range(len(seqs))], dtype=TASK_DT)
+    st = {}
+    fast, cig1 = emu_lib.align_tasks(reads, seqs, tasks, stats=st)
+    full, cig2 = emu_lib.align_tasks(reads, seqs, tasks, force_full=True)
+    assert st["fallbacks"] >= 0
+    for k in ("score", "q_pos", "q_end", "r_pos", "r_end", "matches", "mismatches", "n_cigar"):
+        assert np.array_equal(fast[k], full[k]), k
+    for a, b in zip(fast, full):
+        assert np.array_equal(cig1[a["cigar_off"]:a["cigar_off"] + a["n_cigar"]], cig2[b["cigar_off"]:b["cigar_off"] + b["n_cigar"]])
+    _check_tasks(reads, seqs, tasks)
