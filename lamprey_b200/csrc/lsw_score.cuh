@@ -248,21 +248,36 @@ k_score(const ScoreParams P) {
     Lane L;
     L.n_tasks = L.n_cells = L.n_steps = 0;
 
+    // Warps spread over the sequences of the class (warp w starts on sequence w mod n) and stay on a
+    // sequence until its queue is empty; only then do they move to the fullest remaining queue.
+    // (If every warp chased the fullest queue they would all drain the same one together and
+    // all pay the end-of-queue idle time once per sequence instead of once or twice per launch.)
+    int prefer = (int)((blockIdx.x * SCORE_WARPS + warp) % (unsigned)P.n_class_seqs);
     for (;;) {
-        // choose the sequence of this class with the most unclaimed tasks
         long long bestrem = 0; int bestq = -1;
-        for (int i = lane; i < P.n_class_seqs; i += 32) {
-            const int q = P.class_seqs[i];
+        {
+            const int q = P.class_seqs[prefer];
             const long long cnt = P.seg[q + 1] - P.seg[q];
             const long long hd = (long long)*((volatile unsigned long long*)&P.head[q]);
-            const long long remq = cnt - (hd < cnt ? hd : cnt);
-            if (remq > bestrem) { bestrem = remq; bestq = q; }
+            if (hd < cnt) { bestrem = cnt - hd; bestq = q; }
         }
+        if (bestq < 0) {
+            int besti = -1;
+            for (int i = lane; i < P.n_class_seqs; i += 32) {
+                const int q = P.class_seqs[i];
+                const long long cnt = P.seg[q + 1] - P.seg[q];
+                const long long hd = (long long)*((volatile unsigned long long*)&P.head[q]);
+                const long long remq = cnt - (hd < cnt ? hd : cnt);
+                if (remq > bestrem) { bestrem = remq; bestq = q; besti = i; }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const long long orem = __shfl_xor_sync(0xFFFFFFFFu, bestrem, o);
-            const int oq = __shfl_xor_sync(0xFFFFFFFFu, bestq, o);
-            if (orem > bestrem || (orem == bestrem && oq > bestq)) { bestrem = orem; bestq = oq; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const long long orem = __shfl_xor_sync(0xFFFFFFFFu, bestrem, o);
+                const int oq = __shfl_xor_sync(0xFFFFFFFFu, bestq, o);
+                const int oi = __shfl_xor_sync(0xFFFFFFFFu, besti, o);
+                if (orem > bestrem || (orem == bestrem && oq > bestq)) { bestrem = orem; bestq = oq; besti = oi; }
+            }
+            if (besti >= 0) prefer = besti;
         }
         if (bestq < 0) break;
         const int q = bestq;
