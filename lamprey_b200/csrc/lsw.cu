@@ -94,7 +94,7 @@ struct lsw_ctx {
     DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen;
 
     TaskBuf tb[2], child;
-    DevBuf d_fallback[NCLASS], d_nfallback;
+    DevBuf d_fallback[NCLASS], d_nfallback, d_cand_key[NCLASS], d_cand_sorted[NCLASS], d_cand_key_sorted[NCLASS];
     DevBuf d_res, d_seg[2], d_head, d_cand[NCLASS], d_ncand, d_counters, d_child_flag, d_pos,
            d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_nhits, d_keys[2], d_vals[2], d_err,
            d_results, d_cigar, d_ncigar;
@@ -295,6 +295,7 @@ void fill_score_params(lsw_ctx* ctx, ScoreParams& P, const TaskBuf& cur, int seg
     P.s_match = SC * (ctx->match + ctx->g);
     P.s_mis = SC * (ctx->mismatch + ctx->g);
     P.g = ctx->g;
+    P.match = ctx->match;
 }
 
 void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {
@@ -324,7 +325,12 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
     for (int c = 0; c < NCLASS; c++) {
         ncls[c] = 0; qmax[c] = 0;
         for (int s : ctx->class_seqs[c]) { ncls[c] += h_seg[s + 1] - h_seg[s]; qmax[c] = std::max(qmax[c], ctx->qlen[s]); }
-        if (ncls[c]) { CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4)); CK(ctx->d_fallback[c].ensure((size_t)ncls[c] * 4)); }
+        if (ncls[c]) {
+            CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4)); CK(ctx->d_fallback[c].ensure((size_t)ncls[c] * 4));
+            CK(ctx->d_cand_sorted[c].ensure((size_t)ncls[c] * 4));
+            CK(ctx->d_cand_key[c].ensure((size_t)ncls[c])); CK(ctx->d_cand_key_sorted[c].ensure((size_t)ncls[c]));
+            CK(cudaMemsetAsync(ctx->d_cand_key[c].p, 0xFF, (size_t)ncls[c], ctx->stream));
+        }
     }
     ScoreParams P;
     fill_score_params(ctx, P, cur, segi);
@@ -335,10 +341,25 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             P.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
             P.n_class_seqs = (int)ctx->class_seqs[c].size();
             P.cand = ctx->d_cand[c].as<uint32_t>();
+            P.cand_key = ctx->d_cand_key[c].as<uint8_t>();
             P.ncand = ctx->d_ncand.as<unsigned long long>() + c;
             int rc = launch_score_class(ctx, c, P, ncls[c]);
             if (rc) return rc;
             if (cnt) cnt->score_launches++;
+        }
+    }
+    {
+        // order each class's candidates by traceback window length so the threads of a K2 warp do similar work
+        Span sp(ctx, 2);
+        for (int c = 0; c < NCLASS; c++) {
+            if (!ncls[c]) continue;
+            size_t tmp = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cand_key[c].as<uint8_t>(), ctx->d_cand_key_sorted[c].as<uint8_t>(),
+                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 8, ctx->stream));
+            CK(ctx->d_cubtemp.ensure(tmp));
+            CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtemp.p, tmp, ctx->d_cand_key[c].as<uint8_t>(), ctx->d_cand_key_sorted[c].as<uint8_t>(),
+                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 8, ctx->stream));
+            if (cnt) cnt->other_launches += 2;
         }
     }
     {
@@ -347,7 +368,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             if (!ncls[c]) continue;
             TraceParams T = Tbase;
             T.res = ctx->d_res.as<int2>();
-            T.cand = ctx->d_cand[c].as<uint32_t>();
+            T.cand = ctx->d_cand_sorted[c].as<uint32_t>();
             T.ncand = ctx->d_ncand.as<unsigned long long>() + c;
             T.fallback = ctx->d_fallback[c].as<uint32_t>();
             T.nfallback = ctx->d_nfallback.as<unsigned long long>() + c;
@@ -422,7 +443,7 @@ void lsw_destroy(lsw_ctx* ctx) {
                       &ctx->d_keys[1], &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_err, &ctx->d_results,
                       &ctx->d_cigar, &ctx->d_ncigar};
     for (DevBuf* b : bufs) b->release();
-    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); }
+    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); }
     ctx->d_nfallback.release();
     ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);

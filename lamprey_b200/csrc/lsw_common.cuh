@@ -18,8 +18,13 @@ constexpr int BLOCK_STEPS = 64;        // columns a lane advances between two ta
 constexpr int MAXQ       = 63;         // LSW_MAX_QUERY_LEN
 constexpr int QSTRIDE    = 64;         // bytes per query in the device query-code table
 constexpr int CODE_OTHER = 4;          // read code of any byte that is not A/C/G/T (never matches)
-constexpr int NCODE      = 5;
-constexpr int NIDX       = NCODE * NCODE;   // (code of low-half task, code of high-half task)
+constexpr int CODE_OTHER_HI = 20;      // ... as seen by the task in the HIGH half of a K1 lane (see profile index)
+// K1 profile row of the pair (code of the low-half task, code of the high-half task) is
+//   idx = 4 * lo + hi            with lo in {0..3, 4 = other} and hi in {0..3, 20 = other}:
+//   0..15 ACGT x ACGT, 16..19 lo other, 20/24/28/32 hi other, 36 both other.  The sixteen common
+//   rows are consecutive so that, with a row stride of an odd number of 8-byte words, a half-warp's
+//   LDS.64 requests fall into sixteen distinct bank pairs (no shared-memory bank conflicts).
+constexpr int NIDX       = 37;
 
 // ---- packed s16x2 DPX primitives (VIADDMNMX.S16x2 / VIMNMX3.S16x2 on sm_100a) ------------
 LSW_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) {       // max(a + b, c) per s16 half
@@ -82,11 +87,13 @@ struct ScoreParams {
     int             n_class_seqs;
     const uint8_t*  cand_ok;  // [n_seq][128] 1 if a task with that score can still pass the hit test
     uint32_t*       cand;     // out: tasks that need a traceback
+    uint8_t*        cand_key; // out: their K2 window length (sort key; preset to 0xFF)
     unsigned long long* ncand;
     unsigned long long* counters;   // [0] += tasks, [1] += cells, [2] += lane steps
     int32_t s_match;          // SC * (match + |gap|)
     int32_t s_mis;            // SC * (mismatch + |gap|)
     int32_t g;                // |gap|
+    int32_t match;
 };
 
 struct TraceParams {

@@ -80,7 +80,7 @@ void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& c
     using Lane = ScoreLane<NR>;
     static U4 keep_ge[17], keep_lt[17];
     for (int n = 0; n <= 16; n++) make_keep_masks(keep_ge, keep_lt, n);
-    std::vector<U4> prof((size_t)NIDX * Lane::PROF_STRIDE);
+    std::vector<U2> prof((size_t)NIDX * Lane::PROF_STRIDE);
     const int Q = E.qlen[q];
     Lane::build_profile(P, q, Q, reinterpret_cast<uint32_t*>(prof.data()), 0, 1);
     Lane L;
@@ -91,7 +91,7 @@ void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& c
     bool exhausted = false;
     for (;;) {
         for (int h = 0; h < 2; h++) {
-            if (L.tid[h] >= 0 && L.rem[h] == 0) L.finish(P, h, q, Q, [&](int t) { cand.push_back((uint32_t)t); });
+            if (L.tid[h] >= 0 && L.rem[h] == 0) L.finish(P, h, q, Q, [&](int t, int) { cand.push_back((uint32_t)t); });
             if (L.tid[h] < 0 && !exhausted) {
                 if (head < cnt) L.start(P, h, (int)(base + head++), Q);
                 else exhausted = true;
@@ -147,7 +147,7 @@ void emu_round(Emu& E, TraceParams T) {
     P.codes = E.codes.data(); P.roff = E.roff.data(); P.t = view(E); P.seg = E.seg.data();
     P.res = E.res.data(); P.qcodes = E.qcodes.data(); P.qlen = E.qlen.data();
     P.cand_ok = E.cand_ok.data();
-    P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g;
+    P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g; P.match = E.match;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
     std::vector<uint32_t> scratch((size_t)(size_t)std::max(trace_window_full(qmax, E.match, E.g) * 4, trace_window_fast_max(qmax, E.match, E.g) * 16) + 16);

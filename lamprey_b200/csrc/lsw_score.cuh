@@ -27,11 +27,12 @@
 namespace lsw {
 
 struct U4 { uint32_t x, y, z, w; };
+struct U2 { uint32_t x, y; };
 
 template <int NR>
 struct ScoreLane {
     static_assert(NR % 4 == 0 && NR <= 64, "rows are kept in registers, 4 per profile load");
-    static constexpr int PROF_STRIDE = NR / 4 + 1;      // uint4 per profile row (+1 pad: bank spread)
+    static constexpr int PROF_STRIDE = NR / 2 + 1;      // 8-byte words per profile row: odd, see NIDX
 
     uint32_t M[NR];        // 256 * H of the previous column, two tasks packed
     uint32_t K[NR];        // running max of (256*(H+g) + step) over the current block
@@ -43,6 +44,7 @@ struct ScoreLane {
     uint32_t best[2];      // ((H+g) << 16) | (row << 8) | step of the best cell so far
     int32_t  bestc[2];     // its DP column
     int32_t  len[2];       // slice length
+    U4       nx[2];        // read codes of the next 16 steps, fetched one chunk ahead
     unsigned long long n_tasks, n_cells, n_steps;
 
     LSW_HD void init() {
@@ -52,22 +54,30 @@ struct ScoreLane {
         rem[0] = rem[1] = 0; begin[0] = begin[1] = 0;
         pos[0] = pos[1] = 0; cbase[0] = cbase[1] = 0;
         best[0] = best[1] = 0; bestc[0] = bestc[1] = 0; len[0] = len[1] = 0;
+        nx[0].x = nx[0].y = nx[0].z = nx[0].w = 0;
+        nx[1] = nx[0];
     }
 
-    // Build the packed profile of sequence q for this warp: prof[idx][r/4] holds rows r..r+3 of
-    // (s''(code_lo, q[r]), s''(code_hi, q[r])).  `lane`/`nlanes` split the work.
+    // Build the packed profile of sequence q for this warp: row idx (see NIDX) holds, for every query
+    // row r, (s''(code_lo, q[r]), s''(code_hi, q[r])).  `lane`/`nlanes` split the work.
     static LSW_HD void build_profile(const ScoreParams& P, int q, int Q, uint32_t* prof32, int lane, int nlanes) {
         const uint8_t* qc = P.qcodes + (size_t)q * QSTRIDE;
         for (int e = lane; e < NIDX * NR; e += nlanes) {
             const int idx = e / NR, r = e - idx * NR;
-            const int cl = idx / NCODE, ch = idx - cl * NCODE;
+            int cl, ch;                                   // 0..3, or 4 = other
+            if (idx < 16) { cl = idx >> 2; ch = idx & 3; }
+            else if (idx < 20) { cl = 4; ch = idx - 16; }
+            else if (idx == 36) { cl = 4; ch = 4; }
+            else { cl = (idx - 20) >> 2; ch = 4; }        // 20, 24, 28, 32 (other values are never indexed)
             int lo = P.s_mis, hi = P.s_mis;
-            if (r < Q) {
+            if (r < Q && cl < 4) {
                 const int qb = qc[r];
-                if (cl == qb) lo = P.s_match;      // CODE_OTHER (4) never equals a query code 0..3
+                if (cl == qb) lo = P.s_match;
                 if (ch == qb) hi = P.s_match;
+            } else if (r < Q) {
+                if (ch == qc[r]) hi = P.s_match;
             }
-            prof32[idx * (PROF_STRIDE * 4) + r] = ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
+            prof32[idx * (PROF_STRIDE * 2) + r] = ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
         }
     }
 
@@ -87,6 +97,7 @@ struct ScoreLane {
         const uint32_t keep = h ? 0x0000FFFFu : 0xFFFF0000u;
 #pragma unroll
         for (int r = 0; r < NR; r++) M[r] &= keep;     // zero boundary column for this half
+        nx[h] = *reinterpret_cast<const U4*>(P.codes + pos[h]);
         n_tasks += 1;
         n_cells += (unsigned long long)(b - a) * (unsigned long long)Q;
     }
@@ -106,16 +117,21 @@ struct ScoreLane {
             col = bestc[h];
         }
         P.res[t] = make_int2(score | (row << 16), col);
-        if (P.cand_ok[(size_t)q * 128 + score]) push(t);
+        if (P.cand_ok[(size_t)q * 128 + score]) {
+            // sort key for K2: the number of window columns its traceback will fill (similar work per warp)
+            int w = score > 0 ? row + (P.match * row - score) / P.g + 8 : 0;
+            if (w > col) w = col;
+            push(t, w);
+        }
         tid[h] = -1;
     }
 
     // One DP column for both halves.  prow: profile row of this column's (code_lo, code_hi).
-    LSW_HD void column(const U4* prow, uint32_t tvec, uint32_t G2, uint32_t FLOOR2) {
+    LSW_HD void column(const U2* prow, uint32_t tvec, uint32_t G2, uint32_t FLOOR2) {
         uint32_t d = 0, u = 0;
 #pragma unroll
-        for (int r4 = 0; r4 < NR / 4; r4++) {
-            const U4 s = prow[r4];
+        for (int r2 = 0; r2 < NR / 2; r2++) {
+            const U2 s = prow[r2];
 #define LSW_ROW(R, S)                                            \
             {                                                    \
                 const uint32_t mold = M[R];                      \
@@ -126,17 +142,15 @@ struct ScoreLane {
                 K[R] = addmax2(hh, tvec, K[R]);                  \
                 d = mold;                                        \
             }
-            LSW_ROW(r4 * 4 + 0, s.x)
-            LSW_ROW(r4 * 4 + 1, s.y)
-            LSW_ROW(r4 * 4 + 2, s.z)
-            LSW_ROW(r4 * 4 + 3, s.w)
+            LSW_ROW(r2 * 2 + 0, s.x)
+            LSW_ROW(r2 * 2 + 1, s.y)
 #undef LSW_ROW
         }
     }
 
     // BLOCK_STEPS columns for both halves, then fold the block's arg-max into the task state.
     // keep_ge[n]: bytes j >= n of a 16-byte chunk are live; keep_lt[n]: bytes j < n are live.
-    LSW_HD void run_block(const ScoreParams& P, const U4* prof, const U4* keep_ge, const U4* keep_lt, int Q) {
+    LSW_HD void run_block(const ScoreParams& P, const U2* prof, const U4* keep_ge, const U4* keep_lt, int Q) {
         const uint32_t G2 = (uint32_t)(P.g * SC) * 0x00010001u;
         const uint32_t FLOOR2 = G2;
         int end[2];
@@ -155,12 +169,18 @@ struct ScoreLane {
             U4 c[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                U4 v; v.x = v.y = v.z = v.w = 0;
-                if (tid[h] >= 0) v = *reinterpret_cast<const U4*>(P.codes + pos[h] + 16 * k);
+                U4 v = nx[h];
+                // fetch the next chunk now (the first chunk of the next block when k == 3: the buffer is
+                // padded, and start() reloads if the half switches task); its latency hides behind 16 columns
+                if (tid[h] >= 0) nx[h] = *reinterpret_cast<const U4*>(P.codes + pos[h] + 16 * (k + 1));
                 int nl = begin[h] - 16 * k; nl = nl < 0 ? 0 : (nl > 16 ? 16 : nl);
                 int ne = end[h] - 16 * k;   ne = ne < 0 ? 0 : (ne > 16 ? 16 : ne);
                 const U4 kg = keep_ge[nl], kl = keep_lt[ne];
-                const uint32_t OTH = 0x01010101u * CODE_OTHER;
+                const uint32_t OTH = 0x01010101u * (h ? CODE_OTHER_HI : CODE_OTHER);
+                if (h) {      // a real non-ACGT base is stored as 4; the high half indexes it as 20
+                    v.x |= (v.x & 0x04040404u) << 2; v.y |= (v.y & 0x04040404u) << 2;
+                    v.z |= (v.z & 0x04040404u) << 2; v.w |= (v.w & 0x04040404u) << 2;
+                }
                 uint32_t kp;
                 kp = kg.x & kl.x; v.x = (v.x & kp) | (OTH & ~kp);
                 kp = kg.y & kl.y; v.y = (v.y & kp) | (OTH & ~kp);
@@ -170,7 +190,7 @@ struct ScoreLane {
             }
 #pragma unroll 1
             for (int w = 0; w < 4; w++) {
-                const uint32_t idx4 = c[0].x * NCODE + c[1].x;       // four (lo, hi) code pairs, bytes <= 24
+                const uint32_t idx4 = c[0].x * 4u + c[1].x;          // four profile row indices, bytes <= 36
                 c[0].x = c[0].y; c[0].y = c[0].z; c[0].z = c[0].w;
                 c[1].x = c[1].y; c[1].y = c[1].z; c[1].z = c[1].w;
 #pragma unroll
@@ -238,9 +258,9 @@ k_score(const ScoreParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     U4* keep_ge = reinterpret_cast<U4*>(smem_raw);
     U4* keep_lt = keep_ge + 17;
-    U4* prof_all = keep_lt + 17;
+    U2* prof_all = reinterpret_cast<U2*>(keep_lt + 17);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    U4* prof = prof_all + (size_t)warp * NIDX * Lane::PROF_STRIDE;
+    U2* prof = prof_all + (size_t)warp * NIDX * Lane::PROF_STRIDE;
 
     if (threadIdx.x < 17) make_keep_masks(keep_ge, keep_lt, threadIdx.x);
     __syncthreads();
@@ -295,9 +315,10 @@ k_score(const ScoreParams P) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 if (L.tid[h] >= 0 && L.rem[h] == 0)
-                    L.finish(P, h, q, Q, [&](int t) {
+                    L.finish(P, h, q, Q, [&](int t, int key) {
                         const unsigned long long i = atomicAdd(P.ncand, 1ull);
                         P.cand[i] = (uint32_t)t;
+                        P.cand_key[i] = (uint8_t)key;
                     });
                 if (L.tid[h] < 0 && !exhausted) {
                     const unsigned long long i = atomicAdd(&P.head[q], 1ull);
@@ -320,7 +341,7 @@ k_score(const ScoreParams P) {
 
 template <int NR>
 inline size_t score_smem_bytes() {
-    return sizeof(U4) * (34 + (size_t)SCORE_WARPS * NIDX * ScoreLane<NR>::PROF_STRIDE);
+    return sizeof(U4) * 34 + sizeof(U2) * ((size_t)SCORE_WARPS * NIDX * ScoreLane<NR>::PROF_STRIDE);
 }
 #endif  // __CUDACC__
 
