@@ -245,25 +245,27 @@ int launch_score_class(lsw_ctx* ctx, int c, const ScoreParams& P, int64_t n) {
 
 template <int NR, int NR2>
 int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
-    // short-window kernel over every candidate of the class
+    // short-window kernel over every candidate of the class: one lane per PAIR of candidates
+    const size_t smem = trace_smem_bytes<NR>();
+    CK(cudaFuncSetAttribute(k_trace_fast<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_fast<NR>, TRACE_THREADS, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_fast<NR>, TRACE_THREADS, smem));
     if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
-    const int blocks = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * occ);
+    const int blocks = grid_for((n_class_tasks + 1) / 2, TRACE_THREADS, ctx->num_sms * occ);
     const int64_t threads = (int64_t)blocks * TRACE_THREADS;
     const int64_t Wf = trace_window_fast_max(qmax, ctx->match, ctx->g);
-    // full-window kernel over the (normally empty) fallback list
+    // full-window kernel over the (normally empty) fallback list: one thread per task
     int occ2 = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_trace_full<NR2>, TRACE_THREADS, 0));
     if (occ2 < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
     const int blocks2 = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * std::min(occ2, 2));
     const int64_t threads2 = (int64_t)blocks2 * TRACE_THREADS;
     const int64_t W = trace_window_full(qmax, ctx->match, ctx->g);
-    const size_t need = std::max((size_t)threads * (size_t)Wf * (NR / 4) * 4, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
+    const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * (NR / 2) * 4, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
     CK(ctx->d_scratch.ensure(need));
     P.scratch = ctx->d_scratch.as<uint32_t>();
     P.scratch_stride = threads;
-    k_trace_fast<NR><<<blocks, TRACE_THREADS, 0, ctx->stream>>>(P);
+    k_trace_fast<NR><<<blocks, TRACE_THREADS, smem, ctx->stream>>>(P);
     CK(cudaGetLastError());
     P.scratch_stride = threads2;
     k_trace_full<NR2><<<blocks2, TRACE_THREADS, 0, ctx->stream>>>(P);
@@ -308,6 +310,7 @@ void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {
     T.qlen = ctx->d_qlen.as<int32_t>();
     T.match = ctx->match; T.mismatch = ctx->mismatch; T.g = ctx->g;
     T.errflag = ctx->d_err.as<int32_t>();
+    T.debug = getenv("LSW_K2_DEBUG") ? atoi(getenv("LSW_K2_DEBUG")) : 0;
 }
 
 // Runs K1 then K2 for every class over the task list `cur` (segments h_seg on the host).
@@ -328,8 +331,8 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         if (ncls[c]) {
             CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4)); CK(ctx->d_fallback[c].ensure((size_t)ncls[c] * 4));
             CK(ctx->d_cand_sorted[c].ensure((size_t)ncls[c] * 4));
-            CK(ctx->d_cand_key[c].ensure((size_t)ncls[c])); CK(ctx->d_cand_key_sorted[c].ensure((size_t)ncls[c]));
-            CK(cudaMemsetAsync(ctx->d_cand_key[c].p, 0xFF, (size_t)ncls[c], ctx->stream));
+            CK(ctx->d_cand_key[c].ensure((size_t)ncls[c] * 2)); CK(ctx->d_cand_key_sorted[c].ensure((size_t)ncls[c] * 2));
+            CK(cudaMemsetAsync(ctx->d_cand_key[c].p, 0xFF, (size_t)ncls[c] * 2, ctx->stream));
         }
     }
     ScoreParams P;
@@ -341,7 +344,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             P.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
             P.n_class_seqs = (int)ctx->class_seqs[c].size();
             P.cand = ctx->d_cand[c].as<uint32_t>();
-            P.cand_key = ctx->d_cand_key[c].as<uint8_t>();
+            P.cand_key = ctx->d_cand_key[c].as<uint16_t>();
             P.ncand = ctx->d_ncand.as<unsigned long long>() + c;
             int rc = launch_score_class(ctx, c, P, ncls[c]);
             if (rc) return rc;
@@ -349,18 +352,20 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         }
     }
     {
-        // order each class's candidates by traceback window length so the threads of a K2 warp do similar work
+        // order each class's candidates by (sequence, traceback window length): K2 warps serve one sequence at a
+        // time and their lanes then fill windows of similar length
         Span sp(ctx, 2);
         for (int c = 0; c < NCLASS; c++) {
             if (!ncls[c]) continue;
             size_t tmp = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cand_key[c].as<uint8_t>(), ctx->d_cand_key_sorted[c].as<uint8_t>(),
-                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 8, ctx->stream));
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cand_key[c].as<uint16_t>(), ctx->d_cand_key_sorted[c].as<uint16_t>(),
+                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 16, ctx->stream));
             CK(ctx->d_cubtemp.ensure(tmp));
-            CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtemp.p, tmp, ctx->d_cand_key[c].as<uint8_t>(), ctx->d_cand_key_sorted[c].as<uint8_t>(),
-                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 8, ctx->stream));
+            CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtemp.p, tmp, ctx->d_cand_key[c].as<uint16_t>(), ctx->d_cand_key_sorted[c].as<uint16_t>(),
+                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 16, ctx->stream));
             if (cnt) cnt->other_launches += 2;
         }
+        CK(cudaMemsetAsync(ctx->d_head.p, 0, (size_t)ctx->nseq * 8, ctx->stream));     // K2 reuses the per-sequence queue heads
     }
     {
         Span sp(ctx, 1);
@@ -369,6 +374,10 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             TraceParams T = Tbase;
             T.res = ctx->d_res.as<int2>();
             T.cand = ctx->d_cand_sorted[c].as<uint32_t>();
+            T.cand_key = ctx->d_cand_key_sorted[c].as<uint16_t>();
+            T.head = ctx->d_head.as<unsigned long long>();
+            T.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
+            T.n_class_seqs = (int)ctx->class_seqs[c].size();
             T.ncand = ctx->d_ncand.as<unsigned long long>() + c;
             T.fallback = ctx->d_fallback[c].as<uint32_t>();
             T.nfallback = ctx->d_nfallback.as<unsigned long long>() + c;
@@ -528,7 +537,7 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     CK(cudaSetDevice(ctx->device));
     ctx->h_roff.assign((size_t)n + 1, 0);
     ctx->h_rlen.assign((size_t)n, 0);
-    int64_t d = 0;
+    int64_t d = 256;                        // front pad: K2 reads a few codes before a window start (masked)
     for (int64_t i = 0; i < n; i++) {
         const int64_t len = offs[i + 1] - offs[i];
         if (len < 0 || len >= (1ll << 27)) return fail(ctx, LSW_E_ARG, "read length must be in [0, 2^27)");
@@ -553,6 +562,7 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     CK(cudaMemcpyAsync(ctx->d_roff.p, ctx->h_roff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (n) CK(cudaMemcpyAsync(ctx->d_rlen.p, ctx->h_rlen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_codes.as<uint8_t>() + d, CODE_OTHER, 256, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_codes.as<uint8_t>(), CODE_OTHER, 256, ctx->stream));
     if (n) {
         const int blocks = grid_for(n * 32, 256, ctx->num_sms * 16);
         k_encode_reads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ascii.as<uint8_t>(), ctx->d_offs_in.as<int64_t>(),

@@ -87,7 +87,7 @@ struct ScoreParams {
     int             n_class_seqs;
     const uint8_t*  cand_ok;  // [n_seq][128] 1 if a task with that score can still pass the hit test
     uint32_t*       cand;     // out: tasks that need a traceback
-    uint8_t*        cand_key; // out: their K2 window length (sort key; preset to 0xFF)
+    uint16_t*       cand_key; // out: sequence << 8 | K2 window length (sort key; preset to 0xFFFF)
     unsigned long long* ncand;
     unsigned long long* counters;   // [0] += tasks, [1] += cells, [2] += lane steps
     int32_t s_match;          // SC * (match + |gap|)
@@ -103,8 +103,12 @@ struct TraceParams {
     const int2*     res;
     const uint8_t*  qcodes;
     const int32_t*  qlen;
-    const uint32_t* cand;
+    const uint32_t* cand;         // candidate task ids, sorted by (sequence, window length)
+    const uint16_t* cand_key;     // their sort keys: sequence << 8 | window length (0xFFFF = padding)
     const unsigned long long* ncand;
+    unsigned long long* head;     // [n_seq] next unclaimed candidate of each sequence
+    const int32_t*  class_seqs;   // sequences of this launch's register-row class
+    int             n_class_seqs;
     uint32_t*       fallback;     // tasks the short-window kernel could not prove exact
     unsigned long long* nfallback;
     uint32_t*       scratch;      // direction bits, [window col][word][thread]
@@ -125,6 +129,7 @@ struct TraceParams {
     int64_t cigar_cap;
     unsigned long long* ncigar;
     int32_t* errflag;
+    int32_t debug;            // timing experiments only (LSW_K2_DEBUG): 1 = fill only, 2 = walk only
 };
 
 }  // namespace lsw

@@ -61,7 +61,7 @@ bool setup(Emu& E, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, i
     }
     E.roff.assign((size_t)n_reads + 1, 0);
     E.rlen.assign((size_t)n_reads, 0);
-    int64_t d = 0;
+    int64_t d = 256;
     for (int64_t i = 0; i < n_reads; i++) {
         const int64_t len = offs[i + 1] - offs[i];
         E.roff[i] = d; E.rlen[i] = (int32_t)len;
@@ -114,21 +114,31 @@ void emu_score_class(Emu& E, const ScoreParams& P, int c, int q, std::vector<uin
 }
 
 template <int NR, int NR2>
-void emu_trace_one(Emu& E, const TraceParams& T, int t) {
-    E.counters[3]++;
-    if (E.force_full || !trace_fast_task<NR>(T, t, 0)) {
-        E.fallbacks++;
-        trace_full_task<NR2>(T, t, 0);
+void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, const std::vector<uint32_t>& cand) {
+    using Lane = TraceLane<NR>;
+    std::vector<U2> prof((size_t)NIDX * Lane::PROF_STRIDE);
+    ScoreLane<NR>::build_profile(P, q, E.qlen[q], reinterpret_cast<uint32_t*>(prof.data()), 0, 1);
+    Lane L;
+    for (size_t i = 0; i < cand.size(); i += 2) {
+        const int t0 = (int)cand[i], t1 = i + 1 < cand.size() ? (int)cand[i + 1] : -1;
+        E.counters[3] += t1 >= 0 ? 2 : 1;
+        if (E.force_full) {
+            E.fallbacks += t1 >= 0 ? 2 : 1;
+            trace_full_task<NR2>(T, t0, 0);
+            if (t1 >= 0) trace_full_task<NR2>(T, t1, 0);
+        } else {
+            L.run_pair(T, prof.data(), t0, t1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
+        }
     }
 }
 
-void emu_trace_class(Emu& E, const TraceParams& T, int c, int t) {
+void emu_trace_class(Emu& E, const TraceParams& T, const ScoreParams& P, int c, int q, const std::vector<uint32_t>& cand) {
     switch (CLASS_NR[c]) {
-        case 16: emu_trace_one<16, 16>(E, T, t); break;
-        case 24: emu_trace_one<24, 32>(E, T, t); break;
-        case 32: emu_trace_one<32, 32>(E, T, t); break;
-        case 48: emu_trace_one<48, 48>(E, T, t); break;
-        default: emu_trace_one<64, 64>(E, T, t); break;
+        case 16: emu_trace_seq<16, 16>(E, T, P, q, cand); break;
+        case 24: emu_trace_seq<24, 32>(E, T, P, q, cand); break;
+        case 32: emu_trace_seq<32, 32>(E, T, P, q, cand); break;
+        case 48: emu_trace_seq<48, 48>(E, T, P, q, cand); break;
+        default: emu_trace_seq<64, 64>(E, T, P, q, cand); break;
     }
 }
 
@@ -150,7 +160,7 @@ void emu_round(Emu& E, TraceParams T) {
     P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g; P.match = E.match;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
-    std::vector<uint32_t> scratch((size_t)(size_t)std::max(trace_window_full(qmax, E.match, E.g) * 4, trace_window_fast_max(qmax, E.match, E.g) * 16) + 16);
+    std::vector<uint32_t> scratch((size_t)(size_t)std::max(trace_window_full(qmax, E.match, E.g) * 4, (trace_window_fast_max(qmax, E.match, E.g) + 4) * 32) + 16);
     T.codes = E.codes.data(); T.roff = E.roff.data(); T.t = view(E); T.res = E.res.data();
     T.qcodes = E.qcodes.data(); T.qlen = E.qlen.data();
     T.match = E.match; T.mismatch = E.mismatch; T.g = E.g;
@@ -159,7 +169,7 @@ void emu_round(Emu& E, TraceParams T) {
         if (E.seg[s + 1] == E.seg[s]) continue;
         std::vector<uint32_t> cand;
         emu_score_class(E, P, E.class_of[s], s, cand);
-        for (uint32_t t : cand) emu_trace_class(E, T, E.class_of[s], (int)t);
+        emu_trace_class(E, T, P, E.class_of[s], s, cand);
     }
 }
 

@@ -318,7 +318,7 @@ k_score(const ScoreParams P) {
                     L.finish(P, h, q, Q, [&](int t, int key) {
                         const unsigned long long i = atomicAdd(P.ncand, 1ull);
                         P.cand[i] = (uint32_t)t;
-                        P.cand_key[i] = (uint8_t)key;
+                        P.cand_key[i] = (uint16_t)(((uint32_t)q << 8) | (uint32_t)key);
                     });
                 if (L.tid[h] < 0 && !exhausted) {
                     const unsigned long long i = atomicAdd(&P.head[q], 1ull);

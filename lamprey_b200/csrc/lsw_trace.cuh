@@ -34,6 +34,7 @@
 //      boundary and needs no argument.
 #pragma once
 #include "lsw_common.cuh"
+#include "lsw_score.cuh"
 #include "../../include/lsw.h"
 
 namespace lsw {
@@ -227,156 +228,269 @@ LSW_HD void trace_full_task(const TraceParams& P, const int t, const int64_t slo
 }
 
 // ======================= short-window kernel with lazy, certified op evaluation ==============
-struct FastWalk {
-    const uint32_t* scr; int64_t stride, slot;
-    int words;               // 32-bit words per window column (4 rows per word)
-    int c0;                  // DP column of the zero boundary left of the window (0 = slice start)
-    const uint8_t* qc; const uint8_t* ref;
-    int match, mismatch, g;
-    int budget;
+// Packed like K1: one LANE owns a PAIR of candidate tasks of the same sequence (low / high s16 half),
+// all lanes of a warp serve one sequence whose profile sits in shared memory.  Per pair:
+//   fill   n = max(window lengths) columns of VALUES with the K1 recurrence (2 DPX + 1 add per two
+//          cells, no arg-max key), both windows right-aligned on their own max_col; after every
+//          column the H bytes of both tasks go to scratch, two rows of both tasks per 32-bit word;
+//   walk   each task in turn: a flat state machine, one cell evaluation per iteration, that applies
+//          the op rule lazily and proves every decision (see the file header).
+template <int NR>
+struct TraceLane {
+    static_assert(NR % 4 == 0 && NR <= 64, "rows in registers");
+    static constexpr int PROF_STRIDE = NR / 2 + 1;
+    static constexpr int WORDS = NR / 2;          // scratch words per window column (both tasks)
+    static constexpr int MAXD = 24;               // nesting limit of run-flag evaluations
 
-    LSW_HD int H(int r, int cl) const {          // windowed value; r in [0, Q], cl in [0, ncols]
-        if (r <= 0 || cl <= 0) return 0;
-        const uint32_t w = scr[((int64_t)(cl - 1) * words + ((r - 1) >> 2)) * stride + slot];
-        return (int)((w >> (8 * ((r - 1) & 3))) & 0xFFu);
+    uint32_t M[NR];
+
+    struct Half {
+        TaskView v;
+        int t;                 // task index, -1 = none
+        int c0, ncols, first;  // zero-boundary column, window columns, first live step of the shared loop
+    };
+
+    LSW_HD static void setup(const TraceParams& P, Half& hf, int t) {
+        hf.t = t; hf.c0 = 0; hf.ncols = 0; hf.first = 0;
+        if (t < 0) return;
+        hf.v = load_task(P, t);
+        if (hf.v.score > 0) {
+            const int W = trace_window_fast(hf.v.row, hf.v.score, P.match, P.g);
+            hf.c0 = hf.v.col > W ? hf.v.col - W : 0;
+            hf.ncols = hf.v.col - hf.c0;
+        }
     }
-    LSW_HD bool cert(int r, int cl, int h) const {
-        if (c0 == 0 || r <= 0) return true;      // true boundary / row 0
-        const int num = match * r - h - 1;
-        const int need = r + (num >= 0 ? num / g : -1);
+
+    // windowed value of task h at (r, cl): r in [0, Q], cl in [0, ncols]
+    LSW_HD static int Hval(const TraceParams& P, const Half& hf, int h, int64_t slot, int r, int cl) {
+        if (r <= 0 || cl <= 0) return 0;
+        const int s = hf.first + cl - 1;
+        const uint32_t w = P.scratch[((int64_t)s * WORDS + ((r - 1) >> 1)) * P.scratch_stride + slot];
+        return (int)((w >> (8 * (((r - 1) & 1) + 2 * h))) & 0xFFu);
+    }
+    LSW_HD static bool cert(const TraceParams& P, const Half& hf, int r, int cl, int h) {
+        if (hf.c0 == 0 || r <= 0) return true;             // true boundary / row 0
+        const int num = P.match * r - h - 1;                 // >= -1
+        const int need = r + (P.g == 1 ? num : (num >= 0 ? num / P.g : -1));
         return cl >= need;
     }
-    // op of the positive cell (r0, cl0) whose windowed value is known to be exact; OPC_FAIL = cannot
-    // prove.  The run flags need the op of the left / up neighbour, found by the same rule: an
-    // explicit frame stack instead of device recursion.  state 0 = fresh, 1 = waiting for the left
-    // neighbour's op, 2 = waiting for the up neighbour's op.
-    static constexpr int MAXD = 24;
-    LSW_HD int op_at(int r0, int cl0) {
-        int fr[MAXD], fc[MAXD], fs[MAXD];
-        int sp = 0, ret = OPC_NONE;
-        fr[0] = r0; fc[0] = cl0; fs[0] = 0;
-        while (sp >= 0) {
-            const int r = fr[sp], cl = fc[sp], st = fs[sp];
-            const int h = H(r, cl);
-            const int hl = H(r, cl - 1), hu = H(r - 1, cl), hd = H(r - 1, cl - 1);
-            const int s = (qc[r - 1] == ref[c0 + cl - 1]) ? match : mismatch;
-            const bool tieL = (h == hl - g), tieU = (h == hu - g), tieM = (h == hd + s);
-            if (st == 0) {
-                if (--budget < 0) return OPC_FAIL;
+
+    // returns false if the task must go to the fallback list
+    LSW_HD bool walk(const TraceParams& P, const Half& hf, int h, int64_t slot, PathOut& po) {
+        const TaskView& v = hf.v;
+        int r = v.row, cl = hf.ncols;
+        if (Hval(P, hf, h, slot, r, cl) != v.score) return false;   // window too short to reproduce the best cell
+        int depth = 0, ret = OPC_NONE, last = 0;
+        uint32_t mv = 0;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
+        unsigned long long st = 0;        // 2 bits per level: 0 fresh, 1 waiting for left's op, 2 waiting for up's op
+        int budget = 6 * (v.row + hf.ncols) + 64;
+        const bool keep_ops = (P.mode == 1);
+        for (;;) {
+            const int state = (int)((st >> (2 * depth)) & 3ull);
+            const int hc = Hval(P, hf, h, slot, r, cl);
+            if (depth == 0 && state == 0 && (hc == 0 || r <= 0 || cl <= 0)) break;      // path ends at the first zero
+            const int hl = Hval(P, hf, h, slot, r, cl - 1), hu = Hval(P, hf, h, slot, r - 1, cl);
+            const int hd = Hval(P, hf, h, slot, r - 1, cl - 1);
+            const int sub = (v.qc[r - 1] == v.ref[hf.c0 + cl - 1]) ? P.match : P.mismatch;
+            const bool tieL = (hc == hl - P.g), tieU = (hc == hu - P.g), tieM = (hc == hd + sub);
+            int res = -2;                 // -2: descend (push), otherwise the op of this cell
+            bool pushU = false;
+            if (state == 0) {
+                if (--budget < 0) return false;
                 // a windowed non-tie is only trustworthy if that neighbour's value is certified
-                if (!tieL && !cert(r, cl - 1, hl)) return OPC_FAIL;
-                if (!tieU && !cert(r - 1, cl, hu)) return OPC_FAIL;
-                if (!tieM && !cert(r - 1, cl - 1, hd)) return OPC_FAIL;
-                if (!tieL && !tieU && !tieM) return OPC_FAIL;     // cannot happen for an exact positive cell
+                if (!tieL && !cert(P, hf, r, cl - 1, hl)) return false;
+                if (!tieU && !cert(P, hf, r - 1, cl, hu)) return false;
+                if (!tieM && !cert(P, hf, r - 1, cl - 1, hd)) return false;
+                if (!tieL && !tieU && !tieM) return false;          // cannot happen for an exact positive cell
                 if (tieL) {
-                    if (!tieU && !tieM) { ret = OPC_D; sp--; continue; }
-                    if (sp + 1 >= MAXD) return OPC_FAIL;
-                    fs[sp] = 1;                                  // left value is h + g > 0 and exact (tie)
-                    sp++; fr[sp] = r; fc[sp] = cl - 1; fs[sp] = 0;
-                    continue;
-                }
+                    if (!tieU && !tieM) res = OPC_D;
+                    // else: need left's op (left value is hc + g > 0 and exact because of the tie)
+                } else if (tieU) {
+                    if (!tieM) res = OPC_I; else pushU = true;
+                } else res = OPC_M;
+            } else if (state == 1) {                                // left's op is in ret
+                if (ret == OPC_D) res = OPC_D;
+                else if (tieU) pushU = true;
+                else res = tieM ? OPC_M : OPC_D;
+            } else {                                                // up's op is in ret
+                if (ret == OPC_I) res = OPC_I;
+                else res = tieM ? OPC_M : (tieL ? OPC_D : OPC_I);
             }
-            if (st == 1 && ret == OPC_D) { sp--; continue; }      // left is a 'd' cell: d-run (ret stays D)
-            if (st != 2 && tieU) {
-                if (!tieM && !tieL) { ret = OPC_I; sp--; continue; }
-                if (sp + 1 >= MAXD) return OPC_FAIL;
-                fs[sp] = 2;                                      // up value is h + g > 0 and exact (tie)
-                sp++; fr[sp] = r - 1; fc[sp] = cl; fs[sp] = 0;
+            if (res == -2) {                                        // descend to a neighbour
+                if (depth + 1 >= MAXD) return false;
+                const unsigned long long mask = ~(3ull << (2 * depth));
+                st = (st & mask) | ((unsigned long long)(pushU ? 2 : 1) << (2 * depth));
+                depth++;
+                st &= ~(3ull << (2 * depth));
+                if (pushU) { mv |= 1u << depth; r -= 1; } else { mv &= ~(1u << depth); cl -= 1; }
                 continue;
             }
-            if (st == 2 && ret == OPC_I) { sp--; continue; }      // up is an 'i' cell: i-run (ret stays I)
-            ret = tieM ? OPC_M : (tieL ? OPC_D : OPC_I);
-            sp--;
+            ret = res;
+            if (depth > 0) {                                        // return to the cell that asked
+                if ((mv >> depth) & 1u) r += 1; else cl += 1;
+                depth--;
+                continue;
+            }
+            // a path cell is resolved
+            if (res != last) { po.nrun++; last = res; }
+            if (keep_ops && !po.push(res)) return false;
+            if (res == OPC_M) { if (sub == P.match) po.m++; else po.x++; r--; cl--; }
+            else if (res == OPC_I) { po.x++; r--; }
+            else { po.x++; cl--; }
+            st = 0;
         }
-        return ret;
+        if (cl == 0 && hf.c0 > 0 && r > 0) return false;            // ran into the artificial boundary
+        po.q_pos = r;
+        po.r_pos = hf.c0 + cl;
+        return true;
+    }
+
+    // fill + walk for the pair (t0, t1); t1 may be -1.  fb(t): push a task to the fallback list.
+    template <class Fallback>
+    LSW_HD void run_pair(const TraceParams& P, const U2* prof, int t0, int t1, int64_t slot, Fallback fb) {
+        Half hf[2];
+        setup(P, hf[0], t0);
+        setup(P, hf[1], t1);
+        const int n = hf[0].ncols > hf[1].ncols ? hf[0].ncols : hf[1].ncols;
+        hf[0].first = n - hf[0].ncols;
+        hf[1].first = n - hf[1].ncols;
+
+        if (n > 0) {
+            const uint32_t G2 = (uint32_t)(P.g * SC) * 0x00010001u;
+#pragma unroll
+            for (int r = 0; r < NR; r++) M[r] = 0;
+            // byte address of the read code of shared step 0 for each task (may lie before the window: masked)
+            int64_t addr[2]; int lead[2]; uint32_t prev[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                addr[h] = 0; lead[h] = 0; prev[h] = 0;
+                if (hf[h].ncols > 0) {
+                    const int64_t a0 = (hf[h].v.ref - P.codes) + hf[h].c0 - hf[h].first;
+                    lead[h] = (int)(a0 & 3);
+                    addr[h] = a0 - lead[h];
+                    prev[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h]);
+                }
+            }
+#pragma unroll 1
+            for (int s0 = 0; s0 < n; s0 += 4) {
+                uint32_t c[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    uint32_t v = 0;
+                    if (hf[h].ncols > 0) {
+                        const uint32_t nxt = *reinterpret_cast<const uint32_t*>(P.codes + addr[h] + s0 + 4);
+                        v = prmt(prev[h], nxt, 0x3210u + 0x1111u * (uint32_t)lead[h]);    // bytes of steps s0..s0+3
+                        prev[h] = nxt;
+                    }
+                    if (h) v |= (v & 0x04040404u) << 2;          // stored 'other' (4) is indexed as 20 by the high half
+                    int nl = hf[h].first - s0; nl = nl < 0 ? 0 : (nl > 4 ? 4 : nl);          // dead steps before the window
+                    const uint32_t kp = (hf[h].ncols > 0 && nl < 4) ? (0xFFFFFFFFu << (8 * nl)) : 0u;
+                    const uint32_t OTH = 0x01010101u * (h ? CODE_OTHER_HI : CODE_OTHER);
+                    c[h] = (v & kp) | (OTH & ~kp);
+                }
+                const uint32_t idx4 = c[0] * 4u + c[1];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (s0 + j < n) {
+                        const uint32_t idx = (idx4 >> (8 * j)) & 0xFFu;
+                        const U2* prow = prof + idx * PROF_STRIDE;
+                        uint32_t d = 0, u = 0;
+#pragma unroll
+                        for (int r2 = 0; r2 < NR / 2; r2++) {
+                            const U2 sv = prow[r2];
+                            uint32_t mold = M[2 * r2];
+                            uint32_t T = addmax2(d, sv.x, mold);
+                            uint32_t hh = max3_2(T, u, G2);
+                            u = hh - G2; M[2 * r2] = u; d = mold;
+                            mold = M[2 * r2 + 1];
+                            T = addmax2(d, sv.y, mold);
+                            hh = max3_2(T, u, G2);
+                            u = hh - G2; M[2 * r2 + 1] = u; d = mold;
+                            // bytes: [H_lo(row 2r2), H_lo(row 2r2+1), H_hi(row 2r2), H_hi(row 2r2+1)]
+                            P.scratch[((int64_t)(s0 + j) * WORDS + r2) * P.scratch_stride + slot] =
+                                prmt(M[2 * r2], M[2 * r2 + 1], 0x7351u);
+                        }
+                    }
+                }
+            }
+        }
+
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            if (hf[h].t < 0) continue;
+            PathOut po;
+            po.clear();
+            po.q_pos = hf[h].v.row; po.r_pos = hf[h].v.col;
+            bool ok = true;
+            if (hf[h].v.score > 0) ok = walk(P, hf[h], h, slot, po);
+            if (ok) emit(P, hf[h].t, hf[h].v, po);
+            else fb(hf[h].t);
+        }
     }
 };
-
-// returns true if the task was resolved; false = push it to the fallback list
-template <int NR>
-LSW_HD bool trace_fast_task(const TraceParams& P, const int t, const int64_t slot) {
-    static_assert(NR % 4 == 0 && NR <= 64, "four 8-bit values per 32-bit word");
-    constexpr int WORDS = NR / 4;
-    const TaskView v = load_task(P, t);
-    PathOut po;
-    po.clear();
-    po.q_pos = v.row; po.r_pos = v.col;
-    if (v.score <= 0) { emit(P, t, v, po); return true; }
-
-    const int W = trace_window_fast(v.row, v.score, P.match, P.g);
-    const int c0 = v.col > W ? v.col - W : 0;
-    const int ncols = v.col - c0;
-
-    uint32_t qw[NR / 4];
-#pragma unroll
-    for (int i = 0; i < NR / 4; i++) qw[i] = reinterpret_cast<const uint32_t*>(v.qc)[i];
-    int Hm[NR];                                   // H - g of the previous column
-#pragma unroll
-    for (int r = 0; r < NR; r++) Hm[r] = -P.g;
-
-    for (int c = 1; c <= ncols; c++) {
-        const int bc = v.ref[c0 + c - 1];
-        int diag = 0, upm = -P.g;                 // row 0: H = 0
-#pragma unroll
-        for (int r4 = 0; r4 < NR / 4; r4++) {
-            uint32_t packed = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int r = r4 * 4 + k;
-                const int qb = (int)((qw[r4] >> (8 * k)) & 0xFF);
-                const int s = (qb == bc) ? P.match : P.mismatch;
-                const int cell = __vimax3_s32_relu(diag + s, Hm[r], upm);
-                diag = Hm[r] + P.g;
-                Hm[r] = cell - P.g;
-                upm = Hm[r];
-                packed |= (uint32_t)cell << (8 * k);
-            }
-            P.scratch[((int64_t)(c - 1) * WORDS + r4) * P.scratch_stride + slot] = packed;
-        }
-    }
-
-    FastWalk fw;
-    fw.scr = P.scratch; fw.stride = P.scratch_stride; fw.slot = slot; fw.words = WORDS; fw.c0 = c0;
-    fw.qc = v.qc; fw.ref = v.ref; fw.match = P.match; fw.mismatch = P.mismatch; fw.g = P.g;
-    fw.budget = 4 * (v.row + ncols) + 64;
-
-    int r = v.row, cl = ncols, last = 0;
-    if (fw.H(r, cl) != v.score) return false;     // the window is too short to reproduce the best cell
-    while (r > 0 && cl > 0) {
-        // every cell on the path is exact: it was reached through a tie from an exact cell
-        if (fw.H(r, cl) == 0) break;
-        const int op = fw.op_at(r, cl);
-        if (op == OPC_FAIL) return false;
-        if (op != last) { po.nrun++; last = op; }
-        if (!po.push(op)) return false;
-        if (op == OPC_M) {
-            if (v.qc[r - 1] == v.ref[c0 + cl - 1]) po.m++; else po.x++;
-            r--; cl--;
-        } else if (op == OPC_I) { po.x++; r--; }
-        else { po.x++; cl--; }
-    }
-    if (cl == 0 && c0 > 0 && r > 0) return false; // ran into the artificial boundary
-    po.q_pos = r;
-    po.r_pos = c0 + cl;
-    emit(P, t, v, po);
-    return true;
-}
 
 #if defined(__CUDACC__)
 constexpr int TRACE_THREADS = 128;
 
+// lower bound of `key` in the sorted 16-bit key array (keys >= 0xFF00 are padding)
+__device__ __forceinline__ long long lower_bound_u16(const uint16_t* keys, long long n, uint32_t key) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if ((uint32_t)keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Candidates arrive sorted by (sequence, window length).  Warps pick a sequence of the class (sticky, as
+// in K1), load its profile, and their lanes claim consecutive PAIRS of its candidates.
 template <int NR>
 __global__ void __launch_bounds__(TRACE_THREADS)
 k_trace_fast(const TraceParams P) {
+    using Lane = TraceLane<NR>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    U2* prof = reinterpret_cast<U2*>(smem_raw) + (size_t)warp * NIDX * Lane::PROF_STRIDE;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long n = *P.ncand;
-    for (unsigned long long i = (unsigned long long)slot; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const int t = (int)P.cand[i];
-        if (!trace_fast_task<NR>(P, t, slot)) {
-            const unsigned long long j = atomicAdd(P.nfallback, 1ull);
-            P.fallback[j] = (uint32_t)t;
+    const long long ncand = (long long)*P.ncand;
+    Lane L;
+    int prefer = (int)((blockIdx.x * (TRACE_THREADS / 32) + warp) % (unsigned)P.n_class_seqs);
+    for (int tried = 0; tried < P.n_class_seqs; ) {
+        const int q = P.class_seqs[prefer];
+        // segment of sequence q in the sorted candidate list
+        const long long lo = lower_bound_u16(P.cand_key, ncand, (uint32_t)q << 8);
+        const long long hi = lower_bound_u16(P.cand_key, ncand, ((uint32_t)q + 1) << 8);
+        const long long cnt = hi - lo;
+        const long long hd0 = (long long)*((volatile unsigned long long*)&P.head[q]);
+        if (hd0 >= cnt) { prefer = (prefer + 1) % P.n_class_seqs; tried++; continue; }
+        tried = 0;
+        __syncwarp();
+        {   // profile of q (same layout as K1)
+            ScoreParams SP;
+            SP.qcodes = P.qcodes; SP.s_match = SC * (P.match + P.g); SP.s_mis = SC * (P.mismatch + P.g);
+            ScoreLane<NR>::build_profile(SP, q, P.qlen[q], reinterpret_cast<uint32_t*>(prof), lane, 32);
         }
+        __syncwarp();
+        for (;;) {
+            const long long i = (long long)atomicAdd(&P.head[q], 2ull);
+            const bool active = i < cnt;
+            if (!__any_sync(0xFFFFFFFFu, active)) break;
+            if (active) {
+                const int t0 = (int)P.cand[lo + i];
+                const int t1 = (i + 1 < cnt) ? (int)P.cand[lo + i + 1] : -1;
+                L.run_pair(P, prof, t0, t1, slot, [&](int t) {
+                    const unsigned long long j = atomicAdd(P.nfallback, 1ull);
+                    P.fallback[j] = (uint32_t)t;
+                });
+            }
+        }
+        prefer = (prefer + 1) % P.n_class_seqs;
     }
+}
+
+template <int NR>
+inline size_t trace_smem_bytes() {
+    return sizeof(U2) * ((size_t)(TRACE_THREADS / 32) * NIDX * TraceLane<NR>::PROF_STRIDE);
 }
 
 template <int NR>
