@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblsw.so")
+LIB_PATH = os.environ.get("LSW_LIB") or os.path.join(_HERE, "liblsw.so")     # LSW_LIB: A/B builds during tuning
 
 LSW_OK, LSW_E_CUDA, LSW_E_ARG, LSW_E_UNSUPPORTED, LSW_E_OVERFLOW, LSW_E_STATE, LSW_E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 MAX_QUERY_LEN = 63

@@ -236,9 +236,13 @@ int launch_score(lsw_ctx* ctx, const ScoreParams& P, int64_t n_class_tasks) {
 int launch_score_class(lsw_ctx* ctx, int c, const ScoreParams& P, int64_t n) {
     switch (CLASS_NR[c]) {
         case 16: return launch_score<16>(ctx, P, n);
+        case 20: return launch_score<20>(ctx, P, n);
         case 24: return launch_score<24>(ctx, P, n);
+        case 28: return launch_score<28>(ctx, P, n);
         case 32: return launch_score<32>(ctx, P, n);
+        case 40: return launch_score<40>(ctx, P, n);
         case 48: return launch_score<48>(ctx, P, n);
+        case 56: return launch_score<56>(ctx, P, n);
         default: return launch_score<64>(ctx, P, n);
     }
 }
@@ -261,6 +265,8 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     const int blocks2 = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * std::min(occ2, 2));
     const int64_t threads2 = (int64_t)blocks2 * TRACE_THREADS;
     const int64_t W = trace_window_full(qmax, ctx->match, ctx->g);
+    if ((size_t)threads * (size_t)(Wf + 4) * (NR / 2) >= (1ull << 31))
+        return fail(ctx, LSW_E_INTERNAL, "traceback scratch exceeds the 32-bit index range");
     const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * (NR / 2) * 4, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
     CK(ctx->d_scratch.ensure(need));
     P.scratch = ctx->d_scratch.as<uint32_t>();
@@ -276,9 +282,13 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
 int launch_trace_class(lsw_ctx* ctx, int c, const TraceParams& P, int64_t n, int qmax) {
     switch (CLASS_NR[c]) {
         case 16: return launch_trace<16, 16>(ctx, P, n, qmax);
+        case 20: return launch_trace<20, 32>(ctx, P, n, qmax);
         case 24: return launch_trace<24, 32>(ctx, P, n, qmax);
+        case 28: return launch_trace<28, 32>(ctx, P, n, qmax);
         case 32: return launch_trace<32, 32>(ctx, P, n, qmax);
+        case 40: return launch_trace<40, 48>(ctx, P, n, qmax);
         case 48: return launch_trace<48, 48>(ctx, P, n, qmax);
+        case 56: return launch_trace<56, 64>(ctx, P, n, qmax);
         default: return launch_trace<64, 64>(ctx, P, n, qmax);
     }
 }

@@ -106,9 +106,13 @@ void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& c
 void emu_score_class(Emu& E, const ScoreParams& P, int c, int q, std::vector<uint32_t>& cand) {
     switch (CLASS_NR[c]) {
         case 16: emu_score_seq<16>(E, P, q, cand); break;
+        case 20: emu_score_seq<20>(E, P, q, cand); break;
         case 24: emu_score_seq<24>(E, P, q, cand); break;
+        case 28: emu_score_seq<28>(E, P, q, cand); break;
         case 32: emu_score_seq<32>(E, P, q, cand); break;
+        case 40: emu_score_seq<40>(E, P, q, cand); break;
         case 48: emu_score_seq<48>(E, P, q, cand); break;
+        case 56: emu_score_seq<56>(E, P, q, cand); break;
         default: emu_score_seq<64>(E, P, q, cand); break;
     }
 }
@@ -135,9 +139,13 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
 void emu_trace_class(Emu& E, const TraceParams& T, const ScoreParams& P, int c, int q, const std::vector<uint32_t>& cand) {
     switch (CLASS_NR[c]) {
         case 16: emu_trace_seq<16, 16>(E, T, P, q, cand); break;
+        case 20: emu_trace_seq<20, 32>(E, T, P, q, cand); break;
         case 24: emu_trace_seq<24, 32>(E, T, P, q, cand); break;
+        case 28: emu_trace_seq<28, 32>(E, T, P, q, cand); break;
         case 32: emu_trace_seq<32, 32>(E, T, P, q, cand); break;
+        case 40: emu_trace_seq<40, 48>(E, T, P, q, cand); break;
         case 48: emu_trace_seq<48, 48>(E, T, P, q, cand); break;
+        case 56: emu_trace_seq<56, 64>(E, T, P, q, cand); break;
         default: emu_trace_seq<64, 64>(E, T, P, q, cand); break;
     }
 }

@@ -6,9 +6,9 @@
 
 namespace lsw {
 
-constexpr int NCLASS = 5;
-static const int CLASS_NR[NCLASS] = {16, 24, 32, 48, 64};     // K1 register-row classes
-static const int CLASS_NR2[NCLASS] = {16, 32, 32, 48, 64};    // K2 rows (one op word per 16 rows)
+constexpr int NCLASS = 9;
+static const int CLASS_NR[NCLASS] = {16, 20, 24, 28, 32, 40, 48, 56, 64};    // register-row classes of K1 and K2-fast
+static const int CLASS_NR2[NCLASS] = {16, 32, 32, 32, 32, 48, 48, 64, 64};   // rows of K2-full (one op word per 16 rows)
 
 // cand_ok[s][score]: can a task of sequence s whose best local score is `score` still pass
 // findPrimerAlignments' test  identity >= thr and span >= len(primer) * thr  (lamprey.py:616-617)?

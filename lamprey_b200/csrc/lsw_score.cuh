@@ -251,8 +251,16 @@ LSW_HD void make_keep_masks(U4* keep_ge, U4* keep_lt, int n) {
 // sequence's queue two tasks at a time until it is empty.
 constexpr int SCORE_WARPS = 4;
 
+// resident blocks per SM the register allocator must allow for (65536 / (128 threads * regs))
+#ifndef LSW_OCC_BOOST
+#define LSW_OCC_BOOST 1
+#endif
+template <int NR> struct ScoreOcc {
+    static constexpr int value = LSW_OCC_BOOST ? (NR <= 16 ? 6 : NR <= 24 ? 5 : NR <= 32 ? 4 : NR <= 40 ? 3 : 2) : 1;
+};
+
 template <int NR>
-__global__ void __launch_bounds__(SCORE_WARPS * 32)
+__global__ void __launch_bounds__(SCORE_WARPS * 32, ScoreOcc<NR>::value)
 k_score(const ScoreParams P) {
     using Lane = ScoreLane<NR>;
     extern __shared__ __align__(16) unsigned char smem_raw[];

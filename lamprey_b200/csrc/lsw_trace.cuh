@@ -261,46 +261,57 @@ struct TraceLane {
         }
     }
 
-    // windowed value of task h at (r, cl): r in [0, Q], cl in [0, ncols]
-    LSW_HD static int Hval(const TraceParams& P, const Half& hf, int h, int64_t slot, int r, int cl) {
-        if (r <= 0 || cl <= 0) return 0;
-        const int s = hf.first + cl - 1;
-        const uint32_t w = P.scratch[((int64_t)s * WORDS + ((r - 1) >> 1)) * P.scratch_stride + slot];
-        return (int)((w >> (8 * (((r - 1) & 1) + 2 * h))) & 0xFFu);
-    }
-    LSW_HD static bool cert(const TraceParams& P, const Half& hf, int r, int cl, int h) {
-        if (hf.c0 == 0 || r <= 0) return true;             // true boundary / row 0
-        const int num = P.match * r - h - 1;                 // >= -1
-        const int need = r + (P.g == 1 ? num : (num >= 0 ? num / P.g : -1));
-        return cl >= need;
-    }
-
     // returns false if the task must go to the fallback list
     LSW_HD bool walk(const TraceParams& P, const Half& hf, int h, int64_t slot, PathOut& po) {
         const TaskView& v = hf.v;
+        // scratch word of (window column cl >= 1, 0-based row i >= 0): 32-bit index arithmetic (the host keeps
+        // the scratch below 2^31 words)
+        const uint32_t stride = (uint32_t)P.scratch_stride;
+        const uint32_t* scr = P.scratch + slot;
+        const uint32_t colbase = (uint32_t)(hf.first - 1) * WORDS;
+        const int sh = 16 * h;                               // bytes 0,1 hold the low task, bytes 2,3 the high task
+        const uint8_t* refw = v.ref + hf.c0 - 1;             // refw[cl] = read code of window column cl
+        const int M_ = P.match, X_ = P.mismatch, g = P.g;
+        const bool exact_boundary = (hf.c0 == 0);
+
         int r = v.row, cl = hf.ncols;
-        if (Hval(P, hf, h, slot, r, cl) != v.score) return false;   // window too short to reproduce the best cell
-        int depth = 0, ret = OPC_NONE, last = 0;
+        int depth = 0, ret = OPC_NONE, last = 0, state = 0;
         uint32_t mv = 0;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
-        unsigned long long st = 0;        // 2 bits per level: 0 fresh, 1 waiting for left's op, 2 waiting for up's op
+        unsigned long long st = 0;        // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
         int budget = 6 * (v.row + hf.ncols) + 64;
         const bool keep_ops = (P.mode == 1);
+        bool first_cell = true;
         for (;;) {
-            const int state = (int)((st >> (2 * depth)) & 3ull);
-            const int hc = Hval(P, hf, h, slot, r, cl);
-            if (depth == 0 && state == 0 && (hc == 0 || r <= 0 || cl <= 0)) break;      // path ends at the first zero
-            const int hl = Hval(P, hf, h, slot, r, cl - 1), hu = Hval(P, hf, h, slot, r - 1, cl);
-            const int hd = Hval(P, hf, h, slot, r - 1, cl - 1);
-            const int sub = (v.qc[r - 1] == v.ref[hf.c0 + cl - 1]) ? P.match : P.mismatch;
-            const bool tieL = (hc == hl - P.g), tieU = (hc == hu - P.g), tieM = (hc == hd + sub);
+            if (r <= 0 || cl <= 0) break;                    // only reachable at depth 0: the matrix boundary is zero
+            const int i = r - 1, iu = i > 0 ? i - 1 : 0, cp = cl > 1 ? cl - 1 : 1;
+            const uint32_t wc = scr[(colbase + (uint32_t)cl * WORDS + (uint32_t)(i >> 1)) * stride];
+            const uint32_t wu = scr[(colbase + (uint32_t)cl * WORDS + (uint32_t)(iu >> 1)) * stride];
+            const uint32_t wl = scr[(colbase + (uint32_t)cp * WORDS + (uint32_t)(i >> 1)) * stride];
+            const uint32_t wd = scr[(colbase + (uint32_t)cp * WORDS + (uint32_t)(iu >> 1)) * stride];
+            const int qb = v.qc[i], rb = refw[cl];
+            const int hc = (int)((wc >> (sh + 8 * (i & 1))) & 0xFFu);
+            if (first_cell) { if (hc != v.score) return false; first_cell = false; }   // window too short for the best cell
+            if (depth == 0 && state == 0 && hc == 0) break;  // the path ends at the first zero cell
+            const int hu = i > 0 ? (int)((wu >> (sh + 8 * (iu & 1))) & 0xFFu) : 0;
+            const int hl = cl > 1 ? (int)((wl >> (sh + 8 * (i & 1))) & 0xFFu) : 0;
+            const int hd = (i > 0 && cl > 1) ? (int)((wd >> (sh + 8 * (iu & 1))) & 0xFFu) : 0;
+            const int sub = (qb == rb) ? M_ : X_;
+            const bool tieL = (hc == hl - g), tieU = (hc == hu - g), tieM = (hc == hd + sub);
             int res = -2;                 // -2: descend (push), otherwise the op of this cell
             bool pushU = false;
             if (state == 0) {
                 if (--budget < 0) return false;
-                // a windowed non-tie is only trustworthy if that neighbour's value is certified
-                if (!tieL && !cert(P, hf, r, cl - 1, hl)) return false;
-                if (!tieU && !cert(P, hf, r - 1, cl, hu)) return false;
-                if (!tieM && !cert(P, hf, r - 1, cl - 1, hd)) return false;
+                if (!exact_boundary) {
+                    // a windowed non-tie is only trustworthy if that neighbour's value is certified:
+                    // cl' >= r' + (M r' - h' - 1) / g   (rows r' <= 0 are the true boundary)
+                    const int nL = M_ * r - hl - 1, nU = M_ * (r - 1) - hu - 1, nD = M_ * (r - 1) - hd - 1;
+                    const int needL = r + (g == 1 ? nL : (nL >= 0 ? nL / g : -1));
+                    const int needU = r - 1 + (g == 1 ? nU : (nU >= 0 ? nU / g : -1));
+                    const int needD = r - 1 + (g == 1 ? nD : (nD >= 0 ? nD / g : -1));
+                    if (!tieL && cl - 1 < needL) return false;
+                    if (!tieU && i > 0 && cl < needU) return false;
+                    if (!tieM && i > 0 && cl - 1 < needD) return false;
+                }
                 if (!tieL && !tieU && !tieM) return false;          // cannot happen for an exact positive cell
                 if (tieL) {
                     if (!tieU && !tieM) res = OPC_D;
@@ -318,27 +329,30 @@ struct TraceLane {
             }
             if (res == -2) {                                        // descend to a neighbour
                 if (depth + 1 >= MAXD) return false;
-                const unsigned long long mask = ~(3ull << (2 * depth));
-                st = (st & mask) | ((unsigned long long)(pushU ? 2 : 1) << (2 * depth));
+                st = (st << 2) | (unsigned long long)(pushU ? 2 : 1);
+                mv = (mv << 1) | (pushU ? 1u : 0u);
                 depth++;
-                st &= ~(3ull << (2 * depth));
-                if (pushU) { mv |= 1u << depth; r -= 1; } else { mv &= ~(1u << depth); cl -= 1; }
+                state = 0;
+                if (pushU) r -= 1; else cl -= 1;
                 continue;
             }
             ret = res;
             if (depth > 0) {                                        // return to the cell that asked
-                if ((mv >> depth) & 1u) r += 1; else cl += 1;
+                if (mv & 1u) r += 1; else cl += 1;
+                state = (int)(st & 3ull);
+                mv >>= 1; st >>= 2;
                 depth--;
                 continue;
             }
             // a path cell is resolved
             if (res != last) { po.nrun++; last = res; }
             if (keep_ops && !po.push(res)) return false;
-            if (res == OPC_M) { if (sub == P.match) po.m++; else po.x++; r--; cl--; }
+            if (res == OPC_M) { if (sub == M_) po.m++; else po.x++; r--; cl--; }
             else if (res == OPC_I) { po.x++; r--; }
             else { po.x++; cl--; }
-            st = 0;
+            state = 0;
         }
+        if (first_cell) return false;
         if (cl == 0 && hf.c0 > 0 && r > 0) return false;            // ran into the artificial boundary
         po.q_pos = r;
         po.r_pos = hf.c0 + cl;
