@@ -255,6 +255,7 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_fast<NR>, TRACE_THREADS, smem));
     if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
+    if (getenv("LSW_K2_BLOCKS_PER_SM")) occ = std::max(1, std::min(occ, atoi(getenv("LSW_K2_BLOCKS_PER_SM"))));
     const int blocks = grid_for((n_class_tasks + 1) / 2, TRACE_THREADS, ctx->num_sms * occ);
     const int64_t threads = (int64_t)blocks * TRACE_THREADS;
     const int64_t Wf = trace_window_fast_max(qmax, ctx->match, ctx->g);

@@ -63,6 +63,23 @@ LSW_HD unsigned long long atomic_add_ull(unsigned long long* p, unsigned long lo
     const unsigned long long o = *p; *p += v; return o;    // host emulation is single-threaded
 #endif
 }
+// counter++ for every calling lane with ONE atomic per warp: the lanes that are converged here elect a
+// leader, which adds their count; each gets its own slot.  (Hit and candidate appends all target a single
+// counter; per-lane atomics serialise on that address in L2.)
+LSW_HD unsigned long long append_slot(unsigned long long* counter) {
+#if defined(__CUDA_ARCH__)
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+#else
+    return (*counter)++;
+#endif
+}
+
 LSW_HD void atomicExch_or_store(int32_t* p, int32_t v) { *p = v; }   // benign race: any writer stores the same flag
 
 // ---- task / result records shared by host and device -------------------------------------

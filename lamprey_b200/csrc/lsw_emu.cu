@@ -8,6 +8,7 @@
 // It is built into its own library (liblsw_emu.so) and is never loaded by the product path:
 // lamprey_b200 only opens liblsw.so and fails loudly without a CUDA device.
 #include <cstring>
+#include <cstdio>
 #include <vector>
 #include <algorithm>
 
@@ -227,6 +228,9 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
         E.t_read.swap(nr); E.t_a.swap(na); E.t_b.swap(nb); E.t_seq.swap(ns); E.seg.swap(nseg);
         round++;
     }
+#if defined(LSW_EMU_STATS)
+    fprintf(stderr, "[emu] walks %llu iters %llu (%.1f per walk) fill steps %llu (%.1f per pair)\n", g_walks, g_walk_iters, (double)g_walk_iters / (double)(g_walks ? g_walks : 1), g_fill_steps, 2.0 * g_fill_steps / (double)(g_walks ? g_walks : 1));
+#endif
     if (errflag) return LSW_E_INTERNAL;
     if (n_out) *n_out = (int64_t)nhits;
     if (counters) { counters[0] = E.counters[0]; counters[1] = E.counters[1]; counters[2] = E.counters[2]; counters[3] = round; counters[4] = E.counters[3]; counters[5] = E.fallbacks; }

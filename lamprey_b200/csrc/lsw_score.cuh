@@ -253,7 +253,7 @@ constexpr int SCORE_WARPS = 4;
 
 // resident blocks per SM the register allocator must allow for (65536 / (128 threads * regs))
 #ifndef LSW_OCC_BOOST
-#define LSW_OCC_BOOST 1
+#define LSW_OCC_BOOST 0      // measured on B200: forcing 5-6 blocks/SM spills in the column loop and costs 20 %
 #endif
 template <int NR> struct ScoreOcc {
     static constexpr int value = LSW_OCC_BOOST ? (NR <= 16 ? 6 : NR <= 24 ? 5 : NR <= 32 ? 4 : NR <= 40 ? 3 : 2) : 1;
@@ -324,7 +324,7 @@ k_score(const ScoreParams P) {
             for (int h = 0; h < 2; h++) {
                 if (L.tid[h] >= 0 && L.rem[h] == 0)
                     L.finish(P, h, q, Q, [&](int t, int key) {
-                        const unsigned long long i = atomicAdd(P.ncand, 1ull);
+                        const unsigned long long i = append_slot(P.ncand);
                         P.cand[i] = (uint32_t)t;
                         P.cand_key[i] = (uint16_t)(((uint32_t)q << 8) | (uint32_t)key);
                     });

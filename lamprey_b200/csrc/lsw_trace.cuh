@@ -121,7 +121,7 @@ LSW_HD void emit(const TraceParams& P, int t, const TaskView& v, const PathOut& 
     // identity is float(m)/(m+x) (Python double division), or the int 0 when nothing aligned
     const double identity = tot > 0 ? (double)po.m / (double)tot : 0.0;
     if (identity >= P.thr && (double)span >= (double)v.Q * P.thr) {
-        const unsigned long long hi = atomic_add_ull(P.nhits, 1ull);
+        const unsigned long long hi = append_slot(P.nhits);
         if ((long long)hi < P.hits_cap) {
             lsw_hit* h = reinterpret_cast<lsw_hit*>(P.hits) + hi;
             h->read = v.rd; h->start = v.a + po.r_pos; h->end = v.a + v.col;
@@ -235,6 +235,10 @@ LSW_HD void trace_full_task(const TraceParams& P, const int t, const int64_t slo
 //          column the H bytes of both tasks go to scratch, two rows of both tasks per 32-bit word;
 //   walk   each task in turn: a flat state machine, one cell evaluation per iteration, that applies
 //          the op rule lazily and proves every decision (see the file header).
+#if defined(LSW_EMU_STATS)
+static unsigned long long g_walk_iters = 0, g_walks = 0, g_fill_steps = 0;
+#endif
+
 template <int NR>
 struct TraceLane {
     static_assert(NR % 4 == 0 && NR <= 64, "rows in registers");
@@ -261,37 +265,59 @@ struct TraceLane {
         }
     }
 
-    // returns false if the task must go to the fallback list
-    LSW_HD bool walk(const TraceParams& P, const Half& hf, int h, int64_t slot, PathOut& po) {
-        const TaskView& v = hf.v;
-        // scratch word of (window column cl >= 1, 0-based row i >= 0): 32-bit index arithmetic (the host keeps
-        // the scratch below 2^31 words)
-        const uint32_t stride = (uint32_t)P.scratch_stride;
-        const uint32_t* scr = P.scratch + slot;
-        const uint32_t colbase = (uint32_t)(hf.first - 1) * WORDS;
-        const int sh = 16 * h;                               // bytes 0,1 hold the low task, bytes 2,3 the high task
-        const uint8_t* refw = v.ref + hf.c0 - 1;             // refw[cl] = read code of window column cl
-        const int M_ = P.match, X_ = P.mismatch, g = P.g;
-        const bool exact_boundary = (hf.c0 == 0);
+    // One traceback in progress.  load() issues the scratch / code loads of the current cell, decide()
+    // consumes them and moves on: run_pair() calls load() for BOTH tasks of the lane before either decide(),
+    // so the two dependent-load chains overlap (the walk is latency bound).
+    struct Walker {
+        // constants of the task
+        const uint32_t* scr; uint32_t stride, colbase; int sh;
+        const uint8_t* qc; const uint8_t* refw;
+        int M_, X_, g, score, c0; bool exact_boundary, keep_ops;
+        // state
+        int r, cl, depth, ret, last, state, budget;
+        uint32_t mv;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
+        unsigned long long st;        // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
+        bool active, failed, first_cell;
+        // loaded operands
+        uint32_t wc, wu, wl, wd; int qb, rb;
 
-        int r = v.row, cl = hf.ncols;
-        int depth = 0, ret = OPC_NONE, last = 0, state = 0;
-        uint32_t mv = 0;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
-        unsigned long long st = 0;        // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
-        int budget = 6 * (v.row + hf.ncols) + 64;
-        const bool keep_ops = (P.mode == 1);
-        bool first_cell = true;
-        for (;;) {
-            if (r <= 0 || cl <= 0) break;                    // only reachable at depth 0: the matrix boundary is zero
+        LSW_HD void init(const TraceParams& P, const Half& hf, int h, int64_t slot) {
+            active = failed = false; first_cell = true;
+            r = cl = depth = last = state = 0; ret = OPC_NONE; mv = 0; st = 0; budget = 0;
+            wc = wu = wl = wd = 0; qb = rb = 0;
+            if (hf.t < 0 || hf.v.score <= 0) return;
+            scr = P.scratch + slot;                               // 32-bit index arithmetic below: the host keeps
+            stride = (uint32_t)P.scratch_stride;                  // the scratch under 2^31 words
+            colbase = (uint32_t)(hf.first - 1) * WORDS;
+            sh = 16 * h;                                          // bytes 0,1: low task; bytes 2,3: high task
+            qc = hf.v.qc; refw = hf.v.ref + hf.c0 - 1;            // refw[cl] = read code of window column cl
+            M_ = P.match; X_ = P.mismatch; g = P.g; score = hf.v.score; c0 = hf.c0;
+            exact_boundary = (hf.c0 == 0); keep_ops = (P.mode == 1);
+            r = hf.v.row; cl = hf.ncols;
+            budget = 6 * (hf.v.row + hf.ncols) + 64;
+            active = true;
+        }
+        LSW_HD void load() {
+            if (!active) return;
+            if (r <= 0 || cl <= 0) return;                        // decide() ends the walk
             const int i = r - 1, iu = i > 0 ? i - 1 : 0, cp = cl > 1 ? cl - 1 : 1;
-            const uint32_t wc = scr[(colbase + (uint32_t)cl * WORDS + (uint32_t)(i >> 1)) * stride];
-            const uint32_t wu = scr[(colbase + (uint32_t)cl * WORDS + (uint32_t)(iu >> 1)) * stride];
-            const uint32_t wl = scr[(colbase + (uint32_t)cp * WORDS + (uint32_t)(i >> 1)) * stride];
-            const uint32_t wd = scr[(colbase + (uint32_t)cp * WORDS + (uint32_t)(iu >> 1)) * stride];
-            const int qb = v.qc[i], rb = refw[cl];
+            wc = scr[(colbase + (uint32_t)cl * WORDS + (uint32_t)(i >> 1)) * stride];
+            wu = scr[(colbase + (uint32_t)cl * WORDS + (uint32_t)(iu >> 1)) * stride];
+            wl = scr[(colbase + (uint32_t)cp * WORDS + (uint32_t)(i >> 1)) * stride];
+            wd = scr[(colbase + (uint32_t)cp * WORDS + (uint32_t)(iu >> 1)) * stride];
+            qb = qc[i]; rb = refw[cl];
+        }
+        LSW_HD void fail() { failed = true; active = false; }
+        LSW_HD void decide(PathOut& po) {
+            if (!active) return;
+#if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
+            g_walk_iters++;
+#endif
+            if (r <= 0 || cl <= 0) { active = false; return; }    // only at depth 0: the matrix boundary is zero
+            const int i = r - 1, iu = i > 0 ? i - 1 : 0;
             const int hc = (int)((wc >> (sh + 8 * (i & 1))) & 0xFFu);
-            if (first_cell) { if (hc != v.score) return false; first_cell = false; }   // window too short for the best cell
-            if (depth == 0 && state == 0 && hc == 0) break;  // the path ends at the first zero cell
+            if (first_cell) { if (hc != score) { fail(); return; } first_cell = false; }   // window too short for the best cell
+            if (depth == 0 && state == 0 && hc == 0) { active = false; return; }           // path ends at the first zero cell
             const int hu = i > 0 ? (int)((wu >> (sh + 8 * (iu & 1))) & 0xFFu) : 0;
             const int hl = cl > 1 ? (int)((wl >> (sh + 8 * (i & 1))) & 0xFFu) : 0;
             const int hd = (i > 0 && cl > 1) ? (int)((wd >> (sh + 8 * (iu & 1))) & 0xFFu) : 0;
@@ -300,7 +326,7 @@ struct TraceLane {
             int res = -2;                 // -2: descend (push), otherwise the op of this cell
             bool pushU = false;
             if (state == 0) {
-                if (--budget < 0) return false;
+                if (--budget < 0) { fail(); return; }
                 if (!exact_boundary) {
                     // a windowed non-tie is only trustworthy if that neighbour's value is certified:
                     // cl' >= r' + (M r' - h' - 1) / g   (rows r' <= 0 are the true boundary)
@@ -308,11 +334,11 @@ struct TraceLane {
                     const int needL = r + (g == 1 ? nL : (nL >= 0 ? nL / g : -1));
                     const int needU = r - 1 + (g == 1 ? nU : (nU >= 0 ? nU / g : -1));
                     const int needD = r - 1 + (g == 1 ? nD : (nD >= 0 ? nD / g : -1));
-                    if (!tieL && cl - 1 < needL) return false;
-                    if (!tieU && i > 0 && cl < needU) return false;
-                    if (!tieM && i > 0 && cl - 1 < needD) return false;
+                    if ((!tieL && cl - 1 < needL) || (!tieU && i > 0 && cl < needU) || (!tieM && i > 0 && cl - 1 < needD)) {
+                        fail(); return;
+                    }
                 }
-                if (!tieL && !tieU && !tieM) return false;          // cannot happen for an exact positive cell
+                if (!tieL && !tieU && !tieM) { fail(); return; }   // cannot happen for an exact positive cell
                 if (tieL) {
                     if (!tieU && !tieM) res = OPC_D;
                     // else: need left's op (left value is hc + g > 0 and exact because of the tie)
@@ -328,13 +354,13 @@ struct TraceLane {
                 else res = tieM ? OPC_M : (tieL ? OPC_D : OPC_I);
             }
             if (res == -2) {                                        // descend to a neighbour
-                if (depth + 1 >= MAXD) return false;
+                if (depth + 1 >= MAXD) { fail(); return; }
                 st = (st << 2) | (unsigned long long)(pushU ? 2 : 1);
                 mv = (mv << 1) | (pushU ? 1u : 0u);
                 depth++;
                 state = 0;
                 if (pushU) r -= 1; else cl -= 1;
-                continue;
+                return;
             }
             ret = res;
             if (depth > 0) {                                        // return to the cell that asked
@@ -342,22 +368,25 @@ struct TraceLane {
                 state = (int)(st & 3ull);
                 mv >>= 1; st >>= 2;
                 depth--;
-                continue;
+                return;
             }
             // a path cell is resolved
             if (res != last) { po.nrun++; last = res; }
-            if (keep_ops && !po.push(res)) return false;
+            if (keep_ops && !po.push(res)) { fail(); return; }
             if (res == OPC_M) { if (sub == M_) po.m++; else po.x++; r--; cl--; }
             else if (res == OPC_I) { po.x++; r--; }
             else { po.x++; cl--; }
             state = 0;
         }
-        if (first_cell) return false;
-        if (cl == 0 && hf.c0 > 0 && r > 0) return false;            // ran into the artificial boundary
-        po.q_pos = r;
-        po.r_pos = hf.c0 + cl;
-        return true;
-    }
+        // after the loop: false = the task must go to the fallback list
+        LSW_HD bool finish(PathOut& po) const {
+            if (failed || first_cell) return false;
+            if (cl == 0 && c0 > 0 && r > 0) return false;            // ran into the artificial boundary
+            po.q_pos = r;
+            po.r_pos = c0 + cl;
+            return true;
+        }
+    };
 
     // fill + walk for the pair (t0, t1); t1 may be -1.  fb(t): push a task to the fallback list.
     template <class Fallback>
@@ -429,15 +458,27 @@ struct TraceLane {
             }
         }
 
-#pragma unroll 1
+        // both tracebacks of the lane, interleaved
+        PathOut po[2];
+        Walker w[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            po[h].clear();
+            if (hf[h].t >= 0) { po[h].q_pos = hf[h].v.row; po[h].r_pos = hf[h].v.col; }
+            w[h].init(P, hf[h], h, slot);
+        }
+        while (w[0].active || w[1].active) {
+            w[0].load(); w[1].load();
+            w[0].decide(po[0]); w[1].decide(po[1]);
+        }
+#pragma unroll
         for (int h = 0; h < 2; h++) {
             if (hf[h].t < 0) continue;
-            PathOut po;
-            po.clear();
-            po.q_pos = hf[h].v.row; po.r_pos = hf[h].v.col;
-            bool ok = true;
-            if (hf[h].v.score > 0) ok = walk(P, hf[h], h, slot, po);
-            if (ok) emit(P, hf[h].t, hf[h].v, po);
+#if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
+            g_walks++; if (h == 0) g_fill_steps += n;
+#endif
+            const bool ok = hf[h].v.score > 0 ? w[h].finish(po[h]) : true;
+            if (ok) emit(P, hf[h].t, hf[h].v, po[h]);
             else fb(hf[h].t);
         }
     }
@@ -445,6 +486,11 @@ struct TraceLane {
 
 #if defined(__CUDACC__)
 constexpr int TRACE_THREADS = 128;
+
+template <int NR>
+__host__ __device__ constexpr size_t trace_prof_bytes() {
+    return sizeof(U2) * ((size_t)(TRACE_THREADS / 32) * NIDX * TraceLane<NR>::PROF_STRIDE);
+}
 
 // lower bound of `key` in the sorted 16-bit key array (keys >= 0xFF00 are padding)
 __device__ __forceinline__ long long lower_bound_u16(const uint16_t* keys, long long n, uint32_t key) {
@@ -458,8 +504,17 @@ __device__ __forceinline__ long long lower_bound_u16(const uint16_t* keys, long 
 
 // Candidates arrive sorted by (sequence, window length).  Warps pick a sequence of the class (sticky, as
 // in K1), load its profile, and their lanes claim consecutive PAIRS of its candidates.
+// the walk is latency bound: ask the register allocator for enough resident blocks (measured on B200:
+// K2 time falls almost linearly with resident warps up to the limit)
+#ifndef LSW_K2_OCC_SMALL
+#define LSW_K2_OCC_SMALL 6
+#endif
+template <int NR> struct TraceOcc {
+    static constexpr int value = NR <= 24 ? LSW_K2_OCC_SMALL : NR <= 32 ? (LSW_K2_OCC_SMALL > 5 ? 5 : LSW_K2_OCC_SMALL) : NR <= 48 ? 3 : 2;
+};
+
 template <int NR>
-__global__ void __launch_bounds__(TRACE_THREADS)
+__global__ void __launch_bounds__(TRACE_THREADS, TraceOcc<NR>::value)
 k_trace_fast(const TraceParams P) {
     using Lane = TraceLane<NR>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -467,14 +522,21 @@ k_trace_fast(const TraceParams P) {
     U2* prof = reinterpret_cast<U2*>(smem_raw) + (size_t)warp * NIDX * Lane::PROF_STRIDE;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const long long ncand = (long long)*P.ncand;
+    // segment of every sequence of the class in the sorted candidate list, found once per block
+    long long* seg_lo = reinterpret_cast<long long*>(smem_raw + trace_prof_bytes<NR>());
+    long long* seg_hi = seg_lo + 256;
+    for (int i = threadIdx.x; i < P.n_class_seqs; i += blockDim.x) {
+        const int q = P.class_seqs[i];
+        seg_lo[i] = lower_bound_u16(P.cand_key, ncand, (uint32_t)q << 8);
+        seg_hi[i] = lower_bound_u16(P.cand_key, ncand, ((uint32_t)q + 1) << 8);
+    }
+    __syncthreads();
     Lane L;
     int prefer = (int)((blockIdx.x * (TRACE_THREADS / 32) + warp) % (unsigned)P.n_class_seqs);
     for (int tried = 0; tried < P.n_class_seqs; ) {
         const int q = P.class_seqs[prefer];
-        // segment of sequence q in the sorted candidate list
-        const long long lo = lower_bound_u16(P.cand_key, ncand, (uint32_t)q << 8);
-        const long long hi = lower_bound_u16(P.cand_key, ncand, ((uint32_t)q + 1) << 8);
-        const long long cnt = hi - lo;
+        const long long lo = seg_lo[prefer];
+        const long long cnt = seg_hi[prefer] - lo;
         const long long hd0 = (long long)*((volatile unsigned long long*)&P.head[q]);
         if (hd0 >= cnt) { prefer = (prefer + 1) % P.n_class_seqs; tried++; continue; }
         tried = 0;
@@ -503,9 +565,7 @@ k_trace_fast(const TraceParams P) {
 }
 
 template <int NR>
-inline size_t trace_smem_bytes() {
-    return sizeof(U2) * ((size_t)(TRACE_THREADS / 32) * NIDX * TraceLane<NR>::PROF_STRIDE);
-}
+inline size_t trace_smem_bytes() { return trace_prof_bytes<NR>() + 2 * 256 * sizeof(long long); }
 
 template <int NR>
 __global__ void __launch_bounds__(TRACE_THREADS)
