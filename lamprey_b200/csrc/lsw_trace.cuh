@@ -44,11 +44,18 @@ LSW_HD int trace_window_full(int Q, int match, int g) {
     const int span = Q + dmax;
     return 2 * span + dmax + 4;
 }
+// Short window of the certified walk.  Define the margin of a cell  m(r, c, h) = (c - c0) - r - (M r - h - 1)/g;
+// m >= 0 certifies its windowed value (see above).  Walking back along a path the margin never decreases
+// (match: +0, mismatch: +M+|X|, 'i': +1+M+g.., 'd': +g-1 >= 0), a tying neighbour has a larger value and
+// hence a margin no smaller, and a non-tying neighbour differs by at most M+g in value, i.e. its margin is
+// at most (M+g)/g + 1 smaller.  With  W1 = max_row + (M max_row - score)/g + SLACK,  SLACK = (M+g)/g + 5,
+// the start cell has margin >= SLACK - 1, so EVERY cell the walk consults is certified: the walk checks the
+// start margin once instead of three certificates per step.  (For +2/-1/-1: SLACK = 8.)
+LSW_HD int trace_slack(int match, int g) { return (match + g) / g + 5; }
 LSW_HD int trace_window_fast(int max_row, int score, int match, int g) {
-    const int w = max_row + (match * max_row - score) / g + 8;
-    return w;
+    return max_row + (match * max_row - score) / g + trace_slack(match, g);
 }
-LSW_HD int trace_window_fast_max(int Q, int match, int g) { return Q + (match * Q) / g + 8; }
+LSW_HD int trace_window_fast_max(int Q, int match, int g) { return Q + (match * Q) / g + trace_slack(match, g); }
 
 enum { OPC_NONE = 0, OPC_M = 1, OPC_I = 2, OPC_D = 3, OPC_FAIL = -1 };
 constexpr int MAX_PATH_WORDS = 16;             // 2 bits per op; a path has < Q + M*Q/g <= 3*63 ops ... 256 ops of room
@@ -244,7 +251,7 @@ struct TraceLane {
     static_assert(NR % 4 == 0 && NR <= 64, "rows in registers");
     static constexpr int PROF_STRIDE = NR / 2 + 1;
     static constexpr int WORDS = NR / 2;          // scratch words per window column (both tasks)
-    static constexpr int MAXD = 24;               // nesting limit of run-flag evaluations
+    static constexpr int MAXD = 15;               // nesting limit of run-flag evaluations (2 state bits each)
 
     uint32_t M[NR];
 
@@ -272,11 +279,11 @@ struct TraceLane {
         // constants of the task
         const uint32_t* scr; uint32_t stride, colbase; int sh;
         const uint8_t* qc; const uint8_t* refw;
-        int M_, X_, g, score, c0; bool exact_boundary, keep_ops;
+        int M_, X_, g, score, c0; bool keep_ops;
         // state
         int r, cl, depth, ret, last, state, budget;
         uint32_t mv;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
-        unsigned long long st;        // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
+        uint32_t st;                  // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
         bool active, failed, first_cell;
         // loaded operands
         uint32_t wc, wu, wl, wd; int qb, rb;
@@ -292,19 +299,24 @@ struct TraceLane {
             sh = 16 * h;                                          // bytes 0,1: low task; bytes 2,3: high task
             qc = hf.v.qc; refw = hf.v.ref + hf.c0 - 1;            // refw[cl] = read code of window column cl
             M_ = P.match; X_ = P.mismatch; g = P.g; score = hf.v.score; c0 = hf.c0;
-            exact_boundary = (hf.c0 == 0); keep_ops = (P.mode == 1);
+            keep_ops = (P.mode == 1);
             r = hf.v.row; cl = hf.ncols;
             budget = 6 * (hf.v.row + hf.ncols) + 64;
             active = true;
+            if (hf.c0 > 0) {
+                // one certificate for the whole walk (see trace_slack): margin of the start cell
+                const int num = M_ * r - score - 1;
+                const int margin = cl - r - (num >= 0 ? num / g : -1);
+                if (margin < trace_slack(M_, g) - 1) { failed = true; active = false; }
+            }
         }
         LSW_HD void load() {
             if (!active) return;
             if (r <= 0 || cl <= 0) return;                        // decide() ends the walk
             const int i = r - 1, iu = i > 0 ? i - 1 : 0, cp = cl > 1 ? cl - 1 : 1;
-            wc = scr[(colbase + (uint32_t)cl * WORDS + (uint32_t)(i >> 1)) * stride];
-            wu = scr[(colbase + (uint32_t)cl * WORDS + (uint32_t)(iu >> 1)) * stride];
-            wl = scr[(colbase + (uint32_t)cp * WORDS + (uint32_t)(i >> 1)) * stride];
-            wd = scr[(colbase + (uint32_t)cp * WORDS + (uint32_t)(iu >> 1)) * stride];
+            const uint32_t bc = (colbase + (uint32_t)cl * WORDS) * stride, bp = (colbase + (uint32_t)cp * WORDS) * stride;
+            const uint32_t oi = (uint32_t)(i >> 1) * stride, ou = (uint32_t)(iu >> 1) * stride;
+            wc = scr[bc + oi]; wu = scr[bc + ou]; wl = scr[bp + oi]; wd = scr[bp + ou];
             qb = qc[i]; rb = refw[cl];
         }
         LSW_HD void fail() { failed = true; active = false; }
@@ -323,21 +335,12 @@ struct TraceLane {
             const int hd = (i > 0 && cl > 1) ? (int)((wd >> (sh + 8 * (iu & 1))) & 0xFFu) : 0;
             const int sub = (qb == rb) ? M_ : X_;
             const bool tieL = (hc == hl - g), tieU = (hc == hu - g), tieM = (hc == hd + sub);
+            // a cell next to the artificial left boundary cannot be decided (its left / diagonal value is unknown)
+            if (cl <= 1 && c0 > 0) { fail(); return; }
             int res = -2;                 // -2: descend (push), otherwise the op of this cell
             bool pushU = false;
             if (state == 0) {
                 if (--budget < 0) { fail(); return; }
-                if (!exact_boundary) {
-                    // a windowed non-tie is only trustworthy if that neighbour's value is certified:
-                    // cl' >= r' + (M r' - h' - 1) / g   (rows r' <= 0 are the true boundary)
-                    const int nL = M_ * r - hl - 1, nU = M_ * (r - 1) - hu - 1, nD = M_ * (r - 1) - hd - 1;
-                    const int needL = r + (g == 1 ? nL : (nL >= 0 ? nL / g : -1));
-                    const int needU = r - 1 + (g == 1 ? nU : (nU >= 0 ? nU / g : -1));
-                    const int needD = r - 1 + (g == 1 ? nD : (nD >= 0 ? nD / g : -1));
-                    if ((!tieL && cl - 1 < needL) || (!tieU && i > 0 && cl < needU) || (!tieM && i > 0 && cl - 1 < needD)) {
-                        fail(); return;
-                    }
-                }
                 if (!tieL && !tieU && !tieM) { fail(); return; }   // cannot happen for an exact positive cell
                 if (tieL) {
                     if (!tieU && !tieM) res = OPC_D;
@@ -355,7 +358,7 @@ struct TraceLane {
             }
             if (res == -2) {                                        // descend to a neighbour
                 if (depth + 1 >= MAXD) { fail(); return; }
-                st = (st << 2) | (unsigned long long)(pushU ? 2 : 1);
+                st = (st << 2) | (pushU ? 2u : 1u);
                 mv = (mv << 1) | (pushU ? 1u : 0u);
                 depth++;
                 state = 0;
@@ -365,17 +368,19 @@ struct TraceLane {
             ret = res;
             if (depth > 0) {                                        // return to the cell that asked
                 if (mv & 1u) r += 1; else cl += 1;
-                state = (int)(st & 3ull);
+                state = (int)(st & 3u);
                 mv >>= 1; st >>= 2;
                 depth--;
                 return;
             }
             // a path cell is resolved
-            if (res != last) { po.nrun++; last = res; }
+            po.nrun += (res != last) ? 1 : 0;
+            last = res;
             if (keep_ops && !po.push(res)) { fail(); return; }
-            if (res == OPC_M) { if (sub == M_) po.m++; else po.x++; r--; cl--; }
-            else if (res == OPC_I) { po.x++; r--; }
-            else { po.x++; cl--; }
+            po.m += (res == OPC_M && sub == M_) ? 1 : 0;
+            po.x += (res == OPC_M && sub == M_) ? 0 : 1;
+            r -= (res != OPC_D) ? 1 : 0;
+            cl -= (res != OPC_I) ? 1 : 0;
             state = 0;
         }
         // after the loop: false = the task must go to the fallback list
