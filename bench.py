@@ -145,7 +145,7 @@ def run_reference(args):
         return 0
     from lamprey_b200 import synth
     cores = os.cpu_count() or 1
-    sample = max(cores, 8)
+    sample = 3 * max(cores, 8)        # a few reads per core, so one long read does not set the step time
     kw = dict(synth.CONFIGS[args.workload])
     concat, offs = synth.generate(sample * (args.steps + args.warmup), chunk=sample, **kw)
     reads = synth.reads_as_strings(concat, offs)

@@ -91,7 +91,7 @@ struct lsw_ctx {
     int64_t n_reads = 0, total_bases = 0, codes_bytes = 0;
     std::vector<int64_t> h_roff;
     std::vector<int32_t> h_rlen;
-    DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen;
+    DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen, d_order, d_order_tmp, d_len_tmp[2];
 
     TaskBuf tb[2], child;
     DevBuf d_fallback[NCLASS], d_nfallback, d_cand_key[NCLASS], d_cand_sorted[NCLASS], d_cand_key_sorted[NCLASS];
@@ -141,13 +141,20 @@ __global__ void k_encode_reads(const uint8_t* __restrict__ ascii, const int64_t*
 }
 
 // Round 0 of findAllPrimerAlignments: every sequence against every whole read.
-__global__ void k_init_tasks(TaskArrays t, const int32_t* __restrict__ rlen, int64_t n_reads, int nseq) {
+// Within a sequence the reads are queued longest first (order[]: indices sorted by descending length), so
+// the few very long reads of an ONT length distribution start early instead of forming the tail of the launch.
+__global__ void k_init_tasks(TaskArrays t, const int32_t* __restrict__ rlen, const int32_t* __restrict__ order,
+                             int64_t n_reads, int nseq) {
     const int64_t n = n_reads * nseq;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int s = (int)(i / n_reads);
-        const int64_t r = i - (int64_t)s * n_reads;
-        t.read[i] = (int32_t)r; t.a[i] = 0; t.b[i] = rlen[r]; t.seq[i] = (int16_t)s;
+        const int32_t r = order[i - (int64_t)s * n_reads];
+        t.read[i] = r; t.a[i] = 0; t.b[i] = rlen[r]; t.seq[i] = (int16_t)s;
     }
+}
+
+__global__ void k_iota(int32_t* __restrict__ v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = (int32_t)i;
 }
 
 struct FlagToInt {
@@ -309,6 +316,7 @@ void fill_score_params(lsw_ctx* ctx, ScoreParams& P, const TaskBuf& cur, int seg
     P.s_mis = SC * (ctx->mismatch + ctx->g);
     P.g = ctx->g;
     P.match = ctx->match;
+    P.one = 1u;
 }
 
 void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {
@@ -457,7 +465,7 @@ void lsw_destroy(lsw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_qcodes, &ctx->d_qlen, &ctx->d_cand_ok, &ctx->d_ascii, &ctx->d_offs_in, &ctx->d_codes,
-                      &ctx->d_roff, &ctx->d_rlen, &ctx->d_res, &ctx->d_seg[0], &ctx->d_seg[1], &ctx->d_head,
+                      &ctx->d_roff, &ctx->d_rlen, &ctx->d_order, &ctx->d_order_tmp, &ctx->d_len_tmp[0], &ctx->d_len_tmp[1], &ctx->d_res, &ctx->d_seg[0], &ctx->d_seg[1], &ctx->d_head,
                       &ctx->d_ncand, &ctx->d_counters, &ctx->d_child_flag, &ctx->d_pos, &ctx->d_cubtemp,
                       &ctx->d_scratch, &ctx->d_hits, &ctx->d_hits_sorted, &ctx->d_nhits, &ctx->d_keys[0],
                       &ctx->d_keys[1], &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_err, &ctx->d_results,
@@ -580,6 +588,20 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
                                                         ctx->d_roff.as<int64_t>(), ctx->d_codes.as<uint8_t>(), n);
         CK(cudaGetLastError());
     }
+    if (n) {
+        // read indices by descending length (round-0 queue order)
+        CK(ctx->d_order.ensure((size_t)n * 4)); CK(ctx->d_order_tmp.ensure((size_t)n * 4));
+        CK(ctx->d_len_tmp[0].ensure((size_t)n * 4)); CK(ctx->d_len_tmp[1].ensure((size_t)n * 4));
+        k_iota<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(ctx->d_order_tmp.as<int32_t>(), n);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->d_len_tmp[0].p, ctx->d_rlen.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, ctx->d_len_tmp[0].as<int32_t>(), ctx->d_len_tmp[1].as<int32_t>(),
+                                                     ctx->d_order_tmp.as<int32_t>(), ctx->d_order.as<int32_t>(), (int)n, 0, 27, ctx->stream));
+        CK(ctx->d_cubtemp.ensure(tmp));
+        CK(cub::DeviceRadixSort::SortPairsDescending(ctx->d_cubtemp.p, tmp, ctx->d_len_tmp[0].as<int32_t>(), ctx->d_len_tmp[1].as<int32_t>(),
+                                                     ctx->d_order_tmp.as<int32_t>(), ctx->d_order.as<int32_t>(), (int)n, 0, 27, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));      // `rel` and the caller's buffers may go away
     return LSW_OK;
 }
@@ -624,7 +646,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     {
         Span sp(ctx, 2);
         k_init_tasks<<<grid_for(n0, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
-            ctx->tb[0].view(), ctx->d_rlen.as<int32_t>(), ctx->n_reads, ctx->nseq);
+            ctx->tb[0].view(), ctx->d_rlen.as<int32_t>(), ctx->d_order.as<int32_t>(), ctx->n_reads, ctx->nseq);
         CK(cudaGetLastError());
         cnt.other_launches++;
     }

@@ -166,7 +166,7 @@ void emu_round(Emu& E, TraceParams T) {
     P.codes = E.codes.data(); P.roff = E.roff.data(); P.t = view(E); P.seg = E.seg.data();
     P.res = E.res.data(); P.qcodes = E.qcodes.data(); P.qlen = E.qlen.data();
     P.cand_ok = E.cand_ok.data();
-    P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g; P.match = E.match;
+    P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g; P.match = E.match; P.one = 1u;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
     std::vector<uint32_t> scratch((size_t)(size_t)std::max(trace_window_full(qmax, E.match, E.g) * 4, (trace_window_fast_max(qmax, E.match, E.g) + 4) * 32) + 16);

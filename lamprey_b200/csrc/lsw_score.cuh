@@ -126,25 +126,31 @@ struct ScoreLane {
         tid[h] = -1;
     }
 
-    // One DP column for both halves.  prow: profile row of this column's (code_lo, code_hi).
-    LSW_HD void column(const U2* prow, uint32_t tvec, uint32_t G2, uint32_t FLOOR2) {
-        uint32_t d = 0, u = 0;
+    // TWO DP columns (c, c+1) for both halves, row by row.  prowA / prowB: profile rows of the two columns'
+    // (code_lo, code_hi) pairs.  Doing two columns per sweep lets one VIMNMX3 fold both arg-max keys into K[r]
+    // (the key adds are plain adds and go to the FMA pipe), i.e. 5 ALU-pipe ops per four cells instead of 6.
+    LSW_HD void column2(const U2* prowA, const U2* prowB, uint32_t tvA, uint32_t tvB, uint32_t G2, uint32_t FLOOR2,
+                        uint32_t one) {
+        uint32_t dOld = 0, uA = 0, uB = 0;
 #pragma unroll
         for (int r2 = 0; r2 < NR / 2; r2++) {
-            const U2 s = prow[r2];
-#define LSW_ROW(R, S)                                            \
+            const U2 sa = prowA[r2], sb = prowB[r2];
+#define LSW_ROW2(R, SA, SB)                                      \
             {                                                    \
                 const uint32_t mold = M[R];                      \
-                const uint32_t T = addmax2(d, S, mold);          \
-                const uint32_t hh = max3_2(T, u, FLOOR2);        \
-                u = hh - G2;                                     \
-                M[R] = u;                                        \
-                K[R] = addmax2(hh, tvec, K[R]);                  \
-                d = mold;                                        \
+                const uint32_t T1 = addmax2(dOld, SA, mold);     \
+                const uint32_t h1 = max3_2(T1, uA, FLOOR2);      \
+                const uint32_t m1 = h1 - G2;                     \
+                const uint32_t T2 = addmax2(uA, SB, m1);         \
+                const uint32_t h2 = max3_2(T2, uB, FLOOR2);      \
+                const uint32_t m2 = h2 - G2;                     \
+                K[R] = max3_2(K[R], add_on_fma_pipe(h1, tvA, one), add_on_fma_pipe(h2, tvB, one)); \
+                M[R] = m2;                                       \
+                dOld = mold; uA = m1; uB = m2;                   \
             }
-            LSW_ROW(r2 * 2 + 0, s.x)
-            LSW_ROW(r2 * 2 + 1, s.y)
-#undef LSW_ROW
+            LSW_ROW2(r2 * 2 + 0, sa.x, sb.x)
+            LSW_ROW2(r2 * 2 + 1, sa.y, sb.y)
+#undef LSW_ROW2
         }
     }
 
@@ -194,10 +200,10 @@ struct ScoreLane {
                 c[0].x = c[0].y; c[0].y = c[0].z; c[0].z = c[0].w;
                 c[1].x = c[1].y; c[1].y = c[1].z; c[1].z = c[1].w;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t idx = (idx4 >> (8 * j)) & 0xFFu;
-                    column(prof + idx * PROF_STRIDE, tvec, G2, FLOOR2);
-                    tvec += 0x00010001u;
+                for (int j = 0; j < 4; j += 2) {
+                    const uint32_t ia = (idx4 >> (8 * j)) & 0xFFu, ib = (idx4 >> (8 * j + 8)) & 0xFFu;
+                    column2(prof + ia * PROF_STRIDE, prof + ib * PROF_STRIDE, tvec, tvec + 0x00010001u, G2, FLOOR2, P.one);
+                    tvec += 0x00020002u;
                 }
             }
         }
