@@ -89,7 +89,6 @@ struct lsw_ctx {
     DevBuf d_qcodes, d_qlen, d_class_seqs[NCLASS], d_cand_ok;
 
     int64_t n_reads = 0, total_bases = 0, codes_bytes = 0;
-    std::vector<int64_t> h_roff;
     std::vector<int32_t> h_rlen;
     DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen, d_order, d_order_tmp, d_len_tmp[2];
 
@@ -132,7 +131,7 @@ __global__ void k_encode_reads(const uint8_t* __restrict__ ascii, const int64_t*
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp; i < n_reads; i += nwarps) {
         const int64_t s = offs_in[i], len = offs_in[i + 1] - s, d = roff[i];
-        const int64_t padded = roff[i + 1] - d;
+        const int64_t padded = (len + 15) & ~15ll;
         for (int64_t j = lane; j < padded; j += 32) {
             const uint8_t code = j < len ? encode_base(ascii[s + j]) : (uint8_t)CODE_OTHER;
             codes[d + j] = code;
@@ -151,6 +150,16 @@ __global__ void k_init_tasks(TaskArrays t, const int32_t* __restrict__ rlen, con
         const int32_t r = order[i - (int64_t)s * n_reads];
         t.read[i] = r; t.a[i] = 0; t.b[i] = rlen[r]; t.seq[i] = (int16_t)s;
     }
+}
+
+struct PadLen {
+    __host__ __device__ long long operator()(const int32_t& len) const { return ((long long)len + 15) & ~15ll; }
+};
+
+__global__ void k_scatter_offsets(const int32_t* __restrict__ order, const long long* __restrict__ pos,
+                                  int64_t* __restrict__ roff, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        roff[order[i]] = 256 + pos[i];
 }
 
 __global__ void k_iota(int32_t* __restrict__ v, int64_t n) {
@@ -554,20 +563,19 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     if (!ctx || n < 0 || !offs || (n > 0 && !ascii && offs[n] > offs[0])) return ctx ? fail(ctx, LSW_E_ARG, "lsw_upload_reads: bad argument") : LSW_E_ARG;
     if (n >= (1ll << 26)) return fail(ctx, LSW_E_ARG, "at most 2^26 - 1 reads per batch");
     CK(cudaSetDevice(ctx->device));
-    ctx->h_roff.assign((size_t)n + 1, 0);
     ctx->h_rlen.assign((size_t)n, 0);
-    int64_t d = 256;                        // front pad: K2 reads a few codes before a window start (masked)
+    int64_t padded_total = 0;
     for (int64_t i = 0; i < n; i++) {
         const int64_t len = offs[i + 1] - offs[i];
         if (len < 0 || len >= (1ll << 27)) return fail(ctx, LSW_E_ARG, "read length must be in [0, 2^27)");
-        ctx->h_roff[i] = d;
         ctx->h_rlen[i] = (int32_t)len;
-        d += (len + 15) & ~15ll;
+        padded_total += (len + 15) & ~15ll;
     }
-    ctx->h_roff[n] = d;
     ctx->n_reads = n;
     ctx->total_bases = n ? offs[n] - offs[0] : 0;
-    ctx->codes_bytes = d + 256;             // K1 reads whole 64-byte blocks past a slice end
+    // 256 B front pad (K2 reads a few codes before a window start, masked) and 256 B tail pad (K1 reads
+    // whole 64-byte blocks past a slice end)
+    ctx->codes_bytes = 256 + padded_total + 256;
     const int64_t in_bytes = ctx->total_bases;
     CK(ctx->d_ascii.ensure((size_t)std::max<int64_t>(in_bytes, 1)));
     CK(ctx->d_offs_in.ensure((size_t)(n + 1) * 8));
@@ -578,20 +586,17 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     std::vector<int64_t> rel((size_t)n + 1);
     for (int64_t i = 0; i <= n; i++) rel[i] = offs[i] - offs[0];
     CK(cudaMemcpyAsync(ctx->d_offs_in.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_roff.p, ctx->h_roff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (n) CK(cudaMemcpyAsync(ctx->d_rlen.p, ctx->h_rlen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_codes.as<uint8_t>() + d, CODE_OTHER, 256, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_codes.as<uint8_t>() + 256 + padded_total, CODE_OTHER, 256, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_codes.as<uint8_t>(), CODE_OTHER, 256, ctx->stream));
     if (n) {
-        const int blocks = grid_for(n * 32, 256, ctx->num_sms * 16);
-        k_encode_reads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ascii.as<uint8_t>(), ctx->d_offs_in.as<int64_t>(),
-                                                        ctx->d_roff.as<int64_t>(), ctx->d_codes.as<uint8_t>(), n);
-        CK(cudaGetLastError());
-    }
-    if (n) {
-        // read indices by descending length (round-0 queue order)
+        // The device copy of the reads is laid out LONGEST READ FIRST: round 0 queues the reads in that order
+        // (the few very long reads of an ONT length distribution must not form the tail of a launch), and
+        // consecutive tasks then touch consecutive memory.  Read ids stay the caller's: roff[] is indexed by
+        // the original id and only its VALUES follow the sorted layout.
         CK(ctx->d_order.ensure((size_t)n * 4)); CK(ctx->d_order_tmp.ensure((size_t)n * 4));
         CK(ctx->d_len_tmp[0].ensure((size_t)n * 4)); CK(ctx->d_len_tmp[1].ensure((size_t)n * 4));
+        CK(ctx->d_pos.ensure((size_t)(n + 1) * 8));
         k_iota<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(ctx->d_order_tmp.as<int32_t>(), n);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctx->d_len_tmp[0].p, ctx->d_rlen.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -601,6 +606,19 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
         CK(ctx->d_cubtemp.ensure(tmp));
         CK(cub::DeviceRadixSort::SortPairsDescending(ctx->d_cubtemp.p, tmp, ctx->d_len_tmp[0].as<int32_t>(), ctx->d_len_tmp[1].as<int32_t>(),
                                                      ctx->d_order_tmp.as<int32_t>(), ctx->d_order.as<int32_t>(), (int)n, 0, 27, ctx->stream));
+        // offsets in the sorted layout: exclusive scan of the 16-byte padded sorted lengths, scattered to roff[order[i]]
+        auto padded = thrust::make_transform_iterator((const int32_t*)ctx->d_len_tmp[1].as<int32_t>(), PadLen());
+        tmp = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, padded, ctx->d_pos.as<long long>(), (int)n, ctx->stream));
+        CK(ctx->d_cubtemp.ensure(tmp));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtemp.p, tmp, padded, ctx->d_pos.as<long long>(), (int)n, ctx->stream));
+        k_scatter_offsets<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+            ctx->d_order.as<int32_t>(), ctx->d_pos.as<long long>(), ctx->d_roff.as<int64_t>(), n);
+        CK(cudaGetLastError());
+        const int blocks = grid_for(n * 32, 256, ctx->num_sms * 16);
+        k_encode_reads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ascii.as<uint8_t>(), ctx->d_offs_in.as<int64_t>(),
+                                                        ctx->d_roff.as<int64_t>(), ctx->d_codes.as<uint8_t>(), n);
+        CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(ctx->stream));      // `rel` and the caller's buffers may go away
     return LSW_OK;
