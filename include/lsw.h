@@ -123,6 +123,8 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n_tasks, const lsw_task* tasks, lsw_re
 /* findAllPrimerAlignments for every uploaded read: all queries, greedy recursion on the device.
  * Hits are returned sorted by (read, start, query) -- the order lamprey.py:722's stable sort
  * produces.  Device-resident variant: results stay on the device until lsw_fetch_hits(). */
+int lsw_set_read_base(lsw_ctx* ctx, int64_t base);     /* added to lsw_hit.read: a caller that splits one FASTQ
+                                                           batch over several contexts / GPUs gets global read ids */
 int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap);   /* 0 = default (total bases / 8 + 4096) */
 int lsw_find_all(lsw_ctx* ctx, double identity_threshold, int64_t* n_hits, lsw_counters* counters);
 int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out);

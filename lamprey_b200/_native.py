@@ -30,7 +30,7 @@ assert TASK_DT.itemsize == 16 and RESULT_DT.itemsize == 40 and HIT_DT.itemsize =
 
 # every symbol include/lsw.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",
-           "lsw_upload_reads", "lsw_align_tasks", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
+           "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
            "lsw_measure_int_peak", "lsw_version")
 
 _lib = None
@@ -57,6 +57,7 @@ def load():
     lib.lsw_upload_reads.argtypes = [vp, i64, vp, vp]
     lib.lsw_align_tasks.argtypes = [vp, i64, vp, vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_set_hit_capacity.argtypes = [vp, i64]
+    lib.lsw_set_read_base.argtypes = [vp, i64]
     lib.lsw_find_all.argtypes = [vp, dbl, ctypes.POINTER(i64), vp]
     lib.lsw_fetch_hits.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_measure_int_peak.argtypes = [vp, i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_float)]
@@ -133,6 +134,10 @@ class Engine(object):
         o = np.ascontiguousarray(offs_i64, dtype=np.int64)
         self._check(self._lib.lsw_upload_reads(self._h, len(o) - 1, _ptr(a), _ptr(o)), "lsw_upload_reads")
         self.n_reads = len(o) - 1
+
+    def set_read_base(self, base):
+        """Added to every hit's read index (for callers that split one batch over contexts or GPUs)."""
+        self._check(self._lib.lsw_set_read_base(self._h, int(base)), "lsw_set_read_base")
 
     def upload_read_list(self, reads):
         concat, offs = concat_sequences(reads)

@@ -98,6 +98,7 @@ struct lsw_ctx {
            d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_nhits, d_keys[2], d_vals[2], d_err,
            d_results, d_cigar, d_ncigar;
     int64_t hit_cap_user = 0;
+    int32_t read_base = 0;
     int64_t n_hits = 0;
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> ev_pool;
@@ -200,11 +201,13 @@ __global__ void k_hit_keys(const lsw_hit* __restrict__ hits, int64_t n, unsigned
 }
 
 __global__ void k_gather_hits(const lsw_hit* __restrict__ hits, const uint32_t* __restrict__ vals, int64_t n,
-                              lsw_hit* __restrict__ out) {
+                              lsw_hit* __restrict__ out, int32_t read_base) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int4* src = reinterpret_cast<const int4*>(hits + vals[i]);
         int4* dst = reinterpret_cast<int4*>(out + i);
-        dst[0] = src[0]; dst[1] = src[1];
+        int4 a = src[0];
+        a.x += read_base;                   // lsw_hit.read: index in the caller's whole batch (lsw_set_read_base)
+        dst[0] = a; dst[1] = src[1];
     }
 }
 
@@ -496,6 +499,12 @@ int lsw_set_stream(lsw_ctx* ctx, void* cuda_stream) {
     return LSW_OK;
 }
 
+int lsw_set_read_base(lsw_ctx* ctx, int64_t base) {
+    if (!ctx || base < 0 || base >= (1ll << 31)) return LSW_E_ARG;
+    ctx->read_base = (int32_t)base;
+    return LSW_OK;
+}
+
 int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap) {
     if (!ctx || cap < 0) return LSW_E_ARG;
     ctx->hit_cap_user = cap;
@@ -778,7 +787,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtemp.p, tmp, ctx->d_keys[0].as<unsigned long long>(), ctx->d_keys[1].as<unsigned long long>(),
                                            ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>(), (int)nh, 0, 61, ctx->stream));
         k_gather_hits<<<grid_for(nh, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
-            ctx->d_hits.as<lsw_hit>(), ctx->d_vals[1].as<uint32_t>(), nh, ctx->d_hits_sorted.as<lsw_hit>());
+            ctx->d_hits.as<lsw_hit>(), ctx->d_vals[1].as<uint32_t>(), nh, ctx->d_hits_sorted.as<lsw_hit>(), ctx->read_base);
         CK(cudaGetLastError());
         cnt.other_launches += 3;
     }

@@ -226,3 +226,37 @@ def test_full_size_properties(engine):
     m, x = whole["matches"].astype(np.int64), whole["mismatches"].astype(np.int64)
     assert (m / (m + x) >= 0.7).all() and ((whole["end"] - whole["start"]) >= qlen[whole["query"]] * 0.7).all()
     assert (whole["score"] == 2 * m - x).all()
+
+
+def test_two_contexts_split_one_batch(engine):
+    # a batch split over two contexts (own CUDA streams, own host threads) with lsw_set_read_base must give
+    # exactly the hits of the unsplit batch -- the way bench.py's e2e leg overlaps copies with kernels
+    import threading
+    from lamprey_b200 import _native
+    concat, offs = synth.generate(3000, seed=21, mean_len=900)
+    seqs = _seqs("H33")
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(seqs)
+    engine.set_read_base(0)
+    engine.upload_reads(concat, offs)
+    whole = engine.find_all(0.7).copy()
+    other = _native.Engine(0)
+    other.set_scoring(2, -1, -1, -1)
+    other.set_queries(seqs)
+    shards = seeding.shard_reads(offs, 2)
+    parts = [None, None]
+
+    def work(k, eng):
+        lo, hi = shards[k]
+        eng.set_read_base(lo)
+        eng.upload_reads(concat[offs[lo]:offs[hi]], offs[lo:hi + 1] - offs[lo])
+        parts[k] = eng.find_all(0.7).copy()
+
+    ths = [threading.Thread(target=work, args=(k, e)) for k, e in enumerate((engine, other))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    engine.set_read_base(0)
+    other.close()
+    assert np.concatenate(parts).tobytes() == whole.tobytes()
