@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-engines", type=int, default=2, help="contexts (CUDA streams) one e2e step is split over")
+    ap.add_argument("--e2e-engines", type=int, default=2, help="contexts (CUDA streams) that take alternate e2e steps")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -298,7 +298,7 @@ def main():
     # memory.  With --e2e-engines 2 (default) two contexts, each on its own CUDA stream and driven by its own
     # host thread, take alternate steps, so one batch's PCIe copies overlap the other batch's kernels -- the
     # way a caller streaming FASTQ batches would use the library.  Every step still uploads its own input
-    # and downloads its own hits inside the timed region.
+    # and downloads its own hits inside the timed region (transfers are serialised per direction).
     e2e = None
     if not args.no_e2e:
         import threading
@@ -311,43 +311,43 @@ def main():
             engines.append(e2)
         if n_eng > 1:
             eng.set_stream(0)                                        # back to the context's own non-blocking stream
-        shards = seeding.shard_reads(offs_np, n_eng)                 # contiguous read ranges balanced by bases
-        h_all = torch.empty(max(1, int(n_hits * 1.05) + 4096 * n_eng) * 32, dtype=torch.uint8, pin_memory=True)
-        hits_all = h_all.numpy().view(_native.HIT_DT)
+        bufs = []
+        for _ in engines:
+            hb = torch.empty(max(1, int(n_hits * 1.05) + 1024) * 32, dtype=torch.uint8, pin_memory=True)
+            bufs.append(hb.numpy().view(_native.HIT_DT))
         got = [0] * n_eng
-        # slice of the shared pinned hit buffer each context writes into (sized by its share of the bases)
-        cuts = [int(len(hits_all) * (offs_np[lo] - offs_np[0]) / max(1, offs_np[-1] - offs_np[0])) for lo, _ in shards] + [len(hits_all)]
+        h2d_lock, d2h_lock = threading.Lock(), threading.Lock()       # one transfer per direction at a time
 
-        def e2e_part(k):
-            lo, hi = shards[k]
-            engines[k].set_read_base(lo)
-            engines[k].upload_reads(ascii_np[offs_np[lo]:offs_np[hi]], offs_np[lo:hi + 1] - offs_np[lo])   # H2D
-            engines[k].find_all(args.thr, fetch=False)
-            got[k] = len(engines[k].fetch_hits(out=hits_all[cuts[k]:cuts[k + 1]]))                         # D2H
+        def e2e_worker(k, my_steps):
+            for _ in range(my_steps):
+                with h2d_lock:
+                    engines[k].upload_reads(ascii_np, offs_np)       # H2D of this step's reads (+ re-coding)
+                engines[k].find_all(args.thr, fetch=False)           # overlaps the other context's copies
+                with d2h_lock:
+                    got[k] = len(engines[k].fetch_hits(out=bufs[k]))  # D2H of this step's hits
 
-        def e2e_step():
-            ths = [threading.Thread(target=e2e_part, args=(k,)) for k in range(n_eng)]
+        def run_steps(total):
+            per = [total // n_eng + (1 if k < total % n_eng else 0) for k in range(n_eng)]
+            ths = [threading.Thread(target=e2e_worker, args=(k, per[k])) for k in range(n_eng) if per[k]]
             for t in ths:
                 t.start()
             for t in ths:
                 t.join()
 
-        for _ in range(max(1, args.warmup - 2)):
-            e2e_step()
+        run_steps(max(n_eng, args.warmup - 2))
         barrier()
         e0.record(stream)
-        for _ in range(args.steps):
-            e2e_step()
+        run_steps(args.steps)
         torch.cuda.synchronize()
         e1.record(stream)
         barrier()
         t_e2e = e0.elapsed_time(e1) / 1e3
         t_e2e, reads_e2e = gather_max_and_sum(t_e2e, [args.reads * args.steps])
         e2e = {"value": reads_e2e / t_e2e, "unit": "reads/s",
-               "h2d_bytes_per_step": int(ascii_np.nbytes + offs_np.nbytes), "d2h_bytes_per_step": int(sum(got) * 32),
-               "ms_per_step": 1e3 * t_e2e / args.steps, "engines": n_eng, "hits_per_step": int(sum(got)),
-               "call": "per step: lsw_upload_reads + lsw_find_all + lsw_fetch_hits from/to pinned host buffers; the batch "
-                       "is split over %d contexts (CUDA streams, one host thread each) so copies overlap kernels" % n_eng}
+               "h2d_bytes_per_step": int(ascii_np.nbytes + offs_np.nbytes), "d2h_bytes_per_step": int(max(got) * 32),
+               "ms_per_step": 1e3 * t_e2e / args.steps, "engines": n_eng, "hits_per_step": int(max(got)),
+               "call": "per step: lsw_upload_reads + lsw_find_all + lsw_fetch_hits from/to pinned host buffers; %d contexts "
+                       "(CUDA streams, one host thread each) take alternate steps so one step's copies overlap another's kernels" % n_eng}
         for e2 in engines[1:]:
             e2.close()
 
