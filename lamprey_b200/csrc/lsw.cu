@@ -93,10 +93,6 @@ struct lsw_ctx {
     DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen, d_order, d_order_tmp, d_len_tmp[2];
 
     TaskBuf tb[2], child;
-    cudaStream_t cls_stream[NCLASS] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[NCLASS] = {};
-    DevBuf d_cubtemp_cls[NCLASS], d_scratch_cls[NCLASS], d_head2;
-    bool serial = false;          // LSW_SERIAL: one stream, so per-kernel CUDA-event times do not overlap
     DevBuf d_fallback[NCLASS], d_nfallback, d_cand_key[NCLASS], d_cand_sorted[NCLASS], d_cand_key_sorted[NCLASS];
     DevBuf d_res, d_seg[2], d_head, d_cand[NCLASS], d_ncand, d_counters, d_child_flag, d_pos,
            d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_nhits, d_keys[2], d_vals[2], d_err,
@@ -233,17 +229,17 @@ cudaEvent_t next_event(lsw_ctx* ctx) {
     return ctx->ev_pool[ctx->ev_used++];
 }
 
-struct Span {      // times a region of a stream into one of the lsw_counters buckets
-    lsw_ctx* ctx; Timed t; cudaStream_t st;
-    Span(lsw_ctx* c, int kind, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream) {
+struct Span {      // times a region of the stream into one of the lsw_counters buckets
+    lsw_ctx* ctx; Timed t;
+    Span(lsw_ctx* c, int kind) : ctx(c) {
         t.kind = kind; t.e0 = next_event(c); t.e1 = next_event(c);
-        if (t.e0) cudaEventRecord(t.e0, st);
+        if (t.e0) cudaEventRecord(t.e0, c->stream);
     }
-    ~Span() { if (t.e1) { cudaEventRecord(t.e1, st); ctx->timed.push_back(t); } }
+    ~Span() { if (t.e1) { cudaEventRecord(t.e1, ctx->stream); ctx->timed.push_back(t); } }
 };
 
 template <int NR>
-int launch_score(lsw_ctx* ctx, const ScoreParams& P, int64_t n_class_tasks, cudaStream_t st) {
+int launch_score(lsw_ctx* ctx, const ScoreParams& P, int64_t n_class_tasks) {
     const size_t smem = score_smem_bytes<NR>();
     CK(cudaFuncSetAttribute(k_score<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -251,27 +247,27 @@ int launch_score(lsw_ctx* ctx, const ScoreParams& P, int64_t n_class_tasks, cuda
     if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "score kernel does not fit on an SM");
     const int64_t lanes_needed = (n_class_tasks + 1) / 2;
     const int blocks = grid_for(lanes_needed, SCORE_WARPS * 32, ctx->num_sms * occ);
-    k_score<NR><<<blocks, SCORE_WARPS * 32, smem, st>>>(P);
+    k_score<NR><<<blocks, SCORE_WARPS * 32, smem, ctx->stream>>>(P);
     CK(cudaGetLastError());
     return LSW_OK;
 }
 
-int launch_score_class(lsw_ctx* ctx, int c, const ScoreParams& P, int64_t n, cudaStream_t st) {
+int launch_score_class(lsw_ctx* ctx, int c, const ScoreParams& P, int64_t n) {
     switch (CLASS_NR[c]) {
-        case 16: return launch_score<16>(ctx, P, n, st);
-        case 20: return launch_score<20>(ctx, P, n, st);
-        case 24: return launch_score<24>(ctx, P, n, st);
-        case 28: return launch_score<28>(ctx, P, n, st);
-        case 32: return launch_score<32>(ctx, P, n, st);
-        case 40: return launch_score<40>(ctx, P, n, st);
-        case 48: return launch_score<48>(ctx, P, n, st);
-        case 56: return launch_score<56>(ctx, P, n, st);
-        default: return launch_score<64>(ctx, P, n, st);
+        case 16: return launch_score<16>(ctx, P, n);
+        case 20: return launch_score<20>(ctx, P, n);
+        case 24: return launch_score<24>(ctx, P, n);
+        case 28: return launch_score<28>(ctx, P, n);
+        case 32: return launch_score<32>(ctx, P, n);
+        case 40: return launch_score<40>(ctx, P, n);
+        case 48: return launch_score<48>(ctx, P, n);
+        case 56: return launch_score<56>(ctx, P, n);
+        default: return launch_score<64>(ctx, P, n);
     }
 }
 
 template <int NR, int NR2>
-int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax, cudaStream_t st, DevBuf& scratch) {
+int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     // short-window kernel over every candidate of the class: one lane per PAIR of candidates
     const size_t smem = trace_smem_bytes<NR>();
     CK(cudaFuncSetAttribute(k_trace_fast<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -292,28 +288,28 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax, c
     if ((size_t)threads * (size_t)(Wf + 4) * (NR / 2) >= (1ull << 31))
         return fail(ctx, LSW_E_INTERNAL, "traceback scratch exceeds the 32-bit index range");
     const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * (NR / 2) * 4, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
-    CK(scratch.ensure(need));
-    P.scratch = scratch.as<uint32_t>();
+    CK(ctx->d_scratch.ensure(need));
+    P.scratch = ctx->d_scratch.as<uint32_t>();
     P.scratch_stride = threads;
-    k_trace_fast<NR><<<blocks, TRACE_THREADS, smem, st>>>(P);
+    k_trace_fast<NR><<<blocks, TRACE_THREADS, smem, ctx->stream>>>(P);
     CK(cudaGetLastError());
     P.scratch_stride = threads2;
-    k_trace_full<NR2><<<blocks2, TRACE_THREADS, 0, st>>>(P);
+    k_trace_full<NR2><<<blocks2, TRACE_THREADS, 0, ctx->stream>>>(P);
     CK(cudaGetLastError());
     return LSW_OK;
 }
 
-int launch_trace_class(lsw_ctx* ctx, int c, const TraceParams& P, int64_t n, int qmax, cudaStream_t st, DevBuf& scratch) {
+int launch_trace_class(lsw_ctx* ctx, int c, const TraceParams& P, int64_t n, int qmax) {
     switch (CLASS_NR[c]) {
-        case 16: return launch_trace<16, 16>(ctx, P, n, qmax, st, scratch);
-        case 20: return launch_trace<20, 32>(ctx, P, n, qmax, st, scratch);
-        case 24: return launch_trace<24, 32>(ctx, P, n, qmax, st, scratch);
-        case 28: return launch_trace<28, 32>(ctx, P, n, qmax, st, scratch);
-        case 32: return launch_trace<32, 32>(ctx, P, n, qmax, st, scratch);
-        case 40: return launch_trace<40, 48>(ctx, P, n, qmax, st, scratch);
-        case 48: return launch_trace<48, 48>(ctx, P, n, qmax, st, scratch);
-        case 56: return launch_trace<56, 64>(ctx, P, n, qmax, st, scratch);
-        default: return launch_trace<64, 64>(ctx, P, n, qmax, st, scratch);
+        case 16: return launch_trace<16, 16>(ctx, P, n, qmax);
+        case 20: return launch_trace<20, 32>(ctx, P, n, qmax);
+        case 24: return launch_trace<24, 32>(ctx, P, n, qmax);
+        case 28: return launch_trace<28, 32>(ctx, P, n, qmax);
+        case 32: return launch_trace<32, 32>(ctx, P, n, qmax);
+        case 40: return launch_trace<40, 48>(ctx, P, n, qmax);
+        case 48: return launch_trace<48, 48>(ctx, P, n, qmax);
+        case 56: return launch_trace<56, 64>(ctx, P, n, qmax);
+        default: return launch_trace<64, 64>(ctx, P, n, qmax);
     }
 }
 
@@ -370,67 +366,55 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             CK(cudaMemsetAsync(ctx->d_cand_key[c].p, 0xFF, (size_t)ncls[c] * 2, ctx->stream));
         }
     }
-    CK(ctx->d_head2.ensure((size_t)ctx->nseq * 8));
-    CK(cudaMemsetAsync(ctx->d_head2.p, 0, (size_t)ctx->nseq * 8, ctx->stream));      // K2's per-sequence queue heads
     ScoreParams P;
     fill_score_params(ctx, P, cur, segi);
-
-    // Every class runs K1 -> sort candidates -> K2 on its own stream (forked from / joined to the context
-    // stream), largest class first: the tail of one class's persistent launch is filled by the next class's
-    // blocks, and the latency-bound K2 of one class overlaps the ALU-bound K1 of another.  LSW_SERIAL keeps
-    // everything on the context stream so that per-kernel event times are not overlapped (roofline runs).
-    int order[NCLASS];
-    for (int c = 0; c < NCLASS; c++) order[c] = c;
-    std::sort(order, order + NCLASS, [&](int x, int y) { return ncls[x] * CLASS_NR[x] > ncls[y] * CLASS_NR[y]; });
-    const bool fork = !ctx->serial;
-    if (fork) CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    for (int k = 0; k < NCLASS; k++) {
-        const int c = order[k];
-        if (!ncls[c]) continue;
-        cudaStream_t st = fork ? ctx->cls_stream[c] : ctx->stream;
-        if (fork) CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
-        {
-            Span sp(ctx, 0, st);
+    {
+        Span sp(ctx, 0);
+        for (int c = 0; c < NCLASS; c++) {
+            if (!ncls[c]) continue;
             P.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
             P.n_class_seqs = (int)ctx->class_seqs[c].size();
             P.cand = ctx->d_cand[c].as<uint32_t>();
             P.cand_key = ctx->d_cand_key[c].as<uint16_t>();
             P.ncand = ctx->d_ncand.as<unsigned long long>() + c;
-            int rc = launch_score_class(ctx, c, P, ncls[c], st);
+            int rc = launch_score_class(ctx, c, P, ncls[c]);
             if (rc) return rc;
             if (cnt) cnt->score_launches++;
         }
-        {
-            // order the class's candidates by (sequence, traceback window length): K2 warps serve one sequence at a
-            // time and their lanes then fill windows of similar length
-            Span sp(ctx, 2, st);
+    }
+    {
+        // order each class's candidates by (sequence, traceback window length): K2 warps serve one sequence at a
+        // time and their lanes then fill windows of similar length
+        Span sp(ctx, 2);
+        for (int c = 0; c < NCLASS; c++) {
+            if (!ncls[c]) continue;
             size_t tmp = 0;
             CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cand_key[c].as<uint16_t>(), ctx->d_cand_key_sorted[c].as<uint16_t>(),
-                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 16, st));
-            CK(ctx->d_cubtemp_cls[c].ensure(tmp));
-            CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtemp_cls[c].p, tmp, ctx->d_cand_key[c].as<uint16_t>(), ctx->d_cand_key_sorted[c].as<uint16_t>(),
-                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 16, st));
+                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 16, ctx->stream));
+            CK(ctx->d_cubtemp.ensure(tmp));
+            CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtemp.p, tmp, ctx->d_cand_key[c].as<uint16_t>(), ctx->d_cand_key_sorted[c].as<uint16_t>(),
+                                               ctx->d_cand[c].as<uint32_t>(), ctx->d_cand_sorted[c].as<uint32_t>(), (int)ncls[c], 0, 16, ctx->stream));
             if (cnt) cnt->other_launches += 2;
         }
-        {
-            Span sp(ctx, 1, st);
+        CK(cudaMemsetAsync(ctx->d_head.p, 0, (size_t)ctx->nseq * 8, ctx->stream));     // K2 reuses the per-sequence queue heads
+    }
+    {
+        Span sp(ctx, 1);
+        for (int c = 0; c < NCLASS; c++) {
+            if (!ncls[c]) continue;
             TraceParams T = Tbase;
             T.res = ctx->d_res.as<int2>();
             T.cand = ctx->d_cand_sorted[c].as<uint32_t>();
             T.cand_key = ctx->d_cand_key_sorted[c].as<uint16_t>();
-            T.head = ctx->d_head2.as<unsigned long long>();
+            T.head = ctx->d_head.as<unsigned long long>();
             T.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
             T.n_class_seqs = (int)ctx->class_seqs[c].size();
             T.ncand = ctx->d_ncand.as<unsigned long long>() + c;
             T.fallback = ctx->d_fallback[c].as<uint32_t>();
             T.nfallback = ctx->d_nfallback.as<unsigned long long>() + c;
-            int rc = launch_trace_class(ctx, c, T, ncls[c], qmax[c], st, ctx->d_scratch_cls[c]);
+            int rc = launch_trace_class(ctx, c, T, ncls[c], qmax[c]);
             if (rc) return rc;
             if (cnt) cnt->trace_launches += 2;
-        }
-        if (fork) {
-            CK(cudaEventRecord(ctx->ev_join[c], st));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[c], 0));
         }
     }
     return LSW_OK;
@@ -484,11 +468,6 @@ int lsw_create(int device, lsw_ctx** out) {
         g_create_error = cudaGetErrorString(e); delete ctx; return LSW_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int c = 0; c < NCLASS && ok; c++)
-        ok = cudaStreamCreateWithFlags(&ctx->cls_stream[c], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) { g_create_error = "lsw_create: could not create streams/events"; lsw_destroy(ctx); return LSW_E_CUDA; }
     *out = ctx;
     return LSW_OK;
 }
@@ -508,13 +487,6 @@ void lsw_destroy(lsw_ctx* ctx) {
     ctx->d_nfallback.release();
     ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
-    for (int c = 0; c < NCLASS; c++) {
-        ctx->d_cubtemp_cls[c].release(); ctx->d_scratch_cls[c].release();
-        if (ctx->cls_stream[c]) cudaStreamDestroy(ctx->cls_stream[c]);
-        if (ctx->ev_join[c]) cudaEventDestroy(ctx->ev_join[c]);
-    }
-    ctx->d_head2.release();
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -669,7 +641,6 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     lsw_counters cnt;
     memset(&cnt, 0, sizeof cnt);
     ctx->timed.clear(); ctx->ev_used = 0;
-    ctx->serial = getenv("LSW_SERIAL") && atoi(getenv("LSW_SERIAL")) != 0;
     ctx->n_hits = 0;
     if (n_hits) *n_hits = 0;
     const int64_t n0 = ctx->n_reads * ctx->nseq;
