@@ -290,7 +290,8 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * (NR / 2) * 4, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
     CK(ctx->d_scratch.ensure(need));
     P.scratch = ctx->d_scratch.as<uint32_t>();
-    P.scratch_stride = threads;
+    P.scratch_stride = TRACE_THREADS;
+    P.scratch_block_words = (int64_t)(Wf + 4) * (NR / 2) * TRACE_THREADS;
     k_trace_fast<NR><<<blocks, TRACE_THREADS, smem, ctx->stream>>>(P);
     CK(cudaGetLastError());
     P.scratch_stride = threads2;

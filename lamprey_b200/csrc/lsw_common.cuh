@@ -141,7 +141,8 @@ struct TraceParams {
     uint32_t*       fallback;     // tasks the short-window kernel could not prove exact
     unsigned long long* nfallback;
     uint32_t*       scratch;      // direction bits, [window col][word][thread]
-    int64_t         scratch_stride;   // threads in the launch
+    int64_t         scratch_stride;   // words between consecutive (column, word) rows: threads of a block (fast) / of the launch (full)
+    int64_t         scratch_block_words;  // k_trace_fast: scratch words per block
     int32_t match, mismatch, g;
     int32_t mode;             // 0 = find_all (hit test, children), 1 = align_tasks (result records, CIGAR)
     double  thr;

@@ -525,7 +525,9 @@ k_trace_fast(const TraceParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     U2* prof = reinterpret_cast<U2*>(smem_raw) + (size_t)warp * NIDX * Lane::PROF_STRIDE;
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // scratch is block-local: [block][window column][word][lane of the block], so a block's windows are one
+    // contiguous region (a handful of pages) instead of rows strided across the whole launch
+    const int64_t slot = (int64_t)blockIdx.x * P.scratch_block_words + threadIdx.x;
     const long long ncand = (long long)*P.ncand;
     // segment of every sequence of the class in the sorted candidate list, found once per block
     long long* seg_lo = reinterpret_cast<long long*>(smem_raw + trace_prof_bytes<NR>());
