@@ -56,7 +56,7 @@ def gather_max_and_sum(t_local, sums, device="cuda"):
 _CPU = {}
 
 
-def _cpu_init(schema_path):
+def _cpu_init(schema_path, n_names=None):
     import importlib.util
     from oracle import build_cython
     out = build_cython.build()
@@ -69,6 +69,8 @@ def _cpu_init(schema_path):
     _CPU["sw"] = mods["swalign_cy"].LocalAlignment(mods["swalign_cy"].NucleotideScoringMatrix(2, -1))
     _CPU["seed"] = mods["seeding_cy"]
     _CPU["ps"] = mods["seeding_cy"].PrimerSet(schema_path)
+    if n_names:          # workloads that search only the first n named sequences of the schema
+        _CPU["ps"].primer_dict = dict(list(_CPU["ps"].primer_dict.items())[:n_names])
 
 
 def _cpu_seed(args):
@@ -78,12 +80,12 @@ def _cpu_seed(args):
     return len(hits), st.calls, st.cells
 
 
-def cpu_seed_sample(reads, thr, cores, pool=None):
+def cpu_seed_sample(reads, thr, cores, pool=None, n_names=None):
     """-> (seconds, hits, calls, cells) for seeding `reads` on `cores` processes."""
     import multiprocessing as mp
     own = pool is None
     if own:
-        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(SCHEMA,))
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(SCHEMA, n_names))
         pool.map(_cpu_seed, [("ACGT" * 8, thr)] * cores)        # start-up (imports) outside the timing
     t0 = time.perf_counter()
     res = pool.map(_cpu_seed, [(r, thr) for r in reads], chunksize=1)
@@ -150,7 +152,7 @@ def run_reference(args):
     concat, offs = synth.generate(sample * (args.steps + args.warmup), chunk=sample, **kw)
     reads = synth.reads_as_strings(concat, offs)
     import multiprocessing as mp
-    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(SCHEMA,))
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(SCHEMA, synth.SCHEMA_NAMES.get(args.workload)))
     pool.map(_cpu_seed, [("ACGT" * 8, args.thr)] * cores)
     k = 0
     for _ in range(args.warmup):
@@ -209,7 +211,7 @@ def main():
         per_read = 2.2 * (np.diff(offs).mean() / 2000.0) ** 1.0
         sample = int(max(cores, min(len(offs) - 1, cores * args.cpu_seconds / per_read)))
         reads = synth.reads_as_strings(concat[:offs[sample]], offs[:sample + 1])
-        dt, hits_cpu, calls_cpu, cells_cpu = cpu_seed_sample(reads, args.thr, cores)
+        dt, hits_cpu, calls_cpu, cells_cpu = cpu_seed_sample(reads, args.thr, cores, n_names=synth.SCHEMA_NAMES.get(args.workload))
         cpu_baseline = {"value": sample / dt, "unit": "reads/s", "cores": cores, "kind": "port",
                         "gcups": cells_cpu / dt / 1e9, "seconds": dt,
                         "sample": "first %d reads of the workload, Cython build of oracle/swalign_ref.py + "
@@ -230,7 +232,8 @@ def main():
     eng.set_stream(stream.cuda_stream)
     eng.set_scoring(2, -1, -1, -1)
     ps = seeding.PrimerSet(SCHEMA)
-    seqs = [s for _, s in ps.sequences()]
+    from lamprey_b200 import synth as _synth
+    seqs = [s for _, s in _synth.schema_sequences(ps, args.workload)]
     eng.set_queries(seqs)
 
     def barrier():
@@ -373,7 +376,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16x2",
                 "data": "synthetic", "gcups": gcups, "gcups_top_level": cnt["top_cells"] * args.steps * world / t_value / 1e9,
                 "config": {"workload": args.workload, "reads_per_gpu": args.reads, "mean_len": float(np.diff(offs).mean()),
-                           "schema": "H3.3_set1 (46 sequences, 1140 rows)", "threshold": args.thr,
+                           "schema": "H3.3_set1 (%d sequences, %d rows)" % (len(seqs), sum(len(q) for q in seqs)), "threshold": args.thr,
                            "l2": "inputs larger than L2 (%.2f GB of read codes + task lists per step)" % (len(concat) / 1e9),
                            "tasks_per_step": cnt["tasks"], "cells_per_step": cnt["cells"], "hits_per_step": n_hits,
                            "rounds": cnt["rounds"]},

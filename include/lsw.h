@@ -125,6 +125,10 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n_tasks, const lsw_task* tasks, lsw_re
  * produces.  Device-resident variant: results stay on the device until lsw_fetch_hits(). */
 int lsw_set_read_base(lsw_ctx* ctx, int64_t base);     /* added to lsw_hit.read: a caller that splits one FASTQ
                                                            batch over several contexts / GPUs gets global read ids */
+/* removeOverlappingPrimerAlignments (lamprey.py:859-899, called with 4 at lamprey.py:1536) on the device: with
+ * allowed_overlap >= 0 every hit lsw_find_all returns has reserved = 1 if it survives the pruning of its read's
+ * sorted hit list, 0 otherwise.  Negative (default) = off. */
+int lsw_set_overlap(lsw_ctx* ctx, int allowed_overlap);
 int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap);   /* 0 = default (total bases / 8 + 4096) */
 int lsw_find_all(lsw_ctx* ctx, double identity_threshold, int64_t* n_hits, lsw_counters* counters);
 int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out);

@@ -30,7 +30,7 @@ assert TASK_DT.itemsize == 16 and RESULT_DT.itemsize == 40 and HIT_DT.itemsize =
 
 # every symbol include/lsw.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",
-           "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
+           "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_overlap", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
            "lsw_measure_int_peak", "lsw_version")
 
 _lib = None
@@ -58,6 +58,7 @@ def load():
     lib.lsw_align_tasks.argtypes = [vp, i64, vp, vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_set_hit_capacity.argtypes = [vp, i64]
     lib.lsw_set_read_base.argtypes = [vp, i64]
+    lib.lsw_set_overlap.argtypes = [vp, i32]
     lib.lsw_find_all.argtypes = [vp, dbl, ctypes.POINTER(i64), vp]
     lib.lsw_fetch_hits.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_measure_int_peak.argtypes = [vp, i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_float)]
@@ -138,6 +139,10 @@ class Engine(object):
     def set_read_base(self, base):
         """Added to every hit's read index (for callers that split one batch over contexts or GPUs)."""
         self._check(self._lib.lsw_set_read_base(self._h, int(base)), "lsw_set_read_base")
+
+    def set_overlap(self, allowed_overlap):
+        """>= 0: hits come back with reserved = 1 if they survive removeOverlappingPrimerAlignments; None/-1: off."""
+        self._check(self._lib.lsw_set_overlap(self._h, -1 if allowed_overlap is None else int(allowed_overlap)), "lsw_set_overlap")
 
     def upload_read_list(self, reads):
         concat, offs = concat_sequences(reads)

@@ -99,6 +99,7 @@ struct lsw_ctx {
            d_results, d_cigar, d_ncigar;
     int64_t hit_cap_user = 0;
     int32_t read_base = 0;
+    int32_t allowed_overlap = -1;
     int64_t n_hits = 0;
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> ev_pool;
@@ -208,6 +209,18 @@ __global__ void k_gather_hits(const lsw_hit* __restrict__ hits, const uint32_t* 
         int4 a = src[0];
         a.x += read_base;                   // lsw_hit.read: index in the caller's whole batch (lsw_set_read_base)
         dst[0] = a; dst[1] = src[1];
+    }
+}
+
+// one thread per read: find the read's segment in the sorted hits and prune overlaps (lsw_set_overlap)
+__global__ void k_prune_overlaps(lsw_hit* __restrict__ hits, int64_t n_hits, int64_t n_reads, int32_t read_base, int allowed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t rid = (int32_t)i + read_base;
+        long long lo = 0, hi = n_hits;
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if (hits[mid].read < rid) lo = mid + 1; else hi = mid; }
+        long long e = lo, eh = n_hits;
+        while (e < eh) { const long long mid = (e + eh) >> 1; if (hits[mid].read <= rid) e = mid + 1; else eh = mid; }
+        prune_overlaps_read(hits, lo, e, allowed);
     }
 }
 
@@ -506,6 +519,12 @@ int lsw_set_read_base(lsw_ctx* ctx, int64_t base) {
     return LSW_OK;
 }
 
+int lsw_set_overlap(lsw_ctx* ctx, int allowed_overlap) {
+    if (!ctx) return LSW_E_ARG;
+    ctx->allowed_overlap = allowed_overlap < 0 ? -1 : allowed_overlap;
+    return LSW_OK;
+}
+
 int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap) {
     if (!ctx || cap < 0) return LSW_E_ARG;
     ctx->hit_cap_user = cap;
@@ -791,6 +810,12 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
             ctx->d_hits.as<lsw_hit>(), ctx->d_vals[1].as<uint32_t>(), nh, ctx->d_hits_sorted.as<lsw_hit>(), ctx->read_base);
         CK(cudaGetLastError());
         cnt.other_launches += 3;
+        if (ctx->allowed_overlap >= 0) {
+            k_prune_overlaps<<<grid_for(ctx->n_reads, 128, ctx->num_sms * 8), 128, 0, ctx->stream>>>(
+                ctx->d_hits_sorted.as<lsw_hit>(), nh, ctx->n_reads, ctx->read_base, ctx->allowed_overlap);
+            CK(cudaGetLastError());
+            cnt.other_launches += 1;
+        }
     }
     if (tt.e1) { cudaEventRecord(tt.e1, ctx->stream); ctx->timed.push_back(tt); }
     CK(cudaStreamSynchronize(ctx->stream));

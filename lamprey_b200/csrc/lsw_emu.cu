@@ -188,7 +188,8 @@ extern "C" {
 
 int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
                      const int32_t* qoffs, int match, int mismatch, int gap, double thr, lsw_hit* out, int64_t cap,
-                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds, traced, fallbacks */, int force_full) {
+                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds, traced, fallbacks */, int force_full,
+                     int allowed_overlap) {
     Emu E;
     E.force_full = force_full != 0;
     if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, match, mismatch, gap)) return LSW_E_UNSUPPORTED;
@@ -241,6 +242,15 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
         if (x.start != y.start) return x.start < y.start;
         return x.query < y.query;
     });
+    if (allowed_overlap >= 0) {
+        long long lo = 0;
+        while (lo < (long long)nhits) {
+            long long hi = lo;
+            while (hi < (long long)nhits && out[hi].read == out[lo].read) hi++;
+            prune_overlaps_read(out, lo, hi, allowed_overlap);
+            lo = hi;
+        }
+    }
     return LSW_OK;
 }
 

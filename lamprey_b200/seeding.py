@@ -116,11 +116,16 @@ class SeedBatch(object):
     def __len__(self):
         return len(self.offsets) - 1
 
-    def alignments(self, i):
+    @property
+    def kept(self):
+        """Mask of the hits that survive removeOverlappingPrimerAlignments (needs seed_reads(allowed_overlap=...))."""
+        return self.hits["reserved"] == 1
+
+    def alignments(self, i, pruned=False):
         lo, hi = self.offsets[i], self.offsets[i + 1]
         h = self.hits[lo:hi]
         return [Alignment(int(x["start"]), int(x["end"]), float(self.identity[lo + k]), self.names[x["query"]])
-                for k, x in enumerate(h)]
+                for k, x in enumerate(h) if not pruned or x["reserved"] == 1]
 
     def __getitem__(self, i):
         """(sorted alignment list, coverage) -- findAllPrimerAlignments' return value for read i."""
@@ -129,8 +134,9 @@ class SeedBatch(object):
         return self.alignments(i), float(self.coverage[i])
 
 
-def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None):
-    """findAllPrimerAlignments for every read of a batch in one device pass."""
+def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None):
+    """findAllPrimerAlignments for every read of a batch in one device pass.  allowed_overlap (LAMPrey uses 4,
+    lamprey.py:1536) also runs removeOverlappingPrimerAlignments on the device: see SeedBatch.kept."""
     from . import swalign as _sw
     concat, offs = _read_arrays(reads)
     pairs = primer_set.sequences()
@@ -143,7 +149,9 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
         eng.set_scoring(2, -1, -1, -1)                  # initAligners, lamprey.py:1860-1865
     eng.set_queries([s for _, s in pairs])
     eng.upload_reads(concat, offs)
+    eng.set_overlap(allowed_overlap)
     hits = eng.find_all(threshold)
+    eng.set_overlap(None)
     return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters)
 
 

@@ -113,13 +113,32 @@ def generate(n_reads, seed=3, mean_len=2000, error=0.08, schema="H33", length_ki
     return concat, offs
 
 
+_BARCODES = ["AAGAAAGTTGTCGGTGTCTTTGTG", "TCGATTCCGTTTGTAGTCGTCTGT", "GAGTCTTGTGTCCCAGTTACCAGG",
+             "TTCGGATTCTATCGTGTTTCCCTA", "CTTGTCCAGGGTTTGTGTAACCTT", "TTCTCGCAAAGGCAGAAAGTAGTC",
+             "GTGTTACCGTGGGAATGAATCCTT", "TTCAGGGAACAAACCAAGTTACGT", "AACTAGGCACAGCGAGTCTTGGTT"]   # ontBC01..09
+
 CONFIGS = {
     # BASELINE.json configs[2..4] / SURVEY.md section 8d
     "synth_2kb_8pct": dict(mean_len=2000, error=0.08, min_len=200, max_len=20000, seed=3, schema="H33"),
     "synth_5kb_12pct": dict(mean_len=5000, error=0.12, min_len=500, max_len=50000, seed=4, schema="H33"),
+    # long-read stress: dense concatemers, one adapter + random barcode at the read head
     "synth_20_50kb_12pct": dict(length_kind="uniform", min_len=20000, max_len=50000, error=0.12, seed=5,
-                                schema="H33", adapter_p=1.0),
+                                schema="H33", adapter_p=1.0,
+                                heads=[(ONT_RAP_TOP + b).encode() for b in _BARCODES]),
 }
+# schema used with a workload: number of NAMED sequences taken from the schema file (None = all)
+SCHEMA_NAMES = {"synth_20_50kb_12pct": 20}
+
+
+def schema_sequences(primer_set, workload):
+    """The (name, sequence) search list of a workload: BASELINE.json's long-read config uses the first 20 named
+    sequences of the H3.3 schema (40 with reverse complements), the others the whole schema."""
+    pairs = primer_set.sequences()
+    n = SCHEMA_NAMES.get(workload)
+    if n is None:
+        return pairs
+    keep = set(list(primer_set.primer_dict)[:n])
+    return [(nm, sq) for nm, sq in pairs if (nm[:-1] if nm.endswith("c") and nm[:-1] in primer_set.primer_dict else nm) in keep]
 
 
 def reads_as_strings(concat, offs):

@@ -260,3 +260,19 @@ def test_two_contexts_split_one_batch(engine):
     engine.set_read_base(0)
     other.close()
     assert np.concatenate(parts).tobytes() == whole.tobytes()
+
+
+def test_device_overlap_pruning(engine):
+    from lamprey_b200 import chain
+    reads = load_reads("1k")
+    ps = seeding.PrimerSet(schema_path("H33"))
+    batch = seeding.seed_reads(reads, ps, 0.70, allowed_overlap=4)
+    gold = load_seed_golden("1k", "H33", 0.70)
+    assert np.array_equal(hits_matrix(batch.hits), gold["hits"])           # pruning only sets the flag
+    assert 0 < batch.kept.sum() < len(batch.hits)
+    for i in range(0, len(reads), 7):
+        al = batch.alignments(i)
+        if al:
+            want = chain.removeOverlappingPrimerAlignments(False, al, 4)  # lamprey.py:1536
+            got = batch.alignments(i, pruned=True)
+            assert [(a.start, a.end, a.primer_name) for a in got] == [(a.start, a.end, a.primer_name) for a in want]
