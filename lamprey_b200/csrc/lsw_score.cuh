@@ -16,7 +16,7 @@
 //        T     = max(Mold[r-1] + s'', Mold[r])              s'' = 256*(s + g)
 //        h     = max(T, Mnew[r-1], 256*g)                   h   = 256*(H + g)
 //        Mnew  = h - 256*g                                  (= 256*H, never borrows)
-//        K[r]  = max(K[r], h + step)                        arg-max key, step in the low byte
+//        K[r/2] = max(K[r/2], h + 64*(r&1) + step)          arg-max key of a row pair: row bit and step in the low byte
 //    i.e. 3 ALU-pipe DPX ops + 1 add per TWO cells.
 //  * every BLOCK_STEPS columns the lane folds K into its per-task best (value, row, column)
 //    with swalign's tie rule (last cell in row-major order wins: highest row, then highest
@@ -35,7 +35,7 @@ struct ScoreLane {
     static constexpr int PROF_STRIDE = NR / 2 + 1;      // 8-byte words per profile row: odd, see NIDX
 
     uint32_t M[NR];        // 256 * H of the previous column, two tasks packed
-    uint32_t K[NR];        // running max of (256*(H+g) + step) over the current block
+    uint32_t K[NR / 2];    // per ROW PAIR: running max of (256*(H+g) + 64*(row & 1) + step) over the current block
     int32_t  tid[2];       // task index, -1 = half idle
     int64_t  pos[2];       // byte offset (16-aligned) in codes of step 0 of the next block
     int32_t  begin[2];     // first live step of the next block (only the first block of a task is > 0)
@@ -49,7 +49,9 @@ struct ScoreLane {
 
     LSW_HD void init() {
 #pragma unroll
-        for (int r = 0; r < NR; r++) { M[r] = 0; K[r] = 0; }
+        for (int r = 0; r < NR; r++) M[r] = 0;
+#pragma unroll
+        for (int r = 0; r < NR / 2; r++) K[r] = 0;
         tid[0] = tid[1] = -1;
         rem[0] = rem[1] = 0; begin[0] = begin[1] = 0;
         pos[0] = pos[1] = 0; cbase[0] = cbase[1] = 0;
@@ -113,7 +115,7 @@ struct ScoreLane {
             row = len[h] > 0 ? Q : 0;
             col = len[h] > 0 ? len[h] : 0;
         } else {
-            row = (int)((best[h] >> 8) & 0xFF) + 1;
+            row = (int)((best[h] >> 8) & 0xFF) + (int)((best[h] >> 6) & 1) + 1;
             col = bestc[h];
         }
         P.res[t] = make_int2(score | (row << 16), col);
@@ -144,7 +146,8 @@ struct ScoreLane {
                 const uint32_t T2 = addmax2(uA, SB, m1);         \
                 const uint32_t h2 = max3_2(T2, uB, FLOOR2);      \
                 const uint32_t m2 = h2 - G2;                     \
-                K[R] = max3_2(K[R], add_on_fma_pipe(h1, tvA, one), add_on_fma_pipe(h2, tvB, one)); \
+                K[(R) >> 1] = max3_2(K[(R) >> 1], add_on_fma_pipe(h1, tvA + ((R) & 1) * 0x00400040u, one),       \
+                                     add_on_fma_pipe(h2, tvB + ((R) & 1) * 0x00400040u, one)); \
                 M[R] = m2;                                       \
                 dOld = mold; uA = m1; uB = m2;                   \
             }
@@ -167,7 +170,7 @@ struct ScoreLane {
             else begin[h] = 0;
         }
 #pragma unroll
-        for (int r = 0; r < NR; r++) K[r] = 0;
+        for (int r = 0; r < NR / 2; r++) K[r] = 0;
 
         uint32_t tvec = 0;
 #pragma unroll 1
@@ -213,17 +216,19 @@ struct ScoreLane {
         for (int h = 0; h < 2; h++) {
             uint32_t bb = 0;
 #pragma unroll
-            for (int r = 0; r < NR; r++) {
-                if (r < Q) {
-                    // bytes of K[r]: [step_lo, H_lo, step_hi, H_hi]  ->  [step, row, H, 0]
-                    const uint32_t key = prmt(K[r], (uint32_t)r, h ? 0x5342u : 0x5140u);
+            for (int r2 = 0; r2 < NR / 2; r2++) {
+                if (2 * r2 < Q) {
+                    // bytes of K[r2]: [low_lo, H_lo, low_hi, H_hi] with low = 64 * (row & 1) + step
+                    //   ->  [low, 2 * r2, H, 0]: ordered by (H, row, step) because 256 * (2 r2) + low is monotone in (row, step).
+                    // (If Q is odd the padding row Q can be the pair's best only with a value below a real cell's: see DESIGN.md.)
+                    const uint32_t key = prmt(K[r2], (uint32_t)(2 * r2), h ? 0x5342u : 0x5140u);
                     bb = key > bb ? key : bb;
                 }
             }
             if (tid[h] >= 0) {
-                if ((bb >> 8) >= (best[h] >> 8)) {       // >= : a later block wins ties on (H, row)
+                if ((bb >> 6) >= (best[h] >> 6)) {       // >= : a later block wins ties on (H, row); bits 6.. hold (H, row)
                     best[h] = bb;
-                    bestc[h] = cbase[h] + (int32_t)(bb & 0xFF);
+                    bestc[h] = cbase[h] + (int32_t)(bb & 0x3F);
                 }
                 rem[h] -= end[h] - begin[h];
                 begin[h] = 0;
@@ -259,10 +264,12 @@ constexpr int SCORE_WARPS = 4;
 
 // resident blocks per SM the register allocator must allow for (65536 / (128 threads * regs))
 #ifndef LSW_OCC_BOOST
-#define LSW_OCC_BOOST 0      // measured on B200: forcing 5-6 blocks/SM spills in the column loop and costs 20 %
+#define LSW_OCC_BOOST 2      // measured on B200: 128 registers (4 blocks/SM) for NR <= 28 is spill-free and 1.5 % faster; forcing 5-6 blocks spills and costs 20 %
 #endif
 template <int NR> struct ScoreOcc {
-    static constexpr int value = LSW_OCC_BOOST ? (NR <= 16 ? 6 : NR <= 24 ? 5 : NR <= 32 ? 4 : NR <= 40 ? 3 : 2) : 1;
+    static constexpr int value = LSW_OCC_BOOST == 1 ? (NR <= 16 ? 6 : NR <= 24 ? 5 : NR <= 32 ? 4 : NR <= 40 ? 3 : 2)
+                               : LSW_OCC_BOOST == 2 ? (NR <= 28 ? 4 : NR <= 40 ? 3 : 2)
+                               : LSW_OCC_BOOST == 3 ? (NR <= 20 ? 5 : NR <= 28 ? 4 : NR <= 40 ? 3 : 2) : 1;
 };
 
 template <int NR>
