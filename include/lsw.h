@@ -92,6 +92,8 @@ typedef struct {
     int64_t steps;        /* lane-steps (columns incl. dead padding) the score kernels ran */
     int64_t fallbacks;    /* traced tasks the short-window traceback could not prove exact and that
                              were redone by the full-window kernel                              */
+    int64_t computed_cells; /* cells the score kernels actually filled: child tasks reuse the
+                             round-0 matrix of their read (lsw_reuse.cuh), so this is < cells     */
 } lsw_counters;
 
 /* cigar runs are (count << 2) | op with op 1 = 'M', 2 = 'I', 3 = 'D' */

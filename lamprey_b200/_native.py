@@ -25,8 +25,8 @@ COUNTERS_DT = np.dtype([("tasks", "<i8"), ("cells", "<i8"), ("top_tasks", "<i8")
                         ("traced", "<i8"), ("hits", "<i8"), ("rounds", "<i4"), ("reserved", "<i4"),
                         ("ms_score", "<f4"), ("ms_trace", "<f4"), ("ms_other", "<f4"), ("ms_total", "<f4"),
                         ("score_launches", "<i8"), ("trace_launches", "<i8"), ("other_launches", "<i8"),
-                        ("steps", "<i8"), ("fallbacks", "<i8")])
-assert TASK_DT.itemsize == 16 and RESULT_DT.itemsize == 40 and HIT_DT.itemsize == 32 and COUNTERS_DT.itemsize == 112
+                        ("steps", "<i8"), ("fallbacks", "<i8"), ("computed_cells", "<i8")])
+assert TASK_DT.itemsize == 16 and RESULT_DT.itemsize == 40 and HIT_DT.itemsize == 32 and COUNTERS_DT.itemsize == 120
 
 # every symbol include/lsw.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",

@@ -23,6 +23,7 @@
 #include "lsw_common.cuh"
 #include "lsw_score.cuh"
 #include "lsw_trace.cuh"
+#include "lsw_reuse.cuh"
 #include "intpeak.cuh"
 #include "lsw_host.hpp"
 
@@ -63,7 +64,7 @@ struct TaskBuf {
     TaskArrays view() const {
         TaskArrays t;
         t.read = read.as<int32_t>(); t.a = a.as<int32_t>(); t.b = b.as<int32_t>();
-        t.seq = seq.as<int16_t>(); t.orig = orig.as<int32_t>();
+        t.seq = seq.as<int16_t>(); t.orig = orig.as<int32_t>(); t.skip = nullptr;
         return t;
     }
     void release() { read.release(); a.release(); b.release(); seq.release(); orig.release(); }
@@ -99,6 +100,13 @@ struct lsw_ctx {
            d_results, d_cigar, d_ncigar;
     int64_t hit_cap_user = 0;
     int32_t read_base = 0;
+    // reuse of the round-0 DP by child tasks (lsw_reuse.cuh)
+    bool reuse = true;
+    std::vector<int64_t> h_bb_off;
+    int64_t bb_total = 0;
+    DevBuf d_blockbest, d_bb_off, d_nseg, d_segpos, d_res_s, d_seg_s, d_class_of;
+    TaskBuf segs;
+    DevBuf d_seg_skip;
     int32_t allowed_overlap = -1;
     int64_t n_hits = 0;
     std::vector<Timed> timed;
@@ -222,6 +230,42 @@ __global__ void k_prune_overlaps(lsw_hit* __restrict__ hits, int64_t n_hits, int
         while (e < eh) { const long long mid = (e + eh) >> 1; if (hits[mid].read <= rid) e = mid + 1; else eh = mid; }
         prune_overlaps_read(hits, lo, e, allowed);
     }
+}
+
+// ---- reuse of the round-0 DP (lsw_reuse.cuh): plan, fill, merge ----------------------------------------
+__global__ void k_plan_segments(ReuseParams R) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= R.n; t += (int64_t)gridDim.x * blockDim.x)
+        R.nseg[t] = t < R.n ? plan_task(R.t.a[t], R.t.b[t], R.qlen[R.t.seq[t]], R.match, R.g, R.enable != 0).nseg : 0;
+}
+
+__global__ void k_fill_segments(ReuseParams R, const int64_t* __restrict__ seg_t, int64_t* __restrict__ seg_s, int nseq) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid <= nseq) seg_s[gid] = R.segpos[seg_t[gid]];
+    for (int64_t t = gid; t < R.n; t += (int64_t)gridDim.x * blockDim.x) fill_segments(R, t);
+}
+
+__global__ void k_merge_segments(ReuseParams R) {
+    unsigned long long tasks = 0, cells = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < R.n; t += (int64_t)gridDim.x * blockDim.x) {
+        int score, row, col;
+        const bool cand = combine_task(R, t, score, row, col);
+        const int q = R.t.seq[t];
+        tasks += 1;
+        cells += (unsigned long long)(R.t.b[t] - R.t.a[t]) * (unsigned long long)R.qlen[q];
+        if (cand) {
+            const int c = R.class_of[q];
+            const unsigned long long i = atomicAdd(R.ncand + c, 1ull);
+            R.cand[c][i] = (uint32_t)t;
+            R.cand_key[c][i] = (uint16_t)(((uint32_t)q << 8) | (uint32_t)cand_window(score, row, col, R.match, R.g));
+        }
+    }
+    // block-level reduction of the work counters
+    __shared__ unsigned long long s_tasks, s_cells;
+    if (threadIdx.x == 0) { s_tasks = 0; s_cells = 0; }
+    __syncthreads();
+    atomicAdd(&s_tasks, tasks); atomicAdd(&s_cells, cells);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_tasks) { atomicAdd(&R.counters[0], s_tasks); atomicAdd(&R.counters[1], s_cells); }
 }
 
 // ---- helpers -----------------------------------------------------------------------------
@@ -360,7 +404,7 @@ void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {
 
 // Runs K1 then K2 for every class over the task list `cur` (segments h_seg on the host).
 int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int64_t>& h_seg, int64_t n,
-              TraceParams Tbase, lsw_counters* cnt) {
+              TraceParams Tbase, lsw_counters* cnt, int round_kind = 0 /* 0 plain, 1 store block bests, 2 reuse them */) {
     CK(ctx->d_res.ensure((size_t)n * sizeof(int2)));
     CK(ctx->d_head.ensure((size_t)ctx->nseq * 8));
     CK(ctx->d_ncand.ensure(NCLASS * 8));
@@ -382,6 +426,34 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
     }
     ScoreParams P;
     fill_score_params(ctx, P, cur, segi);
+    P.push_cands = 1; P.count_ref = 1;
+    if (round_kind == 1) {
+        P.blockbest = ctx->d_blockbest.as<uint32_t>(); P.bb_off = ctx->d_bb_off.as<int64_t>(); P.bb_total = ctx->bb_total;
+    }
+    ReuseParams R;
+    memset(&R, 0, sizeof R);
+    if (round_kind == 2) {
+        // child tasks: K1 runs on the segment list (own head + warm-started tail), the whole-read blocks in between are looked up
+        Span sp(ctx, 2);
+        R.t = cur.view(); R.n = n; R.qlen = ctx->d_qlen.as<int32_t>(); R.match = ctx->match; R.g = ctx->g; R.enable = 1;
+        CK(ctx->d_nseg.ensure((size_t)(n + 1) * 4)); CK(ctx->d_segpos.ensure((size_t)(n + 1) * 4));
+        CK(ctx->segs.ensure((size_t)2 * n, false)); CK(ctx->d_seg_skip.ensure((size_t)2 * n));
+        CK(ctx->d_res_s.ensure((size_t)2 * n * sizeof(int2))); CK(ctx->d_seg_s.ensure((size_t)(ctx->nseq + 1) * 8));
+        R.nseg = ctx->d_nseg.as<int32_t>(); R.segpos = ctx->d_segpos.as<int32_t>();
+        R.s = ctx->segs.view(); R.s.skip = ctx->d_seg_skip.as<uint8_t>();
+        k_plan_segments<<<grid_for(n + 1, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(R);
+        CK(cudaGetLastError());
+        size_t tmp = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_nseg.as<int32_t>(), ctx->d_segpos.as<int32_t>(), (int)(n + 1), ctx->stream));
+        CK(ctx->d_cubtemp.ensure(tmp));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtemp.p, tmp, ctx->d_nseg.as<int32_t>(), ctx->d_segpos.as<int32_t>(), (int)(n + 1), ctx->stream));
+        k_fill_segments<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+            R, ctx->d_seg[segi].as<int64_t>(), ctx->d_seg_s.as<int64_t>(), ctx->nseq);
+        CK(cudaGetLastError());
+        if (cnt) cnt->other_launches += 4;
+        P.t = R.s; P.seg = ctx->d_seg_s.as<int64_t>(); P.res = ctx->d_res_s.as<int2>();
+        P.push_cands = 0; P.count_ref = 0;
+    }
     {
         Span sp(ctx, 0);
         for (int c = 0; c < NCLASS; c++) {
@@ -391,10 +463,22 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             P.cand = ctx->d_cand[c].as<uint32_t>();
             P.cand_key = ctx->d_cand_key[c].as<uint16_t>();
             P.ncand = ctx->d_ncand.as<unsigned long long>() + c;
-            int rc = launch_score_class(ctx, c, P, ncls[c]);
+            int rc = launch_score_class(ctx, c, P, round_kind == 2 ? 2 * ncls[c] : ncls[c]);
             if (rc) return rc;
             if (cnt) cnt->score_launches++;
         }
+    }
+    if (round_kind == 2) {
+        Span sp(ctx, 2);
+        R.res_s = ctx->d_res_s.as<int2>(); R.res_t = ctx->d_res.as<int2>();
+        R.blockbest = ctx->d_blockbest.as<uint32_t>(); R.bb_off = ctx->d_bb_off.as<int64_t>(); R.bb_total = ctx->bb_total;
+        R.cand_ok = ctx->d_cand_ok.as<uint8_t>(); R.class_of = ctx->d_class_of.as<int32_t>();
+        for (int c = 0; c < NCLASS; c++) { R.cand[c] = ctx->d_cand[c].as<uint32_t>(); R.cand_key[c] = ctx->d_cand_key[c].as<uint16_t>(); }
+        R.ncand = ctx->d_ncand.as<unsigned long long>();
+        R.counters = ctx->d_counters.as<unsigned long long>();
+        k_merge_segments<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(R);
+        CK(cudaGetLastError());
+        if (cnt) cnt->other_launches++;
     }
     {
         // order each class's candidates by (sequence, traceback window length): K2 warps serve one sequence at a
@@ -499,7 +583,8 @@ void lsw_destroy(lsw_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); }
     ctx->d_nfallback.release();
-    ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release();
+    ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release(); ctx->segs.release();
+    for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_seg_skip}) b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -578,6 +663,8 @@ int lsw_set_queries(lsw_ctx* ctx, int n, const uint8_t* concat, const int32_t* o
     CK(ctx->d_qlen.ensure((size_t)n * 4));
     CK(cudaMemcpyAsync(ctx->d_qcodes.p, qcodes.data(), qcodes.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_qlen.p, qlen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_class_of.ensure((size_t)n * 4));
+    CK(cudaMemcpyAsync(ctx->d_class_of.p, class_of.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     for (int c = 0; c < NCLASS; c++) {
         if (ctx->class_seqs[c].empty()) continue;
         CK(ctx->d_class_seqs[c].ensure(ctx->class_seqs[c].size() * 4));
@@ -602,6 +689,11 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     }
     ctx->n_reads = n;
     ctx->total_bases = n ? offs[n] - offs[0] : 0;
+    ctx->h_bb_off.assign((size_t)n + 1, 0);                       // 64-column blocks of every read (lsw_reuse.cuh)
+    for (int64_t i = 0; i < n; i++) ctx->h_bb_off[i + 1] = ctx->h_bb_off[i] + (ctx->h_rlen[i] + 63) / 64;
+    ctx->bb_total = ctx->h_bb_off[n];
+    CK(ctx->d_bb_off.ensure((size_t)(n + 1) * 8));
+    CK(cudaMemcpyAsync(ctx->d_bb_off.p, ctx->h_bb_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     // 256 B front pad (K2 reads a few codes before a window start, masked) and 256 B tail pad (K1 reads
     // whole 64-byte blocks past a slice end)
     ctx->codes_bytes = 256 + padded_total + 256;
@@ -698,6 +790,9 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         cnt.other_launches++;
     }
 
+    // block bests of round 0 for the child tasks: 4 B per 64 columns per (read, sequence)
+    const bool reuse = ctx->reuse && !getenv("LSW_NO_REUSE");
+    if (reuse) CK(ctx->d_blockbest.ensure((size_t)std::max<int64_t>(1, ctx->bb_total) * ctx->nseq * 4));
     int64_t n = n0;
     int round = 0;
     size_t dbg_from = 0;
@@ -717,7 +812,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         T.hits = ctx->d_hits.p; T.hits_cap = hit_cap; T.nhits = ctx->d_nhits.as<unsigned long long>();
         T.child_flag = ctx->d_child_flag.as<uint8_t>();
         T.child = ctx->child.view();
-        rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt);
+        rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse ? (round == 0 ? 1 : 2) : 0);
         if (rc) break;
 
         {
@@ -774,7 +869,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     CK(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&h_err, ctx->d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cnt.tasks = (int64_t)h_cnt[0]; cnt.cells = (int64_t)h_cnt[1]; cnt.steps = (int64_t)h_cnt[2];
+    cnt.tasks = (int64_t)h_cnt[0]; cnt.cells = (int64_t)h_cnt[1]; cnt.steps = (int64_t)h_cnt[2]; cnt.computed_cells = (int64_t)h_cnt[3];
     cnt.top_cells = 0;
     {
         int64_t sumq = 0;

@@ -100,6 +100,7 @@ struct TaskArrays {           // struct-of-arrays task list of one recursion rou
     int32_t* b;               // slice end (exclusive)
     int16_t* seq;             // schema sequence index
     int32_t* orig;            // align_tasks(): caller's task index (results are written there); else unused
+    uint8_t* skip;            // K1 segments (lsw_reuse.cuh): leading 64-column blocks that only warm the DP up; else null
 };
 
 struct ScoreParams {
@@ -117,12 +118,17 @@ struct ScoreParams {
     uint32_t*       cand;     // out: tasks that need a traceback
     uint16_t*       cand_key; // out: sequence << 8 | K2 window length (sort key; preset to 0xFFFF)
     unsigned long long* ncand;
-    unsigned long long* counters;   // [0] += tasks, [1] += cells, [2] += lane steps
+    unsigned long long* counters;   // [0] += reference tasks, [1] += reference cells, [2] += lane steps, [3] += computed cells
     int32_t s_match;          // SC * (match + |gap|)
     int32_t s_mis;            // SC * (mismatch + |gap|)
     int32_t g;                // |gap|
     int32_t match;
     uint32_t one;             // 1 (see add_on_fma_pipe)
+    uint32_t* blockbest;      // round 0: best cell of every 64-column block, [n_seq][bb_total] (lsw_reuse.cuh); else null
+    const int64_t* bb_off;    // [n_reads] first block of each read
+    int64_t bb_total;
+    int32_t push_cands;       // 1: finish() queues traceback candidates; 0: the merge kernel does (segment mode)
+    int32_t count_ref;        // 1: the tasks are reference align() calls (count them); 0: segments
 };
 
 struct TraceParams {

@@ -16,6 +16,7 @@
 #include "lsw_common.cuh"
 #include "lsw_score.cuh"
 #include "lsw_trace.cuh"
+#include "lsw_reuse.cuh"
 #include "lsw_host.hpp"
 
 using namespace lsw;
@@ -39,6 +40,13 @@ struct Emu {
     unsigned long long counters[4];
     unsigned long long fallbacks = 0;
     bool force_full = false;
+    // reuse of the round-0 DP (lsw_reuse.cuh)
+    bool reuse = false;
+    int round = 0;
+    std::vector<uint32_t> blockbest;
+    std::vector<int64_t> bb_off;
+    int64_t bb_total = 0;
+    unsigned long long comp_cells = 0;
 };
 
 bool setup(Emu& E, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
@@ -85,9 +93,9 @@ void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& c
     const int Q = E.qlen[q];
     Lane::build_profile(P, q, Q, reinterpret_cast<uint32_t*>(prof.data()), 0, 1);
     Lane L;
-    L.n_tasks = L.n_cells = L.n_steps = 0;
+    L.n_tasks = L.n_cells = L.n_steps = L.n_comp = 0;
     L.init();
-    const long long cnt = E.seg[q + 1] - E.seg[q], base = E.seg[q];
+    const long long cnt = P.seg[q + 1] - P.seg[q], base = P.seg[q];
     long long head = 0;
     bool exhausted = false;
     for (;;) {
@@ -101,7 +109,7 @@ void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& c
         if (!(L.tid[0] >= 0 || L.tid[1] >= 0)) break;
         L.run_block(P, prof.data(), keep_ge, keep_lt, Q);
     }
-    E.counters[0] += L.n_tasks; E.counters[1] += L.n_cells; E.counters[2] += L.n_steps;
+    E.counters[0] += L.n_tasks; E.counters[1] += L.n_cells; E.counters[2] += L.n_steps; E.comp_cells += L.n_comp;
 }
 
 void emu_score_class(Emu& E, const ScoreParams& P, int c, int q, std::vector<uint32_t>& cand) {
@@ -154,10 +162,13 @@ void emu_trace_class(Emu& E, const TraceParams& T, const ScoreParams& P, int c, 
 TaskArrays view(Emu& E) {
     TaskArrays t;
     t.read = E.t_read.data(); t.a = E.t_a.data(); t.b = E.t_b.data(); t.seq = E.t_seq.data(); t.orig = E.t_orig.data();
+    t.skip = nullptr;
     return t;
 }
 
 // K1 + K2 over the current task list.  Tbase carries the mode-specific outputs.
+// Round 0 (and every round when reuse is off, and align_tasks) runs K1 on the tasks themselves; later rounds
+// run K1 on the segment list of lsw_reuse.cuh and merge per task.
 void emu_round(Emu& E, TraceParams T) {
     const int64_t n = (int64_t)E.t_read.size();
     E.res.assign((size_t)n, make_int2(0, 0));
@@ -167,6 +178,7 @@ void emu_round(Emu& E, TraceParams T) {
     P.res = E.res.data(); P.qcodes = E.qcodes.data(); P.qlen = E.qlen.data();
     P.cand_ok = E.cand_ok.data();
     P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g; P.match = E.match; P.one = 1u;
+    P.push_cands = 1; P.count_ref = 1;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
     std::vector<uint32_t> scratch((size_t)(size_t)std::max(trace_window_full(qmax, E.match, E.g) * 4, (trace_window_fast_max(qmax, E.match, E.g) + 4) * 32) + 16);
@@ -174,11 +186,53 @@ void emu_round(Emu& E, TraceParams T) {
     T.qcodes = E.qcodes.data(); T.qlen = E.qlen.data();
     T.match = E.match; T.mismatch = E.mismatch; T.g = E.g;
     T.scratch = scratch.data(); T.scratch_stride = 1;
+
+    const bool segmented = E.reuse && E.round > 0;
+    if (E.reuse && E.round == 0) { P.blockbest = E.blockbest.data(); P.bb_off = E.bb_off.data(); P.bb_total = E.bb_total; }
+    if (!segmented) {
+        for (int s = 0; s < E.nseq; s++) {
+            if (E.seg[s + 1] == E.seg[s]) continue;
+            std::vector<uint32_t> cand;
+            emu_score_class(E, P, E.class_of[s], s, cand);
+            emu_trace_class(E, T, P, E.class_of[s], s, cand);
+        }
+        return;
+    }
+    // plan -> scan -> fill -> K1 on segments -> merge -> K2
+    ReuseParams R;
+    memset(&R, 0, sizeof R);
+    R.t = view(E); R.n = n; R.qlen = E.qlen.data(); R.match = E.match; R.g = E.g; R.enable = 1;
+    std::vector<int32_t> segpos((size_t)n + 1, 0);
+    for (int64_t t = 0; t < n; t++)
+        segpos[t + 1] = segpos[t] + plan_task(E.t_a[t], E.t_b[t], E.qlen[E.t_seq[t]], E.match, E.g, true).nseg;
+    const int64_t ns = segpos[n];
+    std::vector<int32_t> s_read(ns), s_a(ns), s_b(ns);
+    std::vector<int16_t> s_seq(ns);
+    std::vector<uint8_t> s_skip(ns);
+    std::vector<int2> res_s((size_t)ns, make_int2(0, 0));
+    std::vector<int64_t> seg_s(E.nseq + 1);
+    for (int s = 0; s <= E.nseq; s++) seg_s[s] = segpos[E.seg[s]];
+    R.segpos = segpos.data();
+    R.s.read = s_read.data(); R.s.a = s_a.data(); R.s.b = s_b.data(); R.s.seq = s_seq.data(); R.s.skip = s_skip.data();
+    for (int64_t t = 0; t < n; t++) fill_segments(R, t);
+    ScoreParams PS = P;
+    PS.t = R.s; PS.seg = seg_s.data(); PS.res = res_s.data(); PS.push_cands = 0; PS.count_ref = 0;
     for (int s = 0; s < E.nseq; s++) {
-        if (E.seg[s + 1] == E.seg[s]) continue;
+        if (seg_s[s + 1] == seg_s[s]) continue;
+        std::vector<uint32_t> none;
+        emu_score_class(E, PS, E.class_of[s], s, none);
+    }
+    R.res_s = res_s.data(); R.res_t = E.res.data();
+    R.blockbest = E.blockbest.data(); R.bb_off = E.bb_off.data(); R.bb_total = E.bb_total;
+    R.cand_ok = E.cand_ok.data();
+    for (int s = 0; s < E.nseq; s++) {
         std::vector<uint32_t> cand;
-        emu_score_class(E, P, E.class_of[s], s, cand);
-        emu_trace_class(E, T, P, E.class_of[s], s, cand);
+        for (int64_t t = E.seg[s]; t < E.seg[s + 1]; t++) {
+            int sc, rw, cl;
+            E.counters[0]++; E.counters[1] += (unsigned long long)(E.t_b[t] - E.t_a[t]) * E.qlen[s];
+            if (combine_task(R, t, sc, rw, cl)) cand.push_back((uint32_t)t);
+        }
+        if (!cand.empty()) emu_trace_class(E, T, P, E.class_of[s], s, cand);
     }
 }
 
@@ -188,10 +242,11 @@ extern "C" {
 
 int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
                      const int32_t* qoffs, int match, int mismatch, int gap, double thr, lsw_hit* out, int64_t cap,
-                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds, traced, fallbacks */, int force_full,
-                     int allowed_overlap) {
+                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds, traced, fallbacks, computed cells */, int force_full,
+                     int allowed_overlap, int reuse) {
     Emu E;
     E.force_full = force_full != 0;
+    E.reuse = reuse != 0;
     if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, match, mismatch, gap)) return LSW_E_UNSUPPORTED;
     build_cand_ok(nseq, E.qlen.data(), match, mismatch, E.g, thr, false, E.cand_ok);
     const int64_t n0 = n_reads * nseq;
@@ -202,10 +257,17 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
         const int s = (int)(i / n_reads); const int64_t r = i - (int64_t)s * n_reads;
         E.t_read[i] = (int32_t)r; E.t_a[i] = 0; E.t_b[i] = E.rlen[r]; E.t_seq[i] = (int16_t)s;
     }
+    if (E.reuse) {
+        E.bb_off.assign((size_t)n_reads + 1, 0);
+        for (int64_t i = 0; i < n_reads; i++) E.bb_off[i + 1] = E.bb_off[i] + (E.rlen[i] + 63) / 64;
+        E.bb_total = E.bb_off[n_reads];
+        E.blockbest.assign((size_t)std::max<int64_t>(1, E.bb_total * nseq), 0u);
+    }
     unsigned long long nhits = 0;
     int32_t errflag = 0;
     int round = 0;
     while (!E.t_read.empty()) {
+        E.round = round;
         const int64_t n = (int64_t)E.t_read.size(), n2 = 2 * n;
         std::vector<int32_t> c_read(n2), c_a(n2), c_b(n2);
         std::vector<int16_t> c_seq(n2);
@@ -234,7 +296,7 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
 #endif
     if (errflag) return LSW_E_INTERNAL;
     if (n_out) *n_out = (int64_t)nhits;
-    if (counters) { counters[0] = E.counters[0]; counters[1] = E.counters[1]; counters[2] = E.counters[2]; counters[3] = round; counters[4] = E.counters[3]; counters[5] = E.fallbacks; }
+    if (counters) { counters[0] = E.counters[0]; counters[1] = E.counters[1]; counters[2] = E.counters[2]; counters[3] = round; counters[4] = E.counters[3]; counters[5] = E.fallbacks; counters[6] = (int64_t)E.comp_cells; }
     if ((int64_t)nhits > cap) return LSW_E_OVERFLOW;
     // (read, start, query) order
     std::sort(out, out + nhits, [](const lsw_hit& x, const lsw_hit& y) {

@@ -1,0 +1,121 @@
+// lsw_reuse.cuh -- reuse of the round-0 DP by the recursion's child tasks.
+//
+// findPrimerAlignments (/root/reference/lamprey.py:596-645) re-aligns the primer against what lies left and
+// right of every hit, so most cells of a child slice [a, b) were already computed when the whole read was
+// aligned in round 0.  They are the SAME cells: an alignment whose every prefix scores > 0 spans fewer than
+// Wx = Q + M*Q/g read columns, so for read positions p >= a + Wx the child's H(r, p) equals the whole read's
+// H(r, p) (both have a zero boundary at their start, and no alignment ending at p can reach back to it).
+// Round 0 therefore stores, for every 64-column block of every (read, sequence), the block's best cell
+// (value, row, column) -- 4 bytes -- and a child task whose slice is long enough is computed as
+//     HEAD   [a, hb)            the child's own DP up to the first block boundary hb >= a + Wx
+//     MIDDLE blocks hb/64 .. te/64-1 of the whole read, looked up                  (te = last boundary <= b)
+//     TAIL   [te - Wxa, b)      a DP that warms up for Wxa >= Wx columns (not counted) and counts (te, b]
+// and the three bests are merged with swalign's tie rule (value, then row, then the LAST column).
+// Everything here is exact; nothing is approximated.  Slices too short to profit are computed directly.
+#pragma once
+#include "lsw_common.cuh"
+
+namespace lsw {
+
+constexpr int REUSE_MIN_SAVING = 96;      // columns a split must save (two extra task starts / block tails)
+
+struct SegPlan {
+    int nseg;        // K1 segments of the task: 1 (direct, or head only) or 2 (head + tail)
+    bool split;
+    int hb;          // head = [a, hb)
+    int te;          // middle = whole-read blocks hb/64 .. te/64 - 1
+    int ts, skip;    // tail = [ts, b), its first `skip` 64-column blocks are warm-up
+    bool tail;
+};
+
+LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable) {
+    SegPlan p;
+    p.nseg = 1; p.split = false; p.hb = b; p.te = b; p.ts = 0; p.skip = 0; p.tail = false;
+    if (!enable) return p;
+    const int Wx = Q + (match * Q) / g;
+    const int hb = ((a + Wx + 63) / 64) * 64;
+    const int te = (b / 64) * 64;
+    if (hb > te) return p;
+    const int Wxa = ((Wx + 63) / 64) * 64;
+    int ts = te - Wxa;
+    if (ts < 0) ts = 0;
+    const bool tail = b > te;
+    const int computed = (hb - a) + (tail ? b - ts : 0);
+    if (computed + REUSE_MIN_SAVING > b - a) return p;
+    p.split = true; p.hb = hb; p.te = te; p.ts = ts; p.skip = (te - ts) / 64; p.tail = tail;
+    p.nseg = tail ? 2 : 1;
+    return p;
+}
+
+struct ReuseParams {
+    TaskArrays t;                // child tasks of the round
+    int64_t n;
+    const int32_t* qlen;
+    int32_t match, g, enable;
+    int32_t* nseg;               // plan: segments per task (scanned into segpos)
+    const int32_t* segpos;       // [n + 1]
+    TaskArrays s;                // segment list K1 runs on (s.skip set)
+    const int2* res_s;           // K1 results per segment
+    int2* res_t;                 // merged result per task
+    const uint32_t* blockbest;   // [n_seq][bb_total]
+    const int64_t* bb_off;       // [n_reads] first block of each read
+    int64_t bb_total;
+    const uint8_t* cand_ok;      // [n_seq][128]
+    const int32_t* class_of;     // [n_seq] register-row class
+    uint32_t* cand[16];          // per class: candidate list / sort key
+    uint16_t* cand_key[16];
+    unsigned long long* ncand;   // [classes]
+    unsigned long long* counters;   // [0] += tasks, [1] += reference cells
+};
+
+LSW_HD void fill_segments(const ReuseParams& R, int64_t t) {
+    const int a = R.t.a[t], b = R.t.b[t], q = R.t.seq[t];
+    const SegPlan p = plan_task(a, b, R.qlen[q], R.match, R.g, R.enable != 0);
+    const int64_t i = R.segpos[t];
+    R.s.read[i] = R.t.read[t]; R.s.seq[i] = (int16_t)q; R.s.skip[i] = 0;
+    R.s.a[i] = a; R.s.b[i] = p.split ? p.hb : b;
+    if (p.split && p.tail) {
+        R.s.read[i + 1] = R.t.read[t]; R.s.seq[i + 1] = (int16_t)q; R.s.skip[i + 1] = (uint8_t)p.skip;
+        R.s.a[i + 1] = p.ts; R.s.b[i + 1] = b;
+    }
+}
+
+// sort key of a K2 candidate: the number of window columns its traceback will fill
+LSW_HD int cand_window(int score, int row, int col, int match, int g) {
+    int w = score > 0 ? row + (match * row - score) / g + 8 : 0;
+    return w > col ? col : w;
+}
+
+// merged (score, max_row, max_col) of task t; returns true if it must be traced (candidate)
+LSW_HD bool combine_task(const ReuseParams& R, int64_t t, int& o_score, int& o_row, int& o_col) {
+    const int a = R.t.a[t], b = R.t.b[t], q = R.t.seq[t], rd = R.t.read[t];
+    const int Q = R.qlen[q];
+    const SegPlan p = plan_task(a, b, Q, R.match, R.g, R.enable != 0);
+    const int64_t i = R.segpos[t];
+    int score = 0, row = 0, col = 0;
+    auto consider = [&](int s, int r, int c) {       // regions are visited in ascending column order: >= keeps the last
+        if (s > 0 && (s > score || (s == score && r >= row))) { score = s; row = r; col = c; }
+    };
+    {
+        const int2 h = R.res_s[i];
+        consider(h.x & 0xFFFF, h.x >> 16, h.y);
+    }
+    if (p.split) {
+        const uint32_t* bb = R.blockbest + (size_t)q * R.bb_total + R.bb_off[rd];
+        for (int j = p.hb / 64; j < p.te / 64; j++) {
+            const uint32_t v = bb[j];
+            const int s = (int)(v >> 16) - R.g;
+            consider(s, (int)((v >> 8) & 0xFF) + (int)((v >> 6) & 1) + 1, 64 * j + (int)(v & 63) + 1 - a);
+        }
+        if (p.tail) {
+            const int2 h = R.res_s[i + 1];
+            consider(h.x & 0xFFFF, h.x >> 16, p.ts + h.y - a);
+        }
+    }
+    if (score == 0) { row = b > a ? Q : 0; col = b > a ? b - a : 0; }
+    R.res_t[t] = make_int2(score | (row << 16), col);
+    o_score = score; o_row = row; o_col = col;
+    return R.cand_ok[(size_t)q * 128 + score] != 0;
+}
+
+}  // namespace lsw

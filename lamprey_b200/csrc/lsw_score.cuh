@@ -44,8 +44,9 @@ struct ScoreLane {
     uint32_t best[2];      // ((H+g) << 16) | (row << 8) | step of the best cell so far
     int32_t  bestc[2];     // its DP column
     int32_t  len[2];       // slice length
+    int32_t  skipb[2];     // leading blocks of the current task that are warm-up only (not folded)
     U4       nx[2];        // read codes of the next 16 steps, fetched one chunk ahead
-    unsigned long long n_tasks, n_cells, n_steps;
+    unsigned long long n_tasks, n_cells, n_steps, n_comp;
 
     LSW_HD void init() {
 #pragma unroll
@@ -55,7 +56,7 @@ struct ScoreLane {
         tid[0] = tid[1] = -1;
         rem[0] = rem[1] = 0; begin[0] = begin[1] = 0;
         pos[0] = pos[1] = 0; cbase[0] = cbase[1] = 0;
-        best[0] = best[1] = 0; bestc[0] = bestc[1] = 0; len[0] = len[1] = 0;
+        best[0] = best[1] = 0; bestc[0] = bestc[1] = 0; len[0] = len[1] = 0; skipb[0] = skipb[1] = 0;
         nx[0].x = nx[0].y = nx[0].z = nx[0].w = 0;
         nx[1] = nx[0];
     }
@@ -100,8 +101,12 @@ struct ScoreLane {
 #pragma unroll
         for (int r = 0; r < NR; r++) M[r] &= keep;     // zero boundary column for this half
         nx[h] = *reinterpret_cast<const U4*>(P.codes + pos[h]);
-        n_tasks += 1;
-        n_cells += (unsigned long long)(b - a) * (unsigned long long)Q;
+        skipb[h] = P.t.skip ? (int32_t)P.t.skip[t] : 0;
+        if (P.count_ref) {
+            n_tasks += 1;
+            n_cells += (unsigned long long)(b - a) * (unsigned long long)Q;
+        }
+        n_comp += (unsigned long long)(b - a) * (unsigned long long)Q;
     }
 
     // Retire the task in half h: publish (score, max_row, max_col) and queue it for traceback.
@@ -119,7 +124,7 @@ struct ScoreLane {
             col = bestc[h];
         }
         P.res[t] = make_int2(score | (row << 16), col);
-        if (P.cand_ok[(size_t)q * 128 + score]) {
+        if (P.push_cands && P.cand_ok[(size_t)q * 128 + score]) {
             // sort key for K2: the number of window columns its traceback will fill (similar work per warp)
             int w = score > 0 ? row + (P.match * row - score) / P.g + 8 : 0;
             if (w > col) w = col;
@@ -225,7 +230,18 @@ struct ScoreLane {
                     bb = key > bb ? key : bb;
                 }
             }
-            if (tid[h] >= 0) {
+            if (tid[h] >= 0 && P.blockbest) {
+                // round 0 (whole reads, block grid = the read's): remember the block's best for the child tasks
+                const int t = tid[h];
+                P.blockbest[(size_t)P.t.seq[t] * P.bb_total + P.bb_off[P.t.read[t]] + ((cbase[h] - 1) >> 6)] = bb;
+            }
+            if (tid[h] >= 0 && skipb[h] > 0) {                 // warm-up block of a tail segment: not counted
+                skipb[h]--;
+                rem[h] -= end[h] - begin[h];
+                begin[h] = 0;
+                pos[h] += BLOCK_STEPS;
+                cbase[h] += BLOCK_STEPS;
+            } else if (tid[h] >= 0) {
                 if ((bb >> 6) >= (best[h] >> 6)) {       // >= : a later block wins ties on (H, row); bits 6.. hold (H, row)
                     best[h] = bb;
                     bestc[h] = cbase[h] + (int32_t)(bb & 0x3F);
@@ -287,7 +303,7 @@ k_score(const ScoreParams P) {
     __syncthreads();
 
     Lane L;
-    L.n_tasks = L.n_cells = L.n_steps = 0;
+    L.n_tasks = L.n_cells = L.n_steps = L.n_comp = 0;
 
     // Warps spread over the sequences of the class (warp w starts on sequence w mod n) and stay on a
     // sequence until its queue is empty; only then do they move to the fullest remaining queue.
@@ -358,6 +374,7 @@ k_score(const ScoreParams P) {
         atomicAdd(&P.counters[1], L.n_cells);
     }
     if (L.n_steps) atomicAdd(&P.counters[2], L.n_steps);
+    if (L.n_comp) atomicAdd(&P.counters[3], L.n_comp);
 }
 
 template <int NR>
