@@ -372,6 +372,7 @@ int launch_trace_class(lsw_ctx* ctx, int c, const TraceParams& P, int64_t n, int
 }
 
 void fill_score_params(lsw_ctx* ctx, ScoreParams& P, const TaskBuf& cur, int segi) {
+    memset(&P, 0, sizeof P);
     P.codes = ctx->d_codes.as<uint8_t>();
     P.roff = ctx->d_roff.as<int64_t>();
     P.t = cur.view();

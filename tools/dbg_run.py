@@ -1,0 +1,12 @@
+import sys, os
+import numpy as np
+sys.path.insert(0, ".")
+from lamprey_b200 import _native, seeding, synth
+n = int(sys.argv[1])
+concat, offs = synth.generate(n, workers=8, **synth.CONFIGS["synth_2kb_8pct"])
+ps = seeding.PrimerSet("tests/golden/H3.3_set1.primers")
+eng = _native.Engine(0)
+eng.set_scoring(2, -1, -1, -1); eng.set_queries([s for _, s in ps.sequences()])
+eng.upload_reads(concat, offs)
+h = eng.find_all(0.7, fetch=False)
+print("ok", n, h, eng.last_counters["tasks"], eng.last_counters["cells"], eng.last_counters["computed_cells"])
