@@ -254,7 +254,7 @@ __global__ void k_merge_segments(ReuseParams R) {
         cells += (unsigned long long)(R.t.b[t] - R.t.a[t]) * (unsigned long long)R.qlen[q];
         if (cand) {
             const int c = R.class_of[q];
-            const unsigned long long i = atomicAdd(R.ncand + c, 1ull);
+            const unsigned long long i = append_slot_grouped(R.ncand + c);
             R.cand[c][i] = (uint32_t)t;
             R.cand_key[c][i] = (uint16_t)(((uint32_t)q << 8) | (uint32_t)cand_window(score, row, col, R.match, R.g));
         }

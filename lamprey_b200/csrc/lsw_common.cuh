@@ -91,6 +91,21 @@ LSW_HD unsigned long long append_slot(unsigned long long* counter) {
 #endif
 }
 
+// same, for lanes that may target DIFFERENT counters (one per class): lanes with the same counter are grouped
+LSW_HD unsigned long long append_slot_grouped(unsigned long long* counter) {
+#if defined(__CUDA_ARCH__)
+    const unsigned mask = __match_any_sync(__activemask(), (unsigned long long)counter);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+#else
+    return (*counter)++;
+#endif
+}
+
 LSW_HD void atomicExch_or_store(int32_t* p, int32_t v) { *p = v; }   // benign race: any writer stores the same flag
 
 // ---- task / result records shared by host and device -------------------------------------
