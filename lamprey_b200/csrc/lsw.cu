@@ -427,7 +427,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
     }
     ScoreParams P;
     fill_score_params(ctx, P, cur, segi);
-    P.push_cands = 1; P.count_ref = 1;
+    P.push_cands = 1; P.count_ref = 1; P.block_steps = BLOCK_STEPS;
     if (round_kind == 1) {
         P.blockbest = ctx->d_blockbest.as<uint32_t>(); P.bb_off = ctx->d_bb_off.as<int64_t>(); P.bb_total = ctx->bb_total;
     }
@@ -453,7 +453,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         CK(cudaGetLastError());
         if (cnt) cnt->other_launches += 4;
         P.t = R.s; P.seg = ctx->d_seg_s.as<int64_t>(); P.res = ctx->d_res_s.as<int2>();
-        P.push_cands = 0; P.count_ref = 0;
+        P.push_cands = 0; P.count_ref = 0; P.block_steps = SEG_BLOCK;
     }
     {
         Span sp(ctx, 0);

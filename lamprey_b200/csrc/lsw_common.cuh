@@ -144,6 +144,7 @@ struct ScoreParams {
     int64_t bb_total;
     int32_t push_cands;       // 1: finish() queues traceback candidates; 0: the merge kernel does (segment mode)
     int32_t count_ref;        // 1: the tasks are reference align() calls (count them); 0: segments
+    int32_t block_steps;      // columns between two task-switch points: BLOCK_STEPS, or 32 for segment lists
 };
 
 struct TraceParams {

@@ -178,7 +178,7 @@ void emu_round(Emu& E, TraceParams T) {
     P.res = E.res.data(); P.qcodes = E.qcodes.data(); P.qlen = E.qlen.data();
     P.cand_ok = E.cand_ok.data();
     P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g; P.match = E.match; P.one = 1u;
-    P.push_cands = 1; P.count_ref = 1;
+    P.push_cands = 1; P.count_ref = 1; P.block_steps = BLOCK_STEPS;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
     std::vector<uint32_t> scratch((size_t)(size_t)std::max(trace_window_full(qmax, E.match, E.g) * 4, (trace_window_fast_max(qmax, E.match, E.g) + 4) * 32) + 16);
@@ -216,7 +216,7 @@ void emu_round(Emu& E, TraceParams T) {
     R.s.read = s_read.data(); R.s.a = s_a.data(); R.s.b = s_b.data(); R.s.seq = s_seq.data(); R.s.skip = s_skip.data();
     for (int64_t t = 0; t < n; t++) fill_segments(R, t);
     ScoreParams PS = P;
-    PS.t = R.s; PS.seg = seg_s.data(); PS.res = res_s.data(); PS.push_cands = 0; PS.count_ref = 0;
+    PS.t = R.s; PS.seg = seg_s.data(); PS.res = res_s.data(); PS.push_cands = 0; PS.count_ref = 0; PS.block_steps = SEG_BLOCK;
     for (int s = 0; s < E.nseq; s++) {
         if (seg_s[s + 1] == seg_s[s]) continue;
         std::vector<uint32_t> none;

@@ -9,7 +9,8 @@
 // (value, row, column) -- 4 bytes -- and a child task whose slice is long enough is computed as
 //     HEAD   [a, hb)            the child's own DP up to the first block boundary hb >= a + Wx
 //     MIDDLE blocks hb/64 .. te/64-1 of the whole read, looked up                  (te = last boundary <= b)
-//     TAIL   [te - Wxa, b)      a DP that warms up for Wxa >= Wx columns (not counted) and counts (te, b]
+//     TAIL   [te - Wxa, b)      a DP that warms up for Wxa >= Wx columns (not counted) and counts (te, b];
+//                               Wxa is a multiple of the 32-column lane block the segment launches use
 // and the three bests are merged with swalign's tie rule (value, then row, then the LAST column).
 // Everything here is exact; nothing is approximated.  Slices too short to profit are computed directly.
 #pragma once
@@ -17,6 +18,7 @@
 
 namespace lsw {
 
+constexpr int SEG_BLOCK = 32;             // lane block (columns between task-switch points) of segment launches
 constexpr int REUSE_MIN_SAVING = 96;      // columns a split must save (two extra task starts / block tails)
 
 struct SegPlan {
@@ -24,11 +26,11 @@ struct SegPlan {
     bool split;
     int hb;          // head = [a, hb)
     int te;          // middle = whole-read blocks hb/64 .. te/64 - 1
-    int ts, skip;    // tail = [ts, b), its first `skip` 64-column blocks are warm-up
+    int ts, skip;    // tail = [ts, b), its first `skip` lane blocks (SEG_BLOCK columns each) are warm-up
     bool tail;
 };
 
-LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable) {
+LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable, int tb = SEG_BLOCK /* lane block of the segment launch */) {
     SegPlan p;
     p.nseg = 1; p.split = false; p.hb = b; p.te = b; p.ts = 0; p.skip = 0; p.tail = false;
     if (!enable) return p;
@@ -36,13 +38,13 @@ LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable) {
     const int hb = ((a + Wx + 63) / 64) * 64;
     const int te = (b / 64) * 64;
     if (hb > te) return p;
-    const int Wxa = ((Wx + 63) / 64) * 64;
+    const int Wxa = ((Wx + tb - 1) / tb) * tb;
     int ts = te - Wxa;
     if (ts < 0) ts = 0;
     const bool tail = b > te;
     const int computed = (hb - a) + (tail ? b - ts : 0);
     if (computed + REUSE_MIN_SAVING > b - a) return p;
-    p.split = true; p.hb = hb; p.te = te; p.ts = ts; p.skip = (te - ts) / 64; p.tail = tail;
+    p.split = true; p.hb = hb; p.te = te; p.ts = ts; p.skip = (te - ts) / tb; p.tail = tail;
     p.nseg = tail ? 2 : 1;
     return p;
 }

@@ -162,7 +162,7 @@ struct ScoreLane {
         }
     }
 
-    // BLOCK_STEPS columns for both halves, then fold the block's arg-max into the task state.
+    // P.block_steps (64, or 32 for the short segment tasks of lsw_reuse.cuh) columns for both halves, then fold the block's arg-max into the task state.
     // keep_ge[n]: bytes j >= n of a 16-byte chunk are live; keep_lt[n]: bytes j < n are live.
     LSW_HD void run_block(const ScoreParams& P, const U2* prof, const U4* keep_ge, const U4* keep_lt, int Q) {
         const uint32_t G2 = (uint32_t)(P.g * SC) * 0x00010001u;
@@ -171,7 +171,7 @@ struct ScoreLane {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             end[h] = 0;
-            if (tid[h] >= 0) { end[h] = begin[h] + rem[h]; if (end[h] > BLOCK_STEPS) end[h] = BLOCK_STEPS; }
+            if (tid[h] >= 0) { end[h] = begin[h] + rem[h]; if (end[h] > P.block_steps) end[h] = P.block_steps; }
             else begin[h] = 0;
         }
 #pragma unroll
@@ -179,7 +179,7 @@ struct ScoreLane {
 
         uint32_t tvec = 0;
 #pragma unroll 1
-        for (int k = 0; k < BLOCK_STEPS / 16; k++) {
+        for (int k = 0; k < P.block_steps / 16; k++) {
             U4 c[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -239,8 +239,8 @@ struct ScoreLane {
                 skipb[h]--;
                 rem[h] -= end[h] - begin[h];
                 begin[h] = 0;
-                pos[h] += BLOCK_STEPS;
-                cbase[h] += BLOCK_STEPS;
+                pos[h] += P.block_steps;
+                cbase[h] += P.block_steps;
             } else if (tid[h] >= 0) {
                 if ((bb >> 6) >= (best[h] >> 6)) {       // >= : a later block wins ties on (H, row); bits 6.. hold (H, row)
                     best[h] = bb;
@@ -248,11 +248,11 @@ struct ScoreLane {
                 }
                 rem[h] -= end[h] - begin[h];
                 begin[h] = 0;
-                pos[h] += BLOCK_STEPS;
-                cbase[h] += BLOCK_STEPS;
+                pos[h] += P.block_steps;
+                cbase[h] += P.block_steps;
             }
         }
-        n_steps += BLOCK_STEPS;
+        n_steps += P.block_steps;
     }
 };
 
