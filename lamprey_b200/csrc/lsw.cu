@@ -104,7 +104,7 @@ struct lsw_ctx {
     bool reuse = true;
     std::vector<int64_t> h_bb_off;
     int64_t bb_total = 0;
-    DevBuf d_blockbest, d_bb_off, d_nseg, d_segpos, d_res_s, d_seg_s, d_class_of;
+    DevBuf d_blockbest, d_bb_off, d_nseg, d_segpos, d_res_s, d_seg_s, d_class_of, d_kt;
     TaskBuf segs;
     DevBuf d_seg_skip;
     int32_t allowed_overlap = -1;
@@ -170,6 +170,14 @@ __global__ void k_scatter_offsets(const int32_t* __restrict__ order, const long 
                                   int64_t* __restrict__ roff, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         roff[order[i]] = 256 + pos[i];
+}
+
+// start descriptors of a plain task list (every task is a whole slice, no warm-up)
+__global__ void k_make_ktasks(TaskArrays t, const int64_t* __restrict__ roff, KTask* __restrict__ kt, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        KTask k; k.p0 = roff[t.read[i]] + t.a[i]; k.len = t.b[i] - t.a[i]; k.skip = 0;
+        kt[i] = k;
+    }
 }
 
 __global__ void k_iota(int32_t* __restrict__ v, int64_t n) {
@@ -433,6 +441,14 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
     }
     ReuseParams R;
     memset(&R, 0, sizeof R);
+    if (round_kind != 2) {
+        Span sp(ctx, 2);
+        CK(ctx->d_kt.ensure((size_t)n * sizeof(KTask)));
+        k_make_ktasks<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(cur.view(), ctx->d_roff.as<int64_t>(), ctx->d_kt.as<KTask>(), n);
+        CK(cudaGetLastError());
+        P.kt = ctx->d_kt.as<KTask>();
+        if (cnt) cnt->other_launches++;
+    }
     if (round_kind == 2) {
         // child tasks: K1 runs on the segment list (own head + warm-started tail), the whole-read blocks in between are looked up
         Span sp(ctx, 2);
@@ -442,6 +458,8 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         CK(ctx->d_res_s.ensure((size_t)2 * n * sizeof(int2))); CK(ctx->d_seg_s.ensure((size_t)(ctx->nseq + 1) * 8));
         R.nseg = ctx->d_nseg.as<int32_t>(); R.segpos = ctx->d_segpos.as<int32_t>();
         R.s = ctx->segs.view(); R.s.skip = ctx->d_seg_skip.as<uint8_t>();
+        CK(ctx->d_kt.ensure((size_t)2 * n * sizeof(KTask)));
+        R.s_kt = ctx->d_kt.as<KTask>(); R.roff = ctx->d_roff.as<int64_t>();
         k_plan_segments<<<grid_for(n + 1, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(R);
         CK(cudaGetLastError());
         size_t tmp = 0;
@@ -452,7 +470,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             R, ctx->d_seg[segi].as<int64_t>(), ctx->d_seg_s.as<int64_t>(), ctx->nseq);
         CK(cudaGetLastError());
         if (cnt) cnt->other_launches += 4;
-        P.t = R.s; P.seg = ctx->d_seg_s.as<int64_t>(); P.res = ctx->d_res_s.as<int2>();
+        P.t = R.s; P.kt = ctx->d_kt.as<KTask>(); P.seg = ctx->d_seg_s.as<int64_t>(); P.res = ctx->d_res_s.as<int2>();
         P.push_cands = 0; P.count_ref = 0; P.block_steps = SEG_BLOCK;
     }
     {
@@ -585,7 +603,7 @@ void lsw_destroy(lsw_ctx* ctx) {
     for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); }
     ctx->d_nfallback.release();
     ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release(); ctx->segs.release();
-    for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_seg_skip}) b->release();
+    for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_seg_skip, &ctx->d_kt}) b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

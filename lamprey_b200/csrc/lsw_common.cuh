@@ -118,10 +118,19 @@ struct TaskArrays {           // struct-of-arrays task list of one recursion rou
     uint8_t* skip;            // K1 segments (lsw_reuse.cuh): leading 64-column blocks that only warm the DP up; else null
 };
 
+// What K1 needs to start a task, in one aligned 16-byte load (built when the task list is built, so a lane
+// does not chase read -> offset -> codes through three dependent loads at every task switch).
+struct __align__(16) KTask {
+    int64_t p0;               // byte offset in codes of the slice's first base
+    int32_t len;              // slice length
+    int32_t skip;             // leading lane blocks that only warm the DP up (tail segments of lsw_reuse.cuh)
+};
+
 struct ScoreParams {
     const uint8_t*  codes;    // read codes, one byte per base, every read 16-byte aligned
     const int64_t*  roff;     // [n_reads + 1] byte offset of each read in codes
     TaskArrays      t;
+    const KTask*    kt;       // [n_tasks] start descriptors, parallel to t
     const int64_t*  seg;      // [n_seq + 1] tasks of sequence s are [seg[s], seg[s+1])
     unsigned long long* head; // [n_seq] next unclaimed task of each sequence (relative to seg[s])
     int2*           res;      // [n_tasks] x = score | (max_row << 16), y = max_col (1-based DP coords)

@@ -102,7 +102,7 @@ void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& c
         for (int h = 0; h < 2; h++) {
             if (L.tid[h] >= 0 && L.rem[h] == 0) L.finish(P, h, q, Q, [&](int t, int) { cand.push_back((uint32_t)t); });
             if (L.tid[h] < 0 && !exhausted) {
-                if (head < cnt) L.start(P, h, (int)(base + head++), Q);
+                if (head < cnt) { const int t = (int)(base + head++); L.start(P, h, t, P.kt[t], Q); }
                 else exhausted = true;
             }
         }
@@ -187,6 +187,9 @@ void emu_round(Emu& E, TraceParams T) {
     T.match = E.match; T.mismatch = E.mismatch; T.g = E.g;
     T.scratch = scratch.data(); T.scratch_stride = 1;
 
+    std::vector<KTask> kt((size_t)n);
+    for (int64_t t = 0; t < n; t++) { kt[t].p0 = E.roff[E.t_read[t]] + E.t_a[t]; kt[t].len = E.t_b[t] - E.t_a[t]; kt[t].skip = 0; }
+    P.kt = kt.data();
     const bool segmented = E.reuse && E.round > 0;
     if (E.reuse && E.round == 0) { P.blockbest = E.blockbest.data(); P.bb_off = E.bb_off.data(); P.bb_total = E.bb_total; }
     if (!segmented) {
@@ -214,9 +217,11 @@ void emu_round(Emu& E, TraceParams T) {
     for (int s = 0; s <= E.nseq; s++) seg_s[s] = segpos[E.seg[s]];
     R.segpos = segpos.data();
     R.s.read = s_read.data(); R.s.a = s_a.data(); R.s.b = s_b.data(); R.s.seq = s_seq.data(); R.s.skip = s_skip.data();
+    std::vector<KTask> s_kt((size_t)ns);
+    R.s_kt = s_kt.data(); R.roff = E.roff.data();
     for (int64_t t = 0; t < n; t++) fill_segments(R, t);
     ScoreParams PS = P;
-    PS.t = R.s; PS.seg = seg_s.data(); PS.res = res_s.data(); PS.push_cands = 0; PS.count_ref = 0; PS.block_steps = SEG_BLOCK;
+    PS.t = R.s; PS.kt = s_kt.data(); PS.seg = seg_s.data(); PS.res = res_s.data(); PS.push_cands = 0; PS.count_ref = 0; PS.block_steps = SEG_BLOCK;
     for (int s = 0; s < E.nseq; s++) {
         if (seg_s[s + 1] == seg_s[s]) continue;
         std::vector<uint32_t> none;

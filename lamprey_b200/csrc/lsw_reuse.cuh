@@ -57,6 +57,8 @@ struct ReuseParams {
     int32_t* nseg;               // plan: segments per task (scanned into segpos)
     const int32_t* segpos;       // [n + 1]
     TaskArrays s;                // segment list K1 runs on (s.skip set)
+    KTask* s_kt;                 // its start descriptors
+    const int64_t* roff;         // [n_reads] byte offset of each read in codes
     const int2* res_s;           // K1 results per segment
     int2* res_t;                 // merged result per task
     const uint32_t* blockbest;   // [n_seq][bb_total]
@@ -76,9 +78,14 @@ LSW_HD void fill_segments(const ReuseParams& R, int64_t t) {
     const int64_t i = R.segpos[t];
     R.s.read[i] = R.t.read[t]; R.s.seq[i] = (int16_t)q; R.s.skip[i] = 0;
     R.s.a[i] = a; R.s.b[i] = p.split ? p.hb : b;
+    const int64_t r0 = R.roff[R.t.read[t]];
+    KTask k; k.p0 = r0 + a; k.len = R.s.b[i] - a; k.skip = 0;
+    R.s_kt[i] = k;
     if (p.split && p.tail) {
         R.s.read[i + 1] = R.t.read[t]; R.s.seq[i + 1] = (int16_t)q; R.s.skip[i + 1] = (uint8_t)p.skip;
         R.s.a[i + 1] = p.ts; R.s.b[i + 1] = b;
+        k.p0 = r0 + p.ts; k.len = b - p.ts; k.skip = p.skip;
+        R.s_kt[i + 1] = k;
     }
 }
 

@@ -84,14 +84,12 @@ struct ScoreLane {
         }
     }
 
-    // Start task `t` in half h.
-    LSW_HD void start(const ScoreParams& P, int h, int t, int Q) {
-        const int rd = P.t.read[t];
-        const int a = P.t.a[t], b = P.t.b[t];
-        const int64_t p0 = P.roff[rd] + a;
+    // Start task `t` (descriptor k) in half h.
+    LSW_HD void start(const ScoreParams& P, int h, int t, const KTask& k, int Q) {
+        const int64_t p0 = k.p0;
         tid[h] = t;
-        len[h] = b - a;
-        rem[h] = b - a;
+        len[h] = k.len;
+        rem[h] = k.len;
         begin[h] = (int32_t)(p0 & 15);
         pos[h] = p0 & ~(int64_t)15;
         cbase[h] = 1 - begin[h];
@@ -101,12 +99,12 @@ struct ScoreLane {
 #pragma unroll
         for (int r = 0; r < NR; r++) M[r] &= keep;     // zero boundary column for this half
         nx[h] = *reinterpret_cast<const U4*>(P.codes + pos[h]);
-        skipb[h] = P.t.skip ? (int32_t)P.t.skip[t] : 0;
+        skipb[h] = k.skip;
         if (P.count_ref) {
             n_tasks += 1;
-            n_cells += (unsigned long long)(b - a) * (unsigned long long)Q;
+            n_cells += (unsigned long long)k.len * (unsigned long long)Q;
         }
-        n_comp += (unsigned long long)(b - a) * (unsigned long long)Q;
+        n_comp += (unsigned long long)k.len * (unsigned long long)Q;
     }
 
     // Retire the task in half h: publish (score, max_row, max_col) and queue it for traceback.
@@ -348,6 +346,11 @@ k_score(const ScoreParams P) {
 
         L.init();
         bool exhausted = false;
+        // the NEXT task of each half is claimed, and its descriptor load issued, one block before it is needed:
+        // the load's latency hides behind that block instead of stalling the warp at the task switch
+        int nxt[2] = {-1, -1};
+        KTask nk[2];
+        nk[0].p0 = nk[1].p0 = 0; nk[0].len = nk[1].len = 0; nk[0].skip = nk[1].skip = 0;
         for (;;) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -357,9 +360,18 @@ k_score(const ScoreParams P) {
                         P.cand[i] = (uint32_t)t;
                         P.cand_key[i] = (uint16_t)(((uint32_t)q << 8) | (uint32_t)key);
                     });
-                if (L.tid[h] < 0 && !exhausted) {
+                if (L.tid[h] < 0) {
+                    if (nxt[h] >= 0) { L.start(P, h, nxt[h], nk[h], Q); nxt[h] = -1; }
+                    else if (!exhausted) {
+                        const unsigned long long i = atomicAdd(&P.head[q], 1ull);
+                        if ((long long)i < cnt) { const int t = (int)(base + (long long)i); L.start(P, h, t, P.kt[t], Q); }
+                        else exhausted = true;
+                    }
+                }
+                if (L.tid[h] >= 0 && L.rem[h] <= P.block_steps - L.begin[h] && nxt[h] < 0 && !exhausted) {
+                    // this block is the task's last: claim the next one now
                     const unsigned long long i = atomicAdd(&P.head[q], 1ull);
-                    if ((long long)i < cnt) L.start(P, h, (int)(base + (long long)i), Q);
+                    if ((long long)i < cnt) { nxt[h] = (int)(base + (long long)i); nk[h] = P.kt[nxt[h]]; }
                     else exhausted = true;
                 }
             }
