@@ -870,8 +870,11 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
                 if (ctx->timed[k].kind < 3 && cudaEventElapsedTime(&m, ctx->timed[k].e0, ctx->timed[k].e1) == cudaSuccess) ms[ctx->timed[k].kind] += m;
             }
             dbg_from = ctx->timed.size();
-            fprintf(stderr, "[lsw] round %d: tasks %lld -> children %d, hits so far %llu, score %.3f ms, trace %.3f ms, other %.3f ms\n",
-                    round, (long long)n, total_next, h_nhits, ms[0], ms[1], ms[2]);
+            unsigned long long c4[4] = {0, 0, 0, 0};
+            cudaMemcpy(c4, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[lsw] round %d: tasks %lld -> children %d, hits so far %llu, score %.3f ms, trace %.3f ms, other %.3f ms; "
+                            "cumulative lane-steps %llu, computed cells %llu, reference cells %llu\n",
+                    round, (long long)n, total_next, h_nhits, ms[0], ms[1], ms[2], c4[2], c4[3], c4[1]);
         }
         if (round == 0) { cnt.top_tasks = n; }
         cur ^= 1;

@@ -352,6 +352,8 @@ k_score(const ScoreParams P) {
         KTask nk[2];
         nk[0].p0 = nk[1].p0 = 0; nk[0].len = nk[1].len = 0; nk[0].skip = nk[1].skip = 0;
         for (;;) {
+            // 1. retire finished tasks, activate prefetched ones
+            bool want[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 if (L.tid[h] >= 0 && L.rem[h] == 0)
@@ -360,19 +362,28 @@ k_score(const ScoreParams P) {
                         P.cand[i] = (uint32_t)t;
                         P.cand_key[i] = (uint16_t)(((uint32_t)q << 8) | (uint32_t)key);
                     });
-                if (L.tid[h] < 0) {
-                    if (nxt[h] >= 0) { L.start(P, h, nxt[h], nk[h], Q); nxt[h] = -1; }
-                    else if (!exhausted) {
-                        const unsigned long long i = atomicAdd(&P.head[q], 1ull);
-                        if ((long long)i < cnt) { const int t = (int)(base + (long long)i); L.start(P, h, t, P.kt[t], Q); }
-                        else exhausted = true;
-                    }
-                }
-                if (L.tid[h] >= 0 && L.rem[h] <= P.block_steps - L.begin[h] && nxt[h] < 0 && !exhausted) {
-                    // this block is the task's last: claim the next one now
-                    const unsigned long long i = atomicAdd(&P.head[q], 1ull);
-                    if ((long long)i < cnt) { nxt[h] = (int)(base + (long long)i); nk[h] = P.kt[nxt[h]]; }
-                    else exhausted = true;
+                if (L.tid[h] < 0 && nxt[h] >= 0) { L.start(P, h, nxt[h], nk[h], Q); nxt[h] = -1; }
+                // a task is wanted now (idle half) or for the next boundary (this block is the current task's last)
+                want[h] = !exhausted && nxt[h] < 0 &&
+                          (L.tid[h] < 0 || L.rem[h] <= P.block_steps - L.begin[h]);
+            }
+            // 2. claim tasks for the whole warp with ONE atomic: all lanes pull from the same per-sequence queue, and
+            //    per-lane atomics on one address serialise in L2 (tens of millions of short tasks per round)
+            const unsigned b0 = __ballot_sync(0xFFFFFFFFu, want[0]), b1 = __ballot_sync(0xFFFFFFFFu, want[1]);
+            if (b0 | b1) {
+                const int c0 = __popc(b0), c1 = __popc(b1);
+                unsigned long long first = 0;
+                if (lane == 0) first = atomicAdd(&P.head[q], (unsigned long long)(c0 + c1));
+                first = __shfl_sync(0xFFFFFFFFu, first, 0);
+                const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (!want[h]) continue;
+                    const long long i = (long long)first + (h ? c0 + __popc(b1 & lt) : __popc(b0 & lt));
+                    if (i >= cnt) { exhausted = true; continue; }
+                    const int t = (int)(base + i);
+                    if (L.tid[h] < 0) L.start(P, h, t, P.kt[t], Q);           // idle half: start right away
+                    else { nxt[h] = t; nk[h] = P.kt[t]; }                     // busy half: descriptor load in flight
                 }
             }
             const bool active = (L.tid[0] >= 0) || (L.tid[1] >= 0);

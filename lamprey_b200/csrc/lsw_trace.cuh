@@ -575,7 +575,10 @@ k_trace_fast(const TraceParams P) {
         }
         __syncwarp();
         for (;;) {
-            const long long i = (long long)atomicAdd(&P.head[q], 2ull);
+            // one claim per warp (64 candidates), not one per lane: per-lane atomics on the queue head serialise in L2
+            unsigned long long first = 0;
+            if (lane == 0) first = atomicAdd(&P.head[q], 64ull);
+            const long long i = (long long)__shfl_sync(0xFFFFFFFFu, first, 0) + 2 * lane;
             const bool active = i < cnt;
             if (!__any_sync(0xFFFFFFFFu, active)) break;
             if (active) {
