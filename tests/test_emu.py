@@ -140,3 +140,49 @@ def test_emu_fast_traceback_equals_full_window():
     for a, b in zip(fast, full):
         assert np.array_equal(cig1[a["cigar_off"]:a["cigar_off"] + a["n_cigar"]], cig2[b["cigar_off"]:b["cigar_off"] + b["n_cigar"]])
     _check_tasks(reads, seqs, tasks)
+
+
+def _oracle_rows(reads, seqs, thr, scoring=(2, -1, -1)):
+    rows, calls, cells = [], 0, 0
+    for i, r in enumerate(reads):
+        h, st = c_oracle.find_all(r, seqs, thr, scoring[0], scoring[1], scoring[2], scoring[2])
+        h = h[np.argsort(h["start"], kind="stable")]
+        calls += st["calls"]
+        cells += st["cells"]
+        rows += [(i, x["seq"], x["start"], x["end"], x["matches"], x["mismatches"], x["score"], x["q_pos"], x["q_end"],
+                  x["depth"]) for x in h]
+    return np.array(rows, np.int32).reshape(-1, 10), calls, cells
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_emu_find_all_random_schemas_and_block_edges(seed):
+    # random schemas (lengths up to the 63-row limit), reads made of noisy copies so the recursion is deep, read
+    # lengths on and around the 64-column block grid the DP-reuse path is built on; compared with the C oracle
+    rng = random.Random(100 + seed)
+    scoring = [(2, -1, -1), (2, -1, -1), (1, -1, -1), (3, -2, -2), (2, -3, -1)][seed]
+    thr = [0.7, 0.75, 0.6, 0.7, 0.8][seed]
+    qlens = [rng.choice([5, 15, 16, 17, 20, 21, 24, 25, 28, 31, 33, 40, 47, 56, 57, 63]) for _ in range(7)]
+    if scoring[0] == 3:
+        qlens = [min(q, 40) for q in qlens]          # match * len + |gap| <= 127
+    seqs = ["".join(rng.choice("ACGT") for _ in range(q)) for q in qlens]
+    reads = []
+    for n in [0, 63, 64, 65, 127, 128, 129, 191, 192, 193, 256, 320, 448, 449, 700, 1024, 1500, 2111, 3000]:
+        r = []
+        while len(r) < n:
+            s = seqs[rng.randrange(len(seqs))]
+            if rng.random() < 0.3:
+                s = "".join(rng.choice("ACGT") for _ in range(rng.randrange(1, 40)))
+            for ch in s:
+                u = rng.random()
+                if u < 0.04:
+                    continue
+                r.append(rng.choice("ACGT") if u < 0.08 else ch)
+                if u > 0.96:
+                    r.append(rng.choice("ACGT"))
+        reads.append("".join(r[:n]))
+    want, calls, cells = _oracle_rows(reads, seqs, thr, scoring)
+    for reuse in (True, False):
+        hits, cnt = emu_lib.find_all(reads, seqs, thr, *scoring, reuse=reuse)
+        assert np.array_equal(hits_matrix(hits), want), (seed, reuse)
+        assert (cnt["tasks"], cnt["cells"]) == (calls, cells)
+    assert len(want) > 50

@@ -276,3 +276,54 @@ def test_device_overlap_pruning(engine):
             want = chain.removeOverlappingPrimerAlignments(False, al, 4)  # lamprey.py:1536
             got = batch.alignments(i, pruned=True)
             assert [(a.start, a.end, a.primer_name) for a in got] == [(a.start, a.end, a.primer_name) for a in want]
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_find_all_random_schemas_and_block_edges(engine, seed, monkeypatch):
+    # random schemas / scoring / thresholds, deep recursion, read lengths on and around the 64-column block grid of
+    # the DP-reuse path; with and without the reuse, against the C oracle
+    rng = random.Random(100 + seed)
+    scoring = [(2, -1, -1), (2, -1, -1), (1, -1, -1), (3, -2, -2), (2, -3, -1)][seed]
+    thr = [0.7, 0.75, 0.6, 0.7, 0.8][seed]
+    qlens = [rng.choice([5, 15, 16, 17, 20, 21, 24, 25, 28, 31, 33, 40, 47, 56, 57, 63]) for _ in range(7)]
+    if scoring[0] == 3:
+        qlens = [min(q, 40) for q in qlens]
+    seqs = ["".join(rng.choice("ACGT") for _ in range(q)) for q in qlens]
+    reads = []
+    for n in [0, 63, 64, 65, 127, 128, 129, 191, 192, 193, 256, 320, 448, 449, 700, 1024, 1500, 2111, 3000] * 3:
+        r = []
+        while len(r) < n:
+            s = seqs[rng.randrange(len(seqs))]
+            if rng.random() < 0.3:
+                s = "".join(rng.choice("ACGT") for _ in range(rng.randrange(1, 40)))
+            for ch in s:
+                u = rng.random()
+                if u < 0.04:
+                    continue
+                r.append(rng.choice("ACGT") if u < 0.08 else ch)
+                if u > 0.96:
+                    r.append(rng.choice("ACGT"))
+        reads.append("".join(r[:n]))
+    rows, calls, cells = [], 0, 0
+    for i, r in enumerate(reads):
+        h, st = c_oracle.find_all(r, seqs, thr, scoring[0], scoring[1], scoring[2], scoring[2])
+        h = h[np.argsort(h["start"], kind="stable")]
+        calls += st["calls"]
+        cells += st["cells"]
+        rows += [(i, x["seq"], x["start"], x["end"], x["matches"], x["mismatches"], x["score"], x["q_pos"], x["q_end"],
+                  x["depth"]) for x in h]
+    want = np.array(rows, np.int32).reshape(-1, 10)
+    engine.set_scoring(scoring[0], scoring[1], scoring[2], scoring[2])
+    engine.set_queries(seqs)
+    engine.upload_read_list(reads)
+    for no_reuse in ("", "1"):
+        if no_reuse:
+            monkeypatch.setenv("LSW_NO_REUSE", "1")
+        else:
+            monkeypatch.delenv("LSW_NO_REUSE", raising=False)
+        hits = engine.find_all(thr)
+        assert np.array_equal(hits_matrix(hits), want), (seed, no_reuse)
+        c = engine.last_counters
+        assert (c["tasks"], c["cells"]) == (calls, cells)
+        assert (c["computed_cells"] < c["cells"]) == (not no_reuse and c["rounds"] > 1 and c["computed_cells"] != c["cells"])
+    engine.set_scoring(2, -1, -1, -1)
