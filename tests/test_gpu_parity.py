@@ -325,5 +325,8 @@ def test_find_all_random_schemas_and_block_edges(engine, seed, monkeypatch):
         assert np.array_equal(hits_matrix(hits), want), (seed, no_reuse)
         c = engine.last_counters
         assert (c["tasks"], c["cells"]) == (calls, cells)
-        assert (c["computed_cells"] < c["cells"]) == (not no_reuse and c["rounds"] > 1 and c["computed_cells"] != c["cells"])
+        if no_reuse:
+            assert c["computed_cells"] == c["cells"]
+        else:
+            assert c["computed_cells"] <= c["cells"]
     engine.set_scoring(2, -1, -1, -1)
