@@ -134,6 +134,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The JSON line goes to the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def workload_reads(args, rank, world, workers):
     from lamprey_b200 import synth
     kw = dict(synth.CONFIGS[args.workload])
@@ -177,7 +190,7 @@ def run_reference(args):
                              "sample": "%d reads of %s per step, Cython build of oracle/swalign_ref.py + "
                                        "seeding_ref.py, one process per core" % (sample, args.workload)},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -195,6 +208,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-engines", type=int, default=2, help="contexts (CUDA streams) that take alternate e2e steps")
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: libraries that print to fd 1 (NCCL's version
+    # banner, forked workers) are pointed at stderr for the whole run.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -389,7 +408,7 @@ def main():
                 "gpu_launches": acc["launches"],
                 "breakdown_ms_per_step": {k: acc[k] / args.steps for k in ("ms_score", "ms_trace", "ms_other", "ms_total")},
                 "parity_vs_cpu_sample": parity}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
