@@ -106,7 +106,9 @@ const char* lsw_last_error(const lsw_ctx* ctx);      /* ctx may be NULL: error o
 int lsw_set_stream(lsw_ctx* ctx, void* cuda_stream);
 
 /* swalign.NucleotideScoringMatrix(match, mismatch) + LocalAlignment(gap_penalty, gap_extension_penalty).
- * Supported: match > 0, mismatch < 0, gap == gap_ext < 0, match*LSW_MAX_QUERY_LEN + |gap| <= 127. */
+ * Supported: match > 0, mismatch < 0, gap == gap_ext < 0, and match*len(query) + |gap| <= 127 for every query.
+ * Scoring and queries may be set in either order; lsw_find_all / lsw_align_tasks return LSW_E_UNSUPPORTED when the
+ * pair in force does not fit. */
 int lsw_set_scoring(lsw_ctx* ctx, int match, int mismatch, int gap, int gap_ext);
 
 /* The schema sequences (already in search order; reverse complements supplied by the caller).

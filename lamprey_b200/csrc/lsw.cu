@@ -646,7 +646,11 @@ int lsw_set_scoring(lsw_ctx* ctx, int match, int mismatch, int gap, int gap_ext)
     if (match * LSW_MAX_QUERY_LEN - gap > 127 && match * 1 - gap > 127)
         return fail(ctx, LSW_E_UNSUPPORTED, "scores do not fit the packed 8.8 fixed-point cells");
     ctx->match = match; ctx->mismatch = mismatch; ctx->g = -gap;
-    // queries set earlier must still fit
+    return LSW_OK;          // scoring and queries may be set in either order: the pair is checked when work is submitted
+}
+
+// Scores are kept as 8.8 fixed point in 16-bit halves, biased by g: the largest value a cell can hold must stay <= 127.
+static int check_scoring_fits(lsw_ctx* ctx) {
     for (int s = 0; s < ctx->nseq; s++)
         if (ctx->match * ctx->qlen[s] + ctx->g > 127)
             return fail(ctx, LSW_E_UNSUPPORTED, "match * len(query) + |gap| must be <= 127 for the packed cells");
@@ -662,8 +666,6 @@ int lsw_set_queries(lsw_ctx* ctx, int n, const uint8_t* concat, const int32_t* o
         const int len = offs[s + 1] - offs[s];
         if (len < 1 || len > LSW_MAX_QUERY_LEN)
             return fail(ctx, LSW_E_UNSUPPORTED, "query length must be 1..63 (all rows are kept in registers)");
-        if (ctx->match * len + ctx->g > 127)
-            return fail(ctx, LSW_E_UNSUPPORTED, "match * len(query) + |gap| must be <= 127 for the packed cells");
         qlen[s] = len;
         for (int j = 0; j < len; j++) {
             const int code = encode_base(concat[offs[s] + j]) < CODE_OTHER ? (int)encode_base(concat[offs[s] + j]) : -1;
@@ -768,6 +770,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     if (!ctx) return LSW_E_ARG;
     if (!(thr > 0.0)) return fail(ctx, LSW_E_ARG, "identity_threshold must be > 0 (the reference recurses forever otherwise)");
     if (ctx->nseq <= 0) return fail(ctx, LSW_E_STATE, "lsw_set_queries has not been called");
+    if (int rc = check_scoring_fits(ctx)) return rc;
     CK(cudaSetDevice(ctx->device));
     lsw_counters cnt;
     memset(&cnt, 0, sizeof cnt);
@@ -960,6 +963,7 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n, const lsw_task* tasks, lsw_result* 
     if (!ctx) return LSW_E_ARG;
     if (n < 0 || (n > 0 && (!tasks || !out))) return fail(ctx, LSW_E_ARG, "lsw_align_tasks: bad argument");
     if (ctx->nseq <= 0) return fail(ctx, LSW_E_STATE, "lsw_set_queries has not been called");
+    if (int rc = check_scoring_fits(ctx)) return rc;
     if (n >= (1ll << 30)) return fail(ctx, LSW_E_ARG, "at most 2^30 - 1 tasks per call");
     if (cigar_used) *cigar_used = 0;
     if (n == 0) return LSW_OK;

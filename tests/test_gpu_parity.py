@@ -330,3 +330,26 @@ def test_find_all_random_schemas_and_block_edges(engine, seed, monkeypatch):
         else:
             assert c["computed_cells"] <= c["cells"]
     engine.set_scoring(2, -1, -1, -1)
+
+
+def test_error_behaviour_of_the_engine(engine):
+    # scoring and queries may arrive in either order; the pair is checked when work is submitted
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(["ACGT" * 15])
+    engine.set_scoring(3, -2, -2, -2)                   # 3 * 60 + 2 > 127: accepted here ...
+    engine.upload_read_list(["ACGT" * 40])
+    with pytest.raises(ValueError, match="127"):        # ... refused when it would have to be computed
+        engine.find_all(0.7)
+    engine.set_queries(["ACGT" * 5])                    # now it fits
+    assert len(engine.find_all(0.7)) > 0
+    with pytest.raises(ValueError):
+        engine.set_queries(["ACGN"])                    # non-ACGT query
+    with pytest.raises(ValueError):
+        engine.set_queries(["A" * 64])                  # longer than the register file holds
+    with pytest.raises(ValueError):
+        engine.set_scoring(2, 0, -1, -1)                # mismatch must be negative
+    with pytest.raises(NotImplementedError):
+        engine.set_scoring(2, -1, -2, -1)               # affine gaps
+    with pytest.raises(ValueError):
+        engine.find_all(0.0)                            # the reference would recurse forever
+    engine.set_scoring(2, -1, -1, -1)
