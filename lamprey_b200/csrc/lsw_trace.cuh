@@ -287,15 +287,11 @@ struct TraceLane {
         bool active, failed, first_cell;
         // loaded operands
         uint32_t wc, wu, wl, wd; int qb, rb;
-        // operands of the diagonal successor (r-1, cl-1), fetched one iteration early: most steps of a traceback are
-        // 'm', so the next cell's loads are in flight while this cell is decided (the walk is a chain of dependent loads)
-        uint32_t pu, pl, pd; int pqb, prb; bool pref;
 
         LSW_HD void init(const TraceParams& P, const Half& hf, int h, int64_t slot) {
             active = failed = false; first_cell = true;
             r = cl = depth = last = state = 0; ret = OPC_NONE; mv = 0; st = 0; budget = 0;
             wc = wu = wl = wd = 0; qb = rb = 0;
-            pu = pl = pd = 0; pqb = prb = 0; pref = false;
             if (hf.t < 0 || hf.v.score <= 0) return;
             scr = P.scratch + slot;                               // 32-bit index arithmetic below: the host keeps
             stride = (uint32_t)P.scratch_stride;                  // the scratch under 2^31 words
@@ -318,20 +314,10 @@ struct TraceLane {
             if (!active) return;
             if (r <= 0 || cl <= 0) return;                        // decide() ends the walk
             const int i = r - 1, iu = i > 0 ? i - 1 : 0, cp = cl > 1 ? cl - 1 : 1;
-            const uint32_t bp = (colbase + (uint32_t)cp * WORDS) * stride;
-            const uint32_t ou = (uint32_t)(iu >> 1) * stride;
-            if (!pref) {                                           // operands of this cell were not prefetched
-                const uint32_t bc = (colbase + (uint32_t)cl * WORDS) * stride;
-                const uint32_t oi = (uint32_t)(i >> 1) * stride;
-                wc = scr[bc + oi]; wu = scr[bc + ou]; wl = scr[bp + oi]; wd = scr[bp + ou];
-                qb = qc[i]; rb = refw[cl];
-            }
-            // successor (r-1, cl-1): its own cell is this cell's diagonal word (wd); fetch its up / left / diagonal
-            const int iuu = iu > 0 ? iu - 1 : 0, cpp = cp > 1 ? cp - 1 : 1;
-            const uint32_t bpp = (colbase + (uint32_t)cpp * WORDS) * stride;
-            const uint32_t ouu = (uint32_t)(iuu >> 1) * stride;
-            pu = scr[bp + ouu]; pl = scr[bpp + ou]; pd = scr[bpp + ouu];
-            pqb = qc[iu]; prb = refw[cp];
+            const uint32_t bc = (colbase + (uint32_t)cl * WORDS) * stride, bp = (colbase + (uint32_t)cp * WORDS) * stride;
+            const uint32_t oi = (uint32_t)(i >> 1) * stride, ou = (uint32_t)(iu >> 1) * stride;
+            wc = scr[bc + oi]; wu = scr[bc + ou]; wl = scr[bp + oi]; wd = scr[bp + ou];
+            qb = qc[i]; rb = refw[cl];
         }
         LSW_HD void fail() { failed = true; active = false; }
         LSW_HD void decide(PathOut& po) {
@@ -376,7 +362,6 @@ struct TraceLane {
                 mv = (mv << 1) | (pushU ? 1u : 0u);
                 depth++;
                 state = 0;
-                pref = false;
                 if (pushU) r -= 1; else cl -= 1;
                 return;
             }
@@ -386,7 +371,6 @@ struct TraceLane {
                 state = (int)(st & 3u);
                 mv >>= 1; st >>= 2;
                 depth--;
-                pref = false;
                 return;
             }
             // a path cell is resolved
@@ -395,9 +379,6 @@ struct TraceLane {
             if (keep_ops && !po.push(res)) { fail(); return; }
             po.m += (res == OPC_M && sub == M_) ? 1 : 0;
             po.x += (res == OPC_M && sub == M_) ? 0 : 1;
-            // diagonal step inside the window: the successor's operands are the prefetched ones
-            pref = (res == OPC_M) && i > 0 && cl > 1;
-            if (pref) { wc = wd; wu = pu; wl = pl; wd = pd; qb = pqb; rb = prb; }
             r -= (res != OPC_D) ? 1 : 0;
             cl -= (res != OPC_I) ? 1 : 0;
             state = 0;
