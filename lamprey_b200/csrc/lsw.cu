@@ -350,13 +350,14 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     const int blocks2 = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * std::min(occ2, 2));
     const int64_t threads2 = (int64_t)blocks2 * TRACE_THREADS;
     const int64_t W = trace_window_full(qmax, ctx->match, ctx->g);
-    if ((size_t)threads * (size_t)(Wf + 4) * (NR / 2) >= (1ull << 31))
+    constexpr int UNITS = TraceLane<NR>::UNITS;          // 16 bytes per (window column, unit, lane): both tasks of the lane
+    if ((size_t)threads2 * (size_t)W * (NR2 / 16) >= (1ull << 31))
         return fail(ctx, LSW_E_INTERNAL, "traceback scratch exceeds the 32-bit index range");
-    const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * (NR / 2) * 4, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
+    const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * UNITS * 16, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
     CK(ctx->d_scratch.ensure(need));
     P.scratch = ctx->d_scratch.as<uint32_t>();
     P.scratch_stride = TRACE_THREADS;
-    P.scratch_block_words = (int64_t)(Wf + 4) * (NR / 2) * TRACE_THREADS;
+    P.scratch_block_words = (int64_t)(Wf + 4) * UNITS * TRACE_THREADS;
     k_trace_fast<NR><<<blocks, TRACE_THREADS, smem, ctx->stream>>>(P);
     CK(cudaGetLastError());
     P.scratch_stride = threads2;

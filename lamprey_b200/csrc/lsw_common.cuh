@@ -171,9 +171,9 @@ struct TraceParams {
     int             n_class_seqs;
     uint32_t*       fallback;     // tasks the short-window kernel could not prove exact
     unsigned long long* nfallback;
-    uint32_t*       scratch;      // direction bits, [window col][word][thread]
+    uint32_t*       scratch;      // fast: H bytes, [block][window col][unit][thread] x 16 B; full: op bits, [window col][word][thread]
     int64_t         scratch_stride;   // words between consecutive (column, word) rows: threads of a block (fast) / of the launch (full)
-    int64_t         scratch_block_words;  // k_trace_fast: scratch words per block
+    int64_t         scratch_block_words;  // k_trace_fast: 16-byte scratch elements per block
     int32_t match, mismatch, g;
     int32_t mode;             // 0 = find_all (hit test, children), 1 = align_tasks (result records, CIGAR)
     double  thr;
@@ -190,7 +190,7 @@ struct TraceParams {
     int64_t cigar_cap;
     unsigned long long* ncigar;
     int32_t* errflag;
-    int32_t debug;            // timing experiments only (LSW_K2_DEBUG): 1 = fill only, 2 = walk only
+    int32_t debug;            // timing experiments only (LSW_K2_DEBUG): 1 = fill only, 2 = fill without the scratch stores
 };
 
 }  // namespace lsw

@@ -140,7 +140,7 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
             trace_full_task<NR2>(T, t0, 0);
             if (t1 >= 0) trace_full_task<NR2>(T, t1, 0);
         } else {
-            L.run_pair(T, prof.data(), t0, t1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
+            L.run_pair(T, prof.data(), T.qcodes + (size_t)q * QSTRIDE, t0, t1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
         }
     }
 }
@@ -181,11 +181,12 @@ void emu_round(Emu& E, TraceParams T) {
     P.push_cands = 1; P.count_ref = 1; P.block_steps = BLOCK_STEPS;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
-    std::vector<uint32_t> scratch((size_t)(size_t)std::max(trace_window_full(qmax, E.match, E.g) * 4, (trace_window_fast_max(qmax, E.match, E.g) + 4) * 32) + 16);
+    // one lane: fast layout = 16 B per (column, unit), at most 9 units; full layout = 4 words per column
+    std::vector<uint4> scratch((size_t)std::max(trace_window_full(qmax, E.match, E.g), (trace_window_fast_max(qmax, E.match, E.g) + 4) * 9) + 4);
     T.codes = E.codes.data(); T.roff = E.roff.data(); T.t = view(E); T.res = E.res.data();
     T.qcodes = E.qcodes.data(); T.qlen = E.qlen.data();
     T.match = E.match; T.mismatch = E.mismatch; T.g = E.g;
-    T.scratch = scratch.data(); T.scratch_stride = 1;
+    T.scratch = reinterpret_cast<uint32_t*>(scratch.data()); T.scratch_stride = 1;
 
     std::vector<KTask> kt((size_t)n);
     for (int64_t t = 0; t < n; t++) { kt[t].p0 = E.roff[E.t_read[t]] + E.t_a[t]; kt[t].len = E.t_b[t] - E.t_a[t]; kt[t].skip = 0; }

@@ -239,9 +239,13 @@ LSW_HD void trace_full_task(const TraceParams& P, const int t, const int64_t slo
 // all lanes of a warp serve one sequence whose profile sits in shared memory.  Per pair:
 //   fill   n = max(window lengths) columns of VALUES with the K1 recurrence (2 DPX + 1 add per two
 //          cells, no arg-max key), both windows right-aligned on their own max_col; after every
-//          column the H bytes of both tasks go to scratch, two rows of both tasks per 32-bit word;
-//   walk   each task in turn: a flat state machine, one cell evaluation per iteration, that applies
-//          the op rule lazily and proves every decision (see the file header).
+//          column the H bytes of both tasks go to scratch in 8-byte UNITS of eight consecutive rows,
+//          unit u = rows 7u .. 7u+7 (neighbouring units share a row, so a cell and the cell above it
+//          are always in one unit); one 16-byte store per unit carries both tasks;
+//   walk   each task: a flat state machine, one cell evaluation per iteration, that applies the op
+//          rule lazily and proves every decision (see the file header).  A cell needs the unit of its
+//          own column and of the column to the left: the walker keeps both and, because it moves one
+//          cell at a time, loads about one new unit per iteration.
 #if defined(LSW_EMU_STATS)
 static unsigned long long g_walk_iters = 0, g_walks = 0, g_fill_steps = 0;
 #endif
@@ -250,7 +254,7 @@ template <int NR>
 struct TraceLane {
     static_assert(NR % 4 == 0 && NR <= 64, "rows in registers");
     static constexpr int PROF_STRIDE = NR / 2 + 1;
-    static constexpr int WORDS = NR / 2;          // scratch words per window column (both tasks)
+    static constexpr int UNITS = (NR + 5) / 7;    // 8-byte units per window column and task: ceil((NR - 1) / 7)
     static constexpr int MAXD = 15;               // nesting limit of run-flag evaluations (2 state bits each)
 
     uint32_t M[NR];
@@ -274,30 +278,38 @@ struct TraceLane {
 
     // One traceback in progress.  load() issues the scratch / code loads of the current cell, decide()
     // consumes them and moves on: run_pair() calls load() for BOTH tasks of the lane before either decide(),
-    // so the two dependent-load chains overlap (the walk is latency bound).
+    // so the two dependent-load chains overlap.
+    LSW_HD static int unit_of(int i) { return i > 0 ? ((i - 1) * 37) >> 8 : 0; }     // (i - 1) / 7 for i <= 63
+    LSW_HD static int unit_byte(const uint2& v, int k) { return (int)(prmt(v.x, v.y, (uint32_t)k) & 0xFFu); }
+
     struct Walker {
         // constants of the task
-        const uint32_t* scr; uint32_t stride, colbase; int sh;
-        const uint8_t* qc; const uint8_t* refw;
+        const uint2* scr; uint32_t stride2, colbase;
+        const uint8_t* qc; const uint32_t* ref4; int rlead;
         int M_, X_, g, score, c0; bool keep_ops;
         // state
         int r, cl, depth, ret, last, state, budget;
         uint32_t mv;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
         uint32_t st;                  // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
         bool active, failed, first_cell;
-        // loaded operands
-        uint32_t wc, wu, wl, wd; int qb, rb;
+        // operands: the units of column cl (A) and cl - 1 (B) that hold rows r-1 and r-2, four read codes
+        uint2 A, B; int tagA, tagB;   // tag = 16 * column + unit, -1 = empty
+        uint32_t rw; int tagR;
+        int pc, qb, rb;               // byte of the cell in its unit, query / read code of the cell
 
-        LSW_HD void init(const TraceParams& P, const Half& hf, int h, int64_t slot) {
+        LSW_HD void init(const TraceParams& P, const Half& hf, int h, int64_t slot, const uint8_t* qcodes) {
             active = failed = false; first_cell = true;
             r = cl = depth = last = state = 0; ret = OPC_NONE; mv = 0; st = 0; budget = 0;
-            wc = wu = wl = wd = 0; qb = rb = 0;
+            A = B = make_uint2(0u, 0u); tagA = tagB = tagR = -1; rw = 0; pc = qb = rb = 0;
             if (hf.t < 0 || hf.v.score <= 0) return;
-            scr = P.scratch + slot;                               // 32-bit index arithmetic below: the host keeps
-            stride = (uint32_t)P.scratch_stride;                  // the scratch under 2^31 words
-            colbase = (uint32_t)(hf.first - 1) * WORDS;
-            sh = 16 * h;                                          // bytes 0,1: low task; bytes 2,3: high task
-            qc = hf.v.qc; refw = hf.v.ref + hf.c0 - 1;            // refw[cl] = read code of window column cl
+            scr = reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(P.scratch) + slot) + h;
+            stride2 = 2u * (uint32_t)P.scratch_stride;            // uint2 elements between consecutive (column, unit) rows
+            colbase = (uint32_t)(hf.first - 1);
+            qc = qcodes;
+            // ref[c0 + cl - 1] is the read code of window column cl; read through aligned words (the code array is padded)
+            const uint8_t* refw = hf.v.ref + hf.c0 - 1;
+            rlead = (int)(reinterpret_cast<uintptr_t>(refw) & 3u);
+            ref4 = reinterpret_cast<const uint32_t*>(refw - rlead);
             M_ = P.match; X_ = P.mismatch; g = P.g; score = hf.v.score; c0 = hf.c0;
             keep_ops = (P.mode == 1);
             r = hf.v.row; cl = hf.ncols;
@@ -313,11 +325,21 @@ struct TraceLane {
         LSW_HD void load() {
             if (!active) return;
             if (r <= 0 || cl <= 0) return;                        // decide() ends the walk
-            const int i = r - 1, iu = i > 0 ? i - 1 : 0, cp = cl > 1 ? cl - 1 : 1;
-            const uint32_t bc = (colbase + (uint32_t)cl * WORDS) * stride, bp = (colbase + (uint32_t)cp * WORDS) * stride;
-            const uint32_t oi = (uint32_t)(i >> 1) * stride, ou = (uint32_t)(iu >> 1) * stride;
-            wc = scr[bc + oi]; wu = scr[bc + ou]; wl = scr[bp + oi]; wd = scr[bp + ou];
-            qb = qc[i]; rb = refw[cl];
+            const int i = r - 1, u = unit_of(i);
+            const int tA = 16 * cl + u, tB = cl > 1 ? tA - 16 : -1;
+            uint2 nA, nB = make_uint2(0u, 0u);
+            if (tagA == tA) nA = A; else if (tagB == tA) nA = B;
+            else nA = scr[((colbase + (uint32_t)cl) * UNITS + (uint32_t)u) * stride2];
+            if (tB >= 0) {
+                if (tagB == tB) nB = B; else if (tagA == tB) nB = A;
+                else nB = scr[((colbase + (uint32_t)cl - 1u) * UNITS + (uint32_t)u) * stride2];
+            }
+            A = nA; B = nB; tagA = tA; tagB = tB;
+            pc = i - 7 * u;
+            qb = qc[i];
+            const int off = cl + rlead;
+            if ((off >> 2) != tagR) { tagR = off >> 2; rw = ref4[tagR]; }
+            rb = (int)((rw >> (8 * (off & 3))) & 0xFFu);
         }
         LSW_HD void fail() { failed = true; active = false; }
         LSW_HD void decide(PathOut& po) {
@@ -326,13 +348,13 @@ struct TraceLane {
             g_walk_iters++;
 #endif
             if (r <= 0 || cl <= 0) { active = false; return; }    // only at depth 0: the matrix boundary is zero
-            const int i = r - 1, iu = i > 0 ? i - 1 : 0;
-            const int hc = (int)((wc >> (sh + 8 * (i & 1))) & 0xFFu);
+            const int i = r - 1;
+            const int hc = unit_byte(A, pc);
             if (first_cell) { if (hc != score) { fail(); return; } first_cell = false; }   // window too short for the best cell
             if (depth == 0 && state == 0 && hc == 0) { active = false; return; }           // path ends at the first zero cell
-            const int hu = i > 0 ? (int)((wu >> (sh + 8 * (iu & 1))) & 0xFFu) : 0;
-            const int hl = cl > 1 ? (int)((wl >> (sh + 8 * (i & 1))) & 0xFFu) : 0;
-            const int hd = (i > 0 && cl > 1) ? (int)((wd >> (sh + 8 * (iu & 1))) & 0xFFu) : 0;
+            const int hu = i > 0 ? unit_byte(A, pc - 1) : 0;
+            const int hl = cl > 1 ? unit_byte(B, pc) : 0;
+            const int hd = (i > 0 && cl > 1) ? unit_byte(B, pc - 1) : 0;
             const int sub = (qb == rb) ? M_ : X_;
             const bool tieL = (hc == hl - g), tieU = (hc == hu - g), tieM = (hc == hd + sub);
             // a cell next to the artificial left boundary cannot be decided (its left / diagonal value is unknown)
@@ -395,7 +417,7 @@ struct TraceLane {
 
     // fill + walk for the pair (t0, t1); t1 may be -1.  fb(t): push a task to the fallback list.
     template <class Fallback>
-    LSW_HD void run_pair(const TraceParams& P, const U2* prof, int t0, int t1, int64_t slot, Fallback fb) {
+    LSW_HD void run_pair(const TraceParams& P, const U2* prof, const uint8_t* qcodes, int t0, int t1, int64_t slot, Fallback fb) {
         Half hf[2];
         setup(P, hf[0], t0);
         setup(P, hf[1], t1);
@@ -405,6 +427,7 @@ struct TraceLane {
 
         if (n > 0) {
             const uint32_t G2 = (uint32_t)(P.g * SC) * 0x00010001u;
+            uint4* sbase = reinterpret_cast<uint4*>(P.scratch) + slot;
 #pragma unroll
             for (int r = 0; r < NR; r++) M[r] = 0;
             // byte address of the read code of shared step 0 for each task (may lie before the window: masked)
@@ -454,9 +477,22 @@ struct TraceLane {
                             T = addmax2(d, sv.y, mold);
                             hh = max3_2(T, u, G2);
                             u = hh - G2; M[2 * r2 + 1] = u; d = mold;
-                            // bytes: [H_lo(row 2r2), H_lo(row 2r2+1), H_hi(row 2r2), H_hi(row 2r2+1)]
-                            P.scratch[((int64_t)(s0 + j) * WORDS + r2) * P.scratch_stride + slot] =
-                                prmt(M[2 * r2], M[2 * r2 + 1], 0x7351u);
+                        }
+                        if (!(P.debug & 2)) {
+                            // H of row r: byte 1 (low task) and byte 3 (high task) of M[r]
+                            uint4* col = sbase + (int64_t)(s0 + j) * UNITS * P.scratch_stride;
+#pragma unroll
+                            for (int un = 0; un < UNITS; un++) {
+                                uint32_t pr[4];
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    const int ra = 7 * un + 2 * k, rb = ra + 1;
+                                    pr[k] = prmt(ra < NR ? M[ra < NR ? ra : 0] : 0u, rb < NR ? M[rb < NR ? rb : 0] : 0u, 0x7531u);
+                                }
+                                col[(int64_t)un * P.scratch_stride] =
+                                    make_uint4(prmt(pr[0], pr[1], 0x6420u), prmt(pr[2], pr[3], 0x6420u),
+                                               prmt(pr[0], pr[1], 0x7531u), prmt(pr[2], pr[3], 0x7531u));
+                            }
                         }
                     }
                 }
@@ -470,7 +506,11 @@ struct TraceLane {
         for (int h = 0; h < 2; h++) {
             po[h].clear();
             if (hf[h].t >= 0) { po[h].q_pos = hf[h].v.row; po[h].r_pos = hf[h].v.col; }
-            w[h].init(P, hf[h], h, slot);
+            w[h].init(P, hf[h], h, slot, qcodes);
+        }
+        if (P.debug & 3) {                                     // timing experiments only: no walk
+            if (P.debug & 2) { uint32_t x = 0; for (int r = 0; r < NR; r++) x ^= M[r]; if (x == 0x12345u) fb(t0); }
+            return;
         }
         while (w[0].active || w[1].active) {
             w[0].load(); w[1].load();
@@ -547,11 +587,12 @@ k_trace_fast(const TraceParams P) {
     U2* prof = reinterpret_cast<U2*>(smem_raw) + (size_t)warp * NIDX * Lane::PROF_STRIDE;
     // scratch is block-local: [block][window column][word][lane of the block], so a block's windows are one
     // contiguous region (a handful of pages) instead of rows strided across the whole launch
-    const int64_t slot = (int64_t)blockIdx.x * P.scratch_block_words + threadIdx.x;
+    const int64_t slot = (int64_t)blockIdx.x * P.scratch_block_words + threadIdx.x;      // in 16-byte units
     const long long ncand = (long long)*P.ncand;
     // segment of every sequence of the class in the sorted candidate list, found once per block
     long long* seg_lo = reinterpret_cast<long long*>(smem_raw + trace_prof_bytes<NR>());
     long long* seg_hi = seg_lo + 256;
+    uint8_t* qsm = reinterpret_cast<uint8_t*>(seg_hi + 256) + warp * QSTRIDE;          // the warp's query codes
     for (int i = threadIdx.x; i < P.n_class_seqs; i += blockDim.x) {
         const int q = P.class_seqs[i];
         seg_lo[i] = lower_bound_u16(P.cand_key, ncand, (uint32_t)q << 8);
@@ -572,6 +613,8 @@ k_trace_fast(const TraceParams P) {
             ScoreParams SP;
             SP.qcodes = P.qcodes; SP.s_match = SC * (P.match + P.g); SP.s_mis = SC * (P.mismatch + P.g);
             ScoreLane<NR>::build_profile(SP, q, P.qlen[q], reinterpret_cast<uint32_t*>(prof), lane, 32);
+            if (lane < QSTRIDE / 4)
+                reinterpret_cast<uint32_t*>(qsm)[lane] = reinterpret_cast<const uint32_t*>(P.qcodes + (size_t)q * QSTRIDE)[lane];
         }
         __syncwarp();
         for (;;) {
@@ -584,7 +627,7 @@ k_trace_fast(const TraceParams P) {
             if (active) {
                 const int t0 = (int)P.cand[lo + i];
                 const int t1 = (i + 1 < cnt) ? (int)P.cand[lo + i + 1] : -1;
-                L.run_pair(P, prof, t0, t1, slot, [&](int t) {
+                L.run_pair(P, prof, qsm, t0, t1, slot, [&](int t) {
                     const unsigned long long j = atomicAdd(P.nfallback, 1ull);
                     P.fallback[j] = (uint32_t)t;
                 });
@@ -595,7 +638,7 @@ k_trace_fast(const TraceParams P) {
 }
 
 template <int NR>
-inline size_t trace_smem_bytes() { return trace_prof_bytes<NR>() + 2 * 256 * sizeof(long long); }
+inline size_t trace_smem_bytes() { return trace_prof_bytes<NR>() + 2 * 256 * sizeof(long long) + (TRACE_THREADS / 32) * QSTRIDE; }
 
 template <int NR>
 __global__ void __launch_bounds__(TRACE_THREADS)

@@ -9,4 +9,4 @@ eng = _native.Engine(0)
 eng.set_scoring(2, -1, -1, -1); eng.set_queries([s for _, s in ps.sequences()])
 eng.upload_reads(concat, offs)
 h = eng.find_all(0.7, fetch=False)
-print("ok", n, h, eng.last_counters["tasks"], eng.last_counters["cells"], eng.last_counters["computed_cells"])
+print("ok", n, h, eng.last_counters)
