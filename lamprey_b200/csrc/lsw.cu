@@ -94,7 +94,7 @@ struct lsw_ctx {
     DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen, d_order, d_order_tmp, d_len_tmp[2];
 
     TaskBuf tb[2], child;
-    DevBuf d_fallback[NCLASS], d_nfallback, d_cand_key[NCLASS], d_cand_sorted[NCLASS], d_cand_key_sorted[NCLASS];
+    DevBuf d_fallback[NCLASS], d_nfallback, d_cand_key[NCLASS], d_cand_sorted[NCLASS], d_cand_key_sorted[NCLASS], d_cand_rec[NCLASS];
     DevBuf d_res, d_seg[2], d_head, d_cand[NCLASS], d_ncand, d_counters, d_child_flag, d_pos,
            d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_nhits, d_keys[2], d_vals[2], d_err,
            d_results, d_cigar, d_ncigar;
@@ -263,8 +263,12 @@ __global__ void k_merge_segments(ReuseParams R) {
         if (cand) {
             const int c = R.class_of[q];
             const unsigned long long i = append_slot_grouped(R.ncand + c);
-            R.cand[c][i] = (uint32_t)t;
+            CandRec cr;
+            cr.rd = R.t.read[t]; cr.a = R.t.a[t]; cr.len = R.t.b[t] - cr.a; cr.p0 = R.roff[cr.rd] + cr.a;
+            cr.res_x = score | (row << 16); cr.col = col; cr.t = (int32_t)t;
+            R.cand[c][i] = (uint32_t)i;
             R.cand_key[c][i] = (uint16_t)(((uint32_t)q << 8) | (uint32_t)cand_window(score, row, col, R.match, R.g));
+            R.cand_rec[c][i] = cr;
         }
     }
     // block-level reduction of the work counters
@@ -335,9 +339,11 @@ template <int NR, int NR2>
 int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     // short-window kernel over every candidate of the class: one lane per PAIR of candidates
     const size_t smem = trace_smem_bytes<NR>();
-    CK(cudaFuncSetAttribute(k_trace_fast<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // find_all never needs the op list of a path, align_tasks (CIGAR output) does
+    auto kernel = P.mode == 1 ? k_trace_fast<NR, true> : k_trace_fast<NR, false>;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_fast<NR>, TRACE_THREADS, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TRACE_THREADS, smem));
     if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
     if (getenv("LSW_K2_BLOCKS_PER_SM")) occ = std::max(1, std::min(occ, atoi(getenv("LSW_K2_BLOCKS_PER_SM"))));
     const int blocks = grid_for((n_class_tasks + 1) / 2, TRACE_THREADS, ctx->num_sms * occ);
@@ -358,7 +364,7 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     P.scratch = ctx->d_scratch.as<uint32_t>();
     P.scratch_stride = TRACE_THREADS;
     P.scratch_block_words = (int64_t)(Wf + 4) * UNITS * TRACE_THREADS;
-    k_trace_fast<NR><<<blocks, TRACE_THREADS, smem, ctx->stream>>>(P);
+    kernel<<<blocks, TRACE_THREADS, smem, ctx->stream>>>(P);
     CK(cudaGetLastError());
     P.scratch_stride = threads2;
     k_trace_full<NR2><<<blocks2, TRACE_THREADS, 0, ctx->stream>>>(P);
@@ -430,6 +436,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         if (ncls[c]) {
             CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4)); CK(ctx->d_fallback[c].ensure((size_t)ncls[c] * 4));
             CK(ctx->d_cand_sorted[c].ensure((size_t)ncls[c] * 4));
+            CK(ctx->d_cand_rec[c].ensure((size_t)ncls[c] * sizeof(CandRec)));
             CK(ctx->d_cand_key[c].ensure((size_t)ncls[c] * 2)); CK(ctx->d_cand_key_sorted[c].ensure((size_t)ncls[c] * 2));
             CK(cudaMemsetAsync(ctx->d_cand_key[c].p, 0xFF, (size_t)ncls[c] * 2, ctx->stream));
         }
@@ -482,6 +489,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             P.n_class_seqs = (int)ctx->class_seqs[c].size();
             P.cand = ctx->d_cand[c].as<uint32_t>();
             P.cand_key = ctx->d_cand_key[c].as<uint16_t>();
+            P.cand_rec = ctx->d_cand_rec[c].as<CandRec>();
             P.ncand = ctx->d_ncand.as<unsigned long long>() + c;
             int rc = launch_score_class(ctx, c, P, round_kind == 2 ? 2 * ncls[c] : ncls[c]);
             if (rc) return rc;
@@ -493,7 +501,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         R.res_s = ctx->d_res_s.as<int2>(); R.res_t = ctx->d_res.as<int2>();
         R.blockbest = ctx->d_blockbest.as<uint32_t>(); R.bb_off = ctx->d_bb_off.as<int64_t>(); R.bb_total = ctx->bb_total;
         R.cand_ok = ctx->d_cand_ok.as<uint8_t>(); R.class_of = ctx->d_class_of.as<int32_t>();
-        for (int c = 0; c < NCLASS; c++) { R.cand[c] = ctx->d_cand[c].as<uint32_t>(); R.cand_key[c] = ctx->d_cand_key[c].as<uint16_t>(); }
+        for (int c = 0; c < NCLASS; c++) { R.cand[c] = ctx->d_cand[c].as<uint32_t>(); R.cand_key[c] = ctx->d_cand_key[c].as<uint16_t>(); R.cand_rec[c] = ctx->d_cand_rec[c].as<CandRec>(); }
         R.ncand = ctx->d_ncand.as<unsigned long long>();
         R.counters = ctx->d_counters.as<unsigned long long>();
         k_merge_segments<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(R);
@@ -524,6 +532,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             T.res = ctx->d_res.as<int2>();
             T.cand = ctx->d_cand_sorted[c].as<uint32_t>();
             T.cand_key = ctx->d_cand_key_sorted[c].as<uint16_t>();
+            T.cand_rec = ctx->d_cand_rec[c].as<CandRec>();
             T.head = ctx->d_head.as<unsigned long long>();
             T.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
             T.n_class_seqs = (int)ctx->class_seqs[c].size();
@@ -601,7 +610,7 @@ void lsw_destroy(lsw_ctx* ctx) {
                       &ctx->d_keys[1], &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_err, &ctx->d_results,
                       &ctx->d_cigar, &ctx->d_ncigar};
     for (DevBuf* b : bufs) b->release();
-    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); }
+    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); ctx->d_cand_rec[c].release(); }
     ctx->d_nfallback.release();
     ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release(); ctx->segs.release();
     for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_seg_skip, &ctx->d_kt}) b->release();

@@ -120,6 +120,17 @@ struct TaskArrays {           // struct-of-arrays task list of one recursion rou
 
 // What K1 needs to start a task, in one aligned 16-byte load (built when the task list is built, so a lane
 // does not chase read -> offset -> codes through three dependent loads at every task switch).
+// What K2 needs to trace a candidate, in one 32-byte record written where the candidate is queued (K1's finish /
+// the merge kernel): K2 visits candidates in (sequence, window length) order, i.e. in random task order, and
+// would otherwise gather seven scattered fields per task.
+struct __align__(16) CandRec {
+    int64_t p0;               // offset of the slice start in the code array
+    int32_t len;              // slice length
+    int32_t rd, a;            // read index and slice start (hits and children are reported in read coordinates)
+    int32_t res_x, col;       // score | max_row << 16, max_col (slice relative)
+    int32_t t;                // task index (child slots, fallback list, caller's result slot)
+};
+
 struct __align__(16) KTask {
     int64_t p0;               // byte offset in codes of the slice's first base
     int32_t len;              // slice length
@@ -141,6 +152,7 @@ struct ScoreParams {
     const uint8_t*  cand_ok;  // [n_seq][128] 1 if a task with that score can still pass the hit test
     uint32_t*       cand;     // out: tasks that need a traceback
     uint16_t*       cand_key; // out: sequence << 8 | K2 window length (sort key; preset to 0xFFFF)
+    CandRec*        cand_rec; // out: the candidates themselves; cand[] holds indices into this array
     unsigned long long* ncand;
     unsigned long long* counters;   // [0] += reference tasks, [1] += reference cells, [2] += lane steps, [3] += computed cells
     int32_t s_match;          // SC * (match + |gap|)
@@ -165,6 +177,7 @@ struct TraceParams {
     const int32_t*  qlen;
     const uint32_t* cand;         // candidate task ids, sorted by (sequence, window length)
     const uint16_t* cand_key;     // their sort keys: sequence << 8 | window length (0xFFFF = padding)
+    const CandRec*  cand_rec;     // candidate records, indexed by cand[]
     const unsigned long long* ncand;
     unsigned long long* head;     // [n_seq] next unclaimed candidate of each sequence
     const int32_t*  class_seqs;   // sequences of this launch's register-row class

@@ -100,7 +100,7 @@ void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& c
     bool exhausted = false;
     for (;;) {
         for (int h = 0; h < 2; h++) {
-            if (L.tid[h] >= 0 && L.rem[h] == 0) L.finish(P, h, q, Q, [&](int t, int) { cand.push_back((uint32_t)t); });
+            if (L.tid[h] >= 0 && L.rem[h] == 0) L.finish(P, h, q, Q, [&](int t, int, int, int) { cand.push_back((uint32_t)t); });
             if (L.tid[h] < 0 && !exhausted) {
                 if (head < cnt) { const int t = (int)(base + head++); L.start(P, h, t, P.kt[t], Q); }
                 else exhausted = true;
@@ -132,6 +132,16 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
     std::vector<U2> prof((size_t)NIDX * Lane::PROF_STRIDE);
     ScoreLane<NR>::build_profile(P, q, E.qlen[q], reinterpret_cast<uint32_t*>(prof.data()), 0, 1);
     Lane L;
+    // the records K1's finish / the merge kernel write on the device
+    std::vector<CandRec> recs(cand.size());
+    for (size_t i = 0; i < cand.size(); i++) {
+        const int t = (int)cand[i];
+        CandRec& c = recs[i];
+        c.p0 = T.roff[T.t.read[t]] + T.t.a[t]; c.len = T.t.b[t] - T.t.a[t]; c.rd = T.t.read[t]; c.a = T.t.a[t];
+        c.res_x = T.res[t].x; c.col = T.res[t].y; c.t = t;
+    }
+    TraceParams TR = T;
+    TR.cand_rec = recs.data();
     for (size_t i = 0; i < cand.size(); i += 2) {
         const int t0 = (int)cand[i], t1 = i + 1 < cand.size() ? (int)cand[i + 1] : -1;
         E.counters[3] += t1 >= 0 ? 2 : 1;
@@ -140,7 +150,10 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
             trace_full_task<NR2>(T, t0, 0);
             if (t1 >= 0) trace_full_task<NR2>(T, t1, 0);
         } else {
-            L.run_pair(T, prof.data(), T.qcodes + (size_t)q * QSTRIDE, t0, t1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
+            if (T.mode == 1)
+                L.template run_pair<true>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
+            else
+                L.template run_pair<false>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
         }
     }
 }
@@ -298,6 +311,9 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
         round++;
     }
 #if defined(LSW_EMU_STATS)
+    fprintf(stderr, "[emu] mean window columns %.1f; columns touched beyond max_row (histogram -20..40):", (double)g_ncols_sum / (double)(g_walks ? g_walks : 1));
+    for (int i = 0; i < 61; i++) if (g_extra_hist[i]) fprintf(stderr, " %d:%llu", i - 20, g_extra_hist[i]);
+    fprintf(stderr, "\n");
     fprintf(stderr, "[emu] walks %llu iters %llu (%.1f per walk) fill steps %llu (%.1f per pair)\n", g_walks, g_walk_iters, (double)g_walk_iters / (double)(g_walks ? g_walks : 1), g_fill_steps, 2.0 * g_fill_steps / (double)(g_walks ? g_walks : 1));
 #endif
     if (errflag) return LSW_E_INTERNAL;

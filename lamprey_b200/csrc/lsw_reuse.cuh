@@ -68,6 +68,7 @@ struct ReuseParams {
     const int32_t* class_of;     // [n_seq] register-row class
     uint32_t* cand[16];          // per class: candidate list / sort key
     uint16_t* cand_key[16];
+    CandRec* cand_rec[16];
     unsigned long long* ncand;   // [classes]
     unsigned long long* counters;   // [0] += tasks, [1] += reference cells
 };

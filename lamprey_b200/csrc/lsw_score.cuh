@@ -126,7 +126,7 @@ struct ScoreLane {
             // sort key for K2: the number of window columns its traceback will fill (similar work per warp)
             int w = score > 0 ? row + (P.match * row - score) / P.g + 8 : 0;
             if (w > col) w = col;
-            push(t, w);
+            push(t, w, score | (row << 16), col);
         }
         tid[h] = -1;
     }
@@ -357,10 +357,15 @@ k_score(const ScoreParams P) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 if (L.tid[h] >= 0 && L.rem[h] == 0)
-                    L.finish(P, h, q, Q, [&](int t, int key) {
+                    L.finish(P, h, q, Q, [&](int t, int key, int res_x, int col) {
+                        const KTask k = P.kt[t];                       // plain task list: p0 = slice start, len = slice length
+                        CandRec c;
+                        c.p0 = k.p0; c.len = k.len; c.rd = P.t.read[t]; c.a = P.t.a[t];
+                        c.res_x = res_x; c.col = col; c.t = t;
                         const unsigned long long i = append_slot(P.ncand);
-                        P.cand[i] = (uint32_t)t;
+                        P.cand[i] = (uint32_t)i;
                         P.cand_key[i] = (uint16_t)(((uint32_t)q << 8) | (uint32_t)key);
+                        P.cand_rec[i] = c;
                     });
                 if (L.tid[h] < 0 && nxt[h] >= 0) { L.start(P, h, nxt[h], nk[h], Q); nxt[h] = -1; }
                 // a task is wanted now (idle half) or for the next boundary (this block is the current task's last)

@@ -60,15 +60,19 @@ LSW_HD int trace_window_fast_max(int Q, int match, int g) { return Q + (match * 
 enum { OPC_NONE = 0, OPC_M = 1, OPC_I = 2, OPC_D = 3, OPC_FAIL = -1 };
 constexpr int MAX_PATH_WORDS = 16;             // 2 bits per op; a path has < Q + M*Q/g <= 3*63 ops ... 256 ops of room
 
-struct PathOut {
+// OPS = false (find_all): only the counts and end points are needed, the op list is never stored
+template <bool OPS>
+struct PathOutT {
+    static constexpr int WORDS = OPS ? MAX_PATH_WORDS : 1;
     int q_pos, r_pos, m, x, nrun, nops;
-    uint32_t ops[MAX_PATH_WORDS];              // ops in walk order (alignment end first)
+    uint32_t ops[WORDS];                       // ops in walk order (alignment end first)
     LSW_HD void clear() {
         q_pos = r_pos = m = x = nrun = nops = 0;
 #pragma unroll
-        for (int i = 0; i < MAX_PATH_WORDS; i++) ops[i] = 0;
+        for (int i = 0; i < WORDS; i++) ops[i] = 0;
     }
     LSW_HD bool push(int op) {
+        if (!OPS) return true;
         if (nops >= MAX_PATH_WORDS * 16) return false;
         ops[nops >> 4] |= (uint32_t)op << (2 * (nops & 15));
         nops++;
@@ -76,15 +80,17 @@ struct PathOut {
     }
     LSW_HD int get(int i) const { return (int)((ops[i >> 4] >> (2 * (i & 15))) & 3u); }
 };
+using PathOut = PathOutT<true>;
 
 struct TaskView {
-    int rd, a, b, q, Q, score, row, col;
+    int t, rd, a, b, q, Q, score, row, col;
     const uint8_t* ref;      // ref[c - 1] is the read code of DP column c (slice relative)
     const uint8_t* qc;       // query codes
 };
 
 LSW_HD TaskView load_task(const TraceParams& P, int t) {
     TaskView v;
+    v.t = t;
     v.rd = P.t.read[t]; v.a = P.t.a[t]; v.b = P.t.b[t]; v.q = P.t.seq[t];
     const int2 rs = P.res[t];
     v.score = rs.x & 0xFFFF; v.row = rs.x >> 16; v.col = rs.y;
@@ -94,9 +100,24 @@ LSW_HD TaskView load_task(const TraceParams& P, int t) {
     return v;
 }
 
+// the same view from a candidate record (k_trace_fast): one 32-byte load, no dependent gathers
+LSW_HD TaskView load_cand(const TraceParams& P, int ci, int q) {
+    const int4* src = reinterpret_cast<const int4*>(P.cand_rec + ci);
+    const int4 lo = src[0], hi = src[1];
+    TaskView v;
+    const int64_t p0 = (int64_t)(((unsigned long long)(uint32_t)lo.y << 32) | (unsigned long long)(uint32_t)lo.x);
+    v.rd = lo.w; v.a = hi.x; v.b = hi.x + lo.z; v.q = q;
+    v.score = hi.y & 0xFFFF; v.row = hi.y >> 16; v.col = hi.z; v.t = hi.w;
+    v.Q = P.qlen[q];
+    v.ref = P.codes + p0;
+    v.qc = P.qcodes + (size_t)q * QSTRIDE;
+    return v;
+}
+
 // Results of one task -> caller-visible records (both kernels end here).
-LSW_HD void emit(const TraceParams& P, int t, const TaskView& v, const PathOut& po) {
-    if (P.mode == 1) {
+template <bool OPS>
+LSW_HD void emit(const TraceParams& P, int t, const TaskView& v, const PathOutT<OPS>& po) {
+    if (OPS && P.mode == 1) {
         lsw_result* out = reinterpret_cast<lsw_result*>(P.results) + P.t.orig[t];
         out->score = v.score;
         out->q_pos = po.q_pos; out->q_end = v.row;
@@ -248,6 +269,8 @@ LSW_HD void trace_full_task(const TraceParams& P, const int t, const int64_t slo
 //          cell at a time, loads about one new unit per iteration.
 #if defined(LSW_EMU_STATS)
 static unsigned long long g_walk_iters = 0, g_walks = 0, g_fill_steps = 0;
+static unsigned long long g_extra_hist[64] = {0}, g_ncols_sum = 0;   // columns a walk touched beyond max_row; window columns
+static int g_min_cl = 0;
 #endif
 
 template <int NR>
@@ -259,154 +282,149 @@ struct TraceLane {
 
     uint32_t M[NR];
 
+    // what the fill needs to know about one task of the pair
     struct Half {
-        TaskView v;
-        int t;                 // task index, -1 = none
-        int c0, ncols, first;  // zero-boundary column, window columns, first live step of the shared loop
+        int ncols, first;      // window columns, first live step of the shared loop (ncols == 0: nothing to fill)
+        int64_t code0;         // offset in the code array of the read code of shared step 0
     };
 
-    LSW_HD static void setup(const TraceParams& P, Half& hf, int t) {
-        hf.t = t; hf.c0 = 0; hf.ncols = 0; hf.first = 0;
-        if (t < 0) return;
-        hf.v = load_task(P, t);
-        if (hf.v.score > 0) {
-            const int W = trace_window_fast(hf.v.row, hf.v.score, P.match, P.g);
-            hf.c0 = hf.v.col > W ? hf.v.col - W : 0;
-            hf.ncols = hf.v.col - hf.c0;
+    // window of a candidate: zero-boundary column c0 and number of columns
+    LSW_HD static void window(const TraceParams& P, const TaskView& v, int& c0, int& ncols) {
+        c0 = 0; ncols = 0;
+        if (v.score > 0) {
+            const int W = trace_window_fast(v.row, v.score, P.match, P.g);
+            c0 = v.col > W ? v.col - W : 0;
+            ncols = v.col - c0;
         }
     }
 
-    // One traceback in progress.  load() issues the scratch / code loads of the current cell, decide()
-    // consumes them and moves on: run_pair() calls load() for BOTH tasks of the lane before either decide(),
-    // so the two dependent-load chains overlap.
     LSW_HD static int unit_of(int i) { return i > 0 ? ((i - 1) * 37) >> 8 : 0; }     // (i - 1) / 7 for i <= 63
     LSW_HD static int unit_byte(const uint2& v, int k) { return (int)(prmt(v.x, v.y, (uint32_t)k) & 0xFFu); }
 
+    // One traceback.  Kept small on purpose: the walk is a chain of dependent loads, it is the resident warps that
+    // hide them, and a walker that does not fit the register budget pays for every step in local-memory traffic.
+    template <bool OPS>
     struct Walker {
         // constants of the task
         const uint2* scr; uint32_t stride2, colbase;
         const uint8_t* qc; const uint32_t* ref4; int rlead;
-        int M_, X_, g, score, c0; bool keep_ops;
+        int score, c0;
         // state
         int r, cl, depth, ret, last, state, budget;
         uint32_t mv;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
         uint32_t st;                  // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
-        bool active, failed, first_cell;
+        bool failed, first_cell;
         // operands: the units of column cl (A) and cl - 1 (B) that hold rows r-1 and r-2, four read codes
-        uint2 A, B; int tagA, tagB;   // tag = 16 * column + unit, -1 = empty
+        uint2 A, B, C; int tagA, tagB, tagC;   // tag = 16 * column + unit, -1 = empty; C: lookahead unit
         uint32_t rw; int tagR;
-        int pc, qb, rb;               // byte of the cell in its unit, query / read code of the cell
 
-        LSW_HD void init(const TraceParams& P, const Half& hf, int h, int64_t slot, const uint8_t* qcodes) {
-            active = failed = false; first_cell = true;
-            r = cl = depth = last = state = 0; ret = OPC_NONE; mv = 0; st = 0; budget = 0;
-            A = B = make_uint2(0u, 0u); tagA = tagB = tagR = -1; rw = 0; pc = qb = rb = 0;
-            if (hf.t < 0 || hf.v.score <= 0) return;
+        // false: nothing to walk (or the start certificate fails: see `failed`)
+        LSW_HD bool init(const TraceParams& P, const TaskView& v, int c0_, int ncols, int first, int h, int64_t slot,
+                         const uint8_t* qcodes) {
+            failed = false; first_cell = true;
+            depth = last = state = 0; ret = OPC_NONE; mv = 0; st = 0;
+            A = B = C = make_uint2(0u, 0u); tagA = tagB = tagC = tagR = -1; rw = 0;
             scr = reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(P.scratch) + slot) + h;
             stride2 = 2u * (uint32_t)P.scratch_stride;            // uint2 elements between consecutive (column, unit) rows
-            colbase = (uint32_t)(hf.first - 1);
+            colbase = (uint32_t)(first - 1);
             qc = qcodes;
             // ref[c0 + cl - 1] is the read code of window column cl; read through aligned words (the code array is padded)
-            const uint8_t* refw = hf.v.ref + hf.c0 - 1;
+            const uint8_t* refw = v.ref + c0_ - 1;
             rlead = (int)(reinterpret_cast<uintptr_t>(refw) & 3u);
             ref4 = reinterpret_cast<const uint32_t*>(refw - rlead);
-            M_ = P.match; X_ = P.mismatch; g = P.g; score = hf.v.score; c0 = hf.c0;
-            keep_ops = (P.mode == 1);
-            r = hf.v.row; cl = hf.ncols;
-            budget = 6 * (hf.v.row + hf.ncols) + 64;
-            active = true;
-            if (hf.c0 > 0) {
+            score = v.score; c0 = c0_;
+            r = v.row; cl = ncols;
+            budget = 6 * (v.row + ncols) + 64;
+            if (c0_ > 0) {
                 // one certificate for the whole walk (see trace_slack): margin of the start cell
-                const int num = M_ * r - score - 1;
-                const int margin = cl - r - (num >= 0 ? num / g : -1);
-                if (margin < trace_slack(M_, g) - 1) { failed = true; active = false; }
+                const int num = P.match * r - score - 1;
+                const int margin = cl - r - (num >= 0 ? num / P.g : -1);
+                if (margin < trace_slack(P.match, P.g) - 1) { failed = true; return false; }
             }
+            return true;
         }
-        LSW_HD void load() {
-            if (!active) return;
-            if (r <= 0 || cl <= 0) return;                        // decide() ends the walk
-            const int i = r - 1, u = unit_of(i);
-            const int tA = 16 * cl + u, tB = cl > 1 ? tA - 16 : -1;
-            uint2 nA, nB = make_uint2(0u, 0u);
-            if (tagA == tA) nA = A; else if (tagB == tA) nA = B;
-            else nA = scr[((colbase + (uint32_t)cl) * UNITS + (uint32_t)u) * stride2];
-            if (tB >= 0) {
-                if (tagB == tB) nB = B; else if (tagA == tB) nB = A;
-                else nB = scr[((colbase + (uint32_t)cl - 1u) * UNITS + (uint32_t)u) * stride2];
-            }
-            A = nA; B = nB; tagA = tA; tagB = tB;
-            pc = i - 7 * u;
-            qb = qc[i];
-            const int off = cl + rlead;
-            if ((off >> 2) != tagR) { tagR = off >> 2; rw = ref4[tagR]; }
-            rb = (int)((rw >> (8 * (off & 3))) & 0xFFu);
-        }
-        LSW_HD void fail() { failed = true; active = false; }
-        LSW_HD void decide(PathOut& po) {
-            if (!active) return;
+        // One cell evaluation; false = the walk is over (path complete, or failed).  Written without data-dependent
+        // branches (selects only, except for the rare exits): the lanes of a warp are at different points of the
+        // state machine, and branches would make the warp run every arm one after the other.
+        LSW_HD bool step(const TraceParams& P, PathOutT<OPS>& po) {
 #if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
             g_walk_iters++;
 #endif
-            if (r <= 0 || cl <= 0) { active = false; return; }    // only at depth 0: the matrix boundary is zero
-            const int i = r - 1;
+            if (r <= 0 || cl <= 0) return false;                  // only at depth 0: the matrix boundary is zero
+#if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
+            if (cl - 1 < g_min_cl) g_min_cl = cl - 1;            // columns cl and cl - 1 are read
+#endif
+            const int i = r - 1, u = unit_of(i);
+            {   // operands: from the cached units, else from scratch
+                const int tA = 16 * cl + u, tB = cl > 1 ? tA - 16 : -2;
+                const bool hitA = (tagA == tA) | (tagB == tA) | (tagC == tA);
+                const bool hitB = (tagA == tB) | (tagB == tB) | (tagC == tB) | (tB < 0);
+                uint2 nA = tagA == tA ? A : (tagB == tA ? B : C);
+                uint2 nB = tagB == tB ? B : (tagA == tB ? A : C);
+                if (!hitA) nA = scr[((colbase + (uint32_t)cl) * UNITS + (uint32_t)u) * stride2];
+                if (!hitB) nB = scr[((colbase + (uint32_t)cl - 1u) * UNITS + (uint32_t)u) * stride2];
+                if (tB < 0) nB = make_uint2(0u, 0u);
+                A = nA; B = nB; tagA = tA; tagB = tB;
+                // lookahead: most steps are diagonal, and the diagonal successor (r-1, cl-1) takes its left-hand unit
+                // from column cl-2; that load is issued now and consumed an iteration later
+                const int u2 = unit_of(i > 0 ? i - 1 : 0);
+                const int tC = 16 * (cl - 2) + u2;
+                if (cl > 2 && tC != tagC) {
+                    C = scr[((colbase + (uint32_t)cl - 2u) * UNITS + (uint32_t)u2) * stride2];
+                    tagC = tC;
+                }
+            }
+            const int off = cl + rlead;
+            if ((off >> 2) != tagR) { tagR = off >> 2; rw = ref4[tagR]; }
+            const int rb = (int)((rw >> (8 * (off & 3))) & 0xFFu);
+            const int qb = qc[i];
+            const int pc = i - 7 * u;
+            const int g = P.g;
+
             const int hc = unit_byte(A, pc);
-            if (first_cell) { if (hc != score) { fail(); return; } first_cell = false; }   // window too short for the best cell
-            if (depth == 0 && state == 0 && hc == 0) { active = false; return; }           // path ends at the first zero cell
             const int hu = i > 0 ? unit_byte(A, pc - 1) : 0;
             const int hl = cl > 1 ? unit_byte(B, pc) : 0;
             const int hd = (i > 0 && cl > 1) ? unit_byte(B, pc - 1) : 0;
-            const int sub = (qb == rb) ? M_ : X_;
+            const int sub = (qb == rb) ? P.match : P.mismatch;
             const bool tieL = (hc == hl - g), tieU = (hc == hu - g), tieM = (hc == hd + sub);
-            // a cell next to the artificial left boundary cannot be decided (its left / diagonal value is unknown)
-            if (cl <= 1 && c0 > 0) { fail(); return; }
-            int res = -2;                 // -2: descend (push), otherwise the op of this cell
-            bool pushU = false;
-            if (state == 0) {
-                if (--budget < 0) { fail(); return; }
-                if (!tieL && !tieU && !tieM) { fail(); return; }   // cannot happen for an exact positive cell
-                if (tieL) {
-                    if (!tieU && !tieM) res = OPC_D;
-                    // else: need left's op (left value is hc + g > 0 and exact because of the tie)
-                } else if (tieU) {
-                    if (!tieM) res = OPC_I; else pushU = true;
-                } else res = OPC_M;
-            } else if (state == 1) {                                // left's op is in ret
-                if (ret == OPC_D) res = OPC_D;
-                else if (tieU) pushU = true;
-                else res = tieM ? OPC_M : OPC_D;
-            } else {                                                // up's op is in ret
-                if (ret == OPC_I) res = OPC_I;
-                else res = tieM ? OPC_M : (tieL ? OPC_D : OPC_I);
-            }
-            if (res == -2) {                                        // descend to a neighbour
-                if (depth + 1 >= MAXD) { fail(); return; }
-                st = (st << 2) | (pushU ? 2u : 1u);
-                mv = (mv << 1) | (pushU ? 1u : 0u);
-                depth++;
-                state = 0;
-                if (pushU) r -= 1; else cl -= 1;
-                return;
-            }
-            ret = res;
-            if (depth > 0) {                                        // return to the cell that asked
-                if (mv & 1u) r += 1; else cl += 1;
-                state = (int)(st & 3u);
-                mv >>= 1; st >>= 2;
-                depth--;
-                return;
-            }
-            // a path cell is resolved
-            po.nrun += (res != last) ? 1 : 0;
-            last = res;
-            if (keep_ops && !po.push(res)) { fail(); return; }
-            po.m += (res == OPC_M && sub == M_) ? 1 : 0;
-            po.x += (res == OPC_M && sub == M_) ? 0 : 1;
-            r -= (res != OPC_D) ? 1 : 0;
-            cl -= (res != OPC_I) ? 1 : 0;
-            state = 0;
+            const bool s0 = state == 0, s1 = state == 1;
+            if (depth == 0 && s0 && hc == 0 && !(first_cell && hc != score)) return false;   // path ends at the first zero cell
+            budget -= s0 ? 1 : 0;
+            const bool retD = ret == OPC_D, retI = ret == OPC_I;
+            const bool pushL = s0 & tieL & (tieU | tieM);          // need left's op (left value is hc + g > 0, exact because of the tie)
+            const bool pushU = (s0 & !tieL & tieU & tieM) | (s1 & !retD & tieU);
+            const bool push = pushL | pushU;
+            // rare exits: window too short for the best cell; a cell next to the artificial left boundary (its left /
+            // diagonal value is unknown); evaluation budget or nesting limit; no tie at all (cannot happen for an exact cell)
+            const bool bad = (first_cell & (hc != score)) | ((cl <= 1) & (c0 > 0)) | (budget < 0) |
+                             (s0 & !tieL & !tieU & !tieM) | (push & (depth + 1 >= MAXD));
+            if (bad) { failed = true; return false; }
+            first_cell = false;
+            const int res0 = tieL ? OPC_D : (tieU ? OPC_I : OPC_M);
+            const int res1 = retD ? OPC_D : (tieM ? OPC_M : OPC_D);
+            const int res2 = retI ? OPC_I : (tieM ? OPC_M : (tieL ? OPC_D : OPC_I));
+            const int res = s0 ? res0 : (s1 ? res1 : res2);
+            const bool isret = !push & (depth > 0);                  // return to the cell that asked
+            const bool isres = !push & (depth == 0);                 // a path cell is resolved
+            const int up1 = (int)(mv & 1u);
+            const int dr = push ? -(int)pushU : (isret ? up1 : -(int)(res != OPC_D));
+            const int dc = push ? -(int)pushL : (isret ? 1 - up1 : -(int)(res != OPC_I));
+            state = isret ? (int)(st & 3u) : 0;
+            st = push ? ((st << 2) | (pushU ? 2u : 1u)) : (isret ? st >> 2 : st);
+            mv = push ? ((mv << 1) | (pushU ? 1u : 0u)) : (isret ? mv >> 1 : mv);
+            depth += push ? 1 : (isret ? -1 : 0);
+            ret = push ? ret : res;
+            r += dr; cl += dc;
+            const bool ismatch = (res == OPC_M) & (sub == P.match);
+            po.nrun += (isres & (res != last)) ? 1 : 0;
+            po.m += (isres & ismatch) ? 1 : 0;
+            po.x += (isres & !ismatch) ? 1 : 0;
+            last = isres ? res : last;
+            if (OPS) { if (isres && !po.push(res)) { failed = true; return false; } }
+            return true;
         }
         // after the loop: false = the task must go to the fallback list
-        LSW_HD bool finish(PathOut& po) const {
+        LSW_HD bool finish(PathOutT<OPS>& po) const {
             if (failed || first_cell) return false;
             if (cl == 0 && c0 > 0 && r > 0) return false;            // ran into the artificial boundary
             po.q_pos = r;
@@ -415,12 +433,21 @@ struct TraceLane {
         }
     };
 
-    // fill + walk for the pair (t0, t1); t1 may be -1.  fb(t): push a task to the fallback list.
-    template <class Fallback>
-    LSW_HD void run_pair(const TraceParams& P, const U2* prof, const uint8_t* qcodes, int t0, int t1, int64_t slot, Fallback fb) {
+    // fill + walk for the pair of candidate records (ci0, ci1) of sequence q; ci1 may be -1.  fb(t): push a task to the fallback list.
+    template <bool OPS, class Fallback>
+    LSW_HD void run_pair(const TraceParams& P, const U2* prof, const uint8_t* qcodes, int q, int ci0, int ci1, int64_t slot, Fallback fb) {
         Half hf[2];
-        setup(P, hf[0], t0);
-        setup(P, hf[1], t1);
+        const int ci[2] = {ci0, ci1};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            hf[h].ncols = 0; hf[h].first = 0; hf[h].code0 = 0;
+            if (ci[h] >= 0) {
+                const TaskView v = load_cand(P, ci[h], q);
+                int c0;
+                window(P, v, c0, hf[h].ncols);
+                hf[h].code0 = (v.ref - P.codes) + c0;
+            }
+        }
         const int n = hf[0].ncols > hf[1].ncols ? hf[0].ncols : hf[1].ncols;
         hf[0].first = n - hf[0].ncols;
         hf[1].first = n - hf[1].ncols;
@@ -436,7 +463,7 @@ struct TraceLane {
             for (int h = 0; h < 2; h++) {
                 addr[h] = 0; lead[h] = 0; prev[h] = 0;
                 if (hf[h].ncols > 0) {
-                    const int64_t a0 = (hf[h].v.ref - P.codes) + hf[h].c0 - hf[h].first;
+                    const int64_t a0 = hf[h].code0 - hf[h].first;
                     lead[h] = (int)(a0 & 3);
                     addr[h] = a0 - lead[h];
                     prev[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h]);
@@ -498,33 +525,41 @@ struct TraceLane {
                 }
             }
         }
-
-        // both tracebacks of the lane, interleaved
-        PathOut po[2];
-        Walker w[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            po[h].clear();
-            if (hf[h].t >= 0) { po[h].q_pos = hf[h].v.row; po[h].r_pos = hf[h].v.col; }
-            w[h].init(P, hf[h], h, slot, qcodes);
-        }
         if (P.debug & 3) {                                     // timing experiments only: no walk
-            if (P.debug & 2) { uint32_t x = 0; for (int r = 0; r < NR; r++) x ^= M[r]; if (x == 0x12345u) fb(t0); }
+            if (P.debug & 2) { uint32_t x = 0; for (int r = 0; r < NR; r++) x ^= M[r]; if (x == 0x12345u) fb(0); }
             return;
         }
-        while (w[0].active || w[1].active) {
-            w[0].load(); w[1].load();
-            w[0].decide(po[0]); w[1].decide(po[1]);
-        }
-#pragma unroll
+
+        // the two tracebacks, one after the other; the record is read again (it is cache-hot) instead of being
+        // kept in registers across the fill
+#pragma unroll 1
         for (int h = 0; h < 2; h++) {
-            if (hf[h].t < 0) continue;
+            const int cidx = h ? ci1 : ci0;
+            if (cidx < 0) continue;
+            const TaskView v = load_cand(P, cidx, q);
+            PathOutT<OPS> po;
+            po.clear();
+            po.q_pos = v.row; po.r_pos = v.col;
+            bool ok = true;
+            if (v.score > 0) {
+                int c0, ncols;
+                window(P, v, c0, ncols);
+                Walker<OPS> w;
+#if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
+                g_min_cl = ncols; g_ncols_sum += ncols;
+#endif
+                if (w.init(P, v, c0, ncols, n - ncols, h, slot, qcodes))
+                    while (w.step(P, po)) { }
+#if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
+                { int e = (ncols - g_min_cl) - v.row; e = e < -20 ? -20 : (e > 40 ? 40 : e); g_extra_hist[e + 20]++; }
+#endif
+                ok = w.finish(po);
+            }
 #if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
             g_walks++; if (h == 0) g_fill_steps += n;
 #endif
-            const bool ok = hf[h].v.score > 0 ? w[h].finish(po[h]) : true;
-            if (ok) emit(P, hf[h].t, hf[h].v, po[h]);
-            else fb(hf[h].t);
+            if (ok) emit(P, v.t, v, po);
+            else fb(v.t);
         }
     }
 };
@@ -578,7 +613,7 @@ template <int NR> struct TraceOcc {
     static constexpr int value = NR <= 24 ? LSW_K2_OCC_SMALL : NR <= 32 ? (LSW_K2_OCC_SMALL > 5 ? 5 : LSW_K2_OCC_SMALL) : NR <= 48 ? 3 : 2;
 };
 
-template <int NR>
+template <int NR, bool OPS>
 __global__ void __launch_bounds__(TRACE_THREADS, TraceOcc<NR>::value)
 k_trace_fast(const TraceParams P) {
     using Lane = TraceLane<NR>;
@@ -625,9 +660,9 @@ k_trace_fast(const TraceParams P) {
             const bool active = i < cnt;
             if (!__any_sync(0xFFFFFFFFu, active)) break;
             if (active) {
-                const int t0 = (int)P.cand[lo + i];
-                const int t1 = (i + 1 < cnt) ? (int)P.cand[lo + i + 1] : -1;
-                L.run_pair(P, prof, qsm, t0, t1, slot, [&](int t) {
+                const int c0 = (int)P.cand[lo + i];
+                const int c1 = (i + 1 < cnt) ? (int)P.cand[lo + i + 1] : -1;
+                L.template run_pair<OPS>(P, prof, qsm, q, c0, c1, slot, [&](int t) {
                     const unsigned long long j = atomicAdd(P.nfallback, 1ull);
                     P.fallback[j] = (uint32_t)t;
                 });

@@ -9,7 +9,7 @@ import numpy as np
 from lamprey_b200._native import HIT_DT, RESULT_DT, TASK_DT, concat_sequences, _ptr
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PATH = os.path.join(ROOT, "lamprey_b200", "liblsw_emu.so")
+PATH = os.environ.get("LSW_EMU_LIB") or os.path.join(ROOT, "lamprey_b200", "liblsw_emu.so")
 _lib = None
 
 

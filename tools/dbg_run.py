@@ -1,3 +1,5 @@
+"""Per-round timing of one find_all (second call: buffers are allocated by the first).
+usage: LSW_LIB=... [LSW_K2_DEBUG=n] python tools/dbg_run.py <reads>"""
 import sys, os
 import numpy as np
 sys.path.insert(0, ".")
@@ -8,5 +10,9 @@ ps = seeding.PrimerSet("tests/golden/H3.3_set1.primers")
 eng = _native.Engine(0)
 eng.set_scoring(2, -1, -1, -1); eng.set_queries([s for _, s in ps.sequences()])
 eng.upload_reads(concat, offs)
+os.environ.pop("LSW_DEBUG", None)
+eng.find_all(0.7, fetch=False)
+os.environ["LSW_DEBUG"] = "1"
 h = eng.find_all(0.7, fetch=False)
-print("ok", n, h, eng.last_counters)
+c = eng.last_counters
+print("ok", n, h, {k: c[k] for k in ("tasks", "traced", "hits", "ms_score", "ms_trace", "ms_other", "ms_total", "fallbacks")})
