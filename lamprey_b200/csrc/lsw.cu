@@ -356,7 +356,7 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     const int blocks2 = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * std::min(occ2, 2));
     const int64_t threads2 = (int64_t)blocks2 * TRACE_THREADS;
     const int64_t W = trace_window_full(qmax, ctx->match, ctx->g);
-    constexpr int UNITS = TraceLane<NR>::UNITS;          // 16 bytes per (window column, unit, lane): both tasks of the lane
+    constexpr int UNITS = TraceLane<NR>::UPAIRS;         // 16 bytes per (window column, unit pair, lane): both tasks of the lane
     if ((size_t)threads2 * (size_t)W * (NR2 / 16) >= (1ull << 31))
         return fail(ctx, LSW_E_INTERNAL, "traceback scratch exceeds the 32-bit index range");
     const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * UNITS * 16, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
@@ -415,6 +415,7 @@ void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {
     T.qlen = ctx->d_qlen.as<int32_t>();
     T.match = ctx->match; T.mismatch = ctx->mismatch; T.g = ctx->g;
     T.errflag = ctx->d_err.as<int32_t>();
+    T.all_fallback = nibble_walk_ok(ctx->match, ctx->mismatch, ctx->g) ? 0 : 1;
     T.debug = getenv("LSW_K2_DEBUG") ? atoi(getenv("LSW_K2_DEBUG")) : 0;
 }
 

@@ -145,7 +145,7 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
     for (size_t i = 0; i < cand.size(); i += 2) {
         const int t0 = (int)cand[i], t1 = i + 1 < cand.size() ? (int)cand[i + 1] : -1;
         E.counters[3] += t1 >= 0 ? 2 : 1;
-        if (E.force_full) {
+        if (E.force_full || !nibble_walk_ok(T.match, T.mismatch, T.g)) {
             E.fallbacks += t1 >= 0 ? 2 : 1;
             trace_full_task<NR2>(T, t0, 0);
             if (t1 >= 0) trace_full_task<NR2>(T, t1, 0);

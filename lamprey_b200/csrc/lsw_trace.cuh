@@ -55,6 +55,11 @@ LSW_HD int trace_slack(int match, int g) { return (match + g) / g + 5; }
 LSW_HD int trace_window_fast(int max_row, int score, int match, int g) {
     return max_row + (match * max_row - score) / g + trace_slack(match, g);
 }
+// The short-window kernel stores H modulo 16.  For exact cells H(r,c) - H(r,c-1) <= M + g, H(r,c) - H(r-1,c) <= M + g and
+// H(r,c) - H(r-1,c-1) <= M (drop the last column / row of the best alignment ending in (r,c)), so the three candidates
+// hl - g, hu - g, hd + s lie in [H - (M + 2g), H] and [H - (M + |X|), H]: modulo 16 decides equality with H exactly when both
+// spans stay below 16.  Other scorings take the full-window kernel for every candidate.
+LSW_HD bool nibble_walk_ok(int match, int mismatch, int g) { return match + 2 * g <= 15 && match - mismatch <= 15; }
 LSW_HD int trace_window_fast_max(int Q, int match, int g) { return Q + (match * Q) / g + trace_slack(match, g); }
 
 enum { OPC_NONE = 0, OPC_M = 1, OPC_I = 2, OPC_D = 3, OPC_FAIL = -1 };
@@ -260,13 +265,16 @@ LSW_HD void trace_full_task(const TraceParams& P, const int t, const int64_t slo
 // all lanes of a warp serve one sequence whose profile sits in shared memory.  Per pair:
 //   fill   n = max(window lengths) columns of VALUES with the K1 recurrence (2 DPX + 1 add per two
 //          cells, no arg-max key), both windows right-aligned on their own max_col; after every
-//          column the H bytes of both tasks go to scratch in 8-byte UNITS of eight consecutive rows,
-//          unit u = rows 7u .. 7u+7 (neighbouring units share a row, so a cell and the cell above it
-//          are always in one unit); one 16-byte store per unit carries both tasks;
+//          column the low NIBBLE of every H of both tasks goes to scratch (the traffic to and from the
+//          scratch bounds this kernel) in 32-bit UNITS of eight consecutive rows, unit u = rows 7u .. 7u+7
+//          (neighbouring units share a row, so a cell and the cell above it are always in one unit);
+//          one 16-byte store carries two units of both tasks;
 //   walk   each task: a flat state machine, one cell evaluation per iteration, that applies the op
-//          rule lazily and proves every decision (see the file header).  A cell needs the unit of its
-//          own column and of the column to the left: the walker keeps both and, because it moves one
-//          cell at a time, loads about one new unit per iteration.
+//          rule lazily and proves every decision (see the file header).  The walker knows the VALUE of
+//          the cell it stands on (the score at the start; every move changes it by a known amount), and
+//          neighbouring values differ from it by less than 16 (see nibble_walk_ok), so the nibbles decide
+//          every tie exactly.  A cell needs the unit of its own column and of the column to the left: the
+//          walker keeps both and, because it moves one cell at a time, loads about one new unit per step.
 #if defined(LSW_EMU_STATS)
 static unsigned long long g_walk_iters = 0, g_walks = 0, g_fill_steps = 0;
 static unsigned long long g_extra_hist[64] = {0}, g_ncols_sum = 0;   // columns a walk touched beyond max_row; window columns
@@ -277,7 +285,8 @@ template <int NR>
 struct TraceLane {
     static_assert(NR % 4 == 0 && NR <= 64, "rows in registers");
     static constexpr int PROF_STRIDE = NR / 2 + 1;
-    static constexpr int UNITS = (NR + 5) / 7;    // 8-byte units per window column and task: ceil((NR - 1) / 7)
+    static constexpr int UNITS = (NR + 5) / 7;    // 32-bit units per window column and task: ceil((NR - 1) / 7)
+    static constexpr int UPAIRS = (UNITS + 1) / 2; // 16-byte scratch elements per window column and lane
     static constexpr int MAXD = 15;               // nesting limit of run-flag evaluations (2 state bits each)
 
     uint32_t M[NR];
@@ -299,23 +308,23 @@ struct TraceLane {
     }
 
     LSW_HD static int unit_of(int i) { return i > 0 ? ((i - 1) * 37) >> 8 : 0; }     // (i - 1) / 7 for i <= 63
-    LSW_HD static int unit_byte(const uint2& v, int k) { return (int)(prmt(v.x, v.y, (uint32_t)k) & 0xFFu); }
+    LSW_HD static int nib(uint32_t v, int k) { return (int)((v >> (4 * k)) & 15u); }
 
     // One traceback.  Kept small on purpose: the walk is a chain of dependent loads, it is the resident warps that
     // hide them, and a walker that does not fit the register budget pays for every step in local-memory traffic.
     template <bool OPS>
     struct Walker {
         // constants of the task
-        const uint2* scr; uint32_t stride2, colbase;
+        const uint32_t* scr; uint32_t stride4, colbase;
         const uint8_t* qc; const uint32_t* ref4; int rlead;
         int score, c0;
         // state
-        int r, cl, depth, ret, last, state, budget;
+        int r, cl, hv, depth, ret, last, state, budget;   // hv: H of the cell (r, cl)
         uint32_t mv;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
         uint32_t st;                  // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
         bool failed, first_cell;
         // operands: the units of column cl (A) and cl - 1 (B) that hold rows r-1 and r-2, four read codes
-        uint2 A, B, C; int tagA, tagB, tagC;   // tag = 16 * column + unit, -1 = empty; C: lookahead unit
+        uint32_t A, B, C; int tagA, tagB, tagC;   // tag = 16 * column + unit, -1 = empty; C: lookahead unit
         uint32_t rw; int tagR;
 
         // false: nothing to walk (or the start certificate fails: see `failed`)
@@ -323,9 +332,9 @@ struct TraceLane {
                          const uint8_t* qcodes) {
             failed = false; first_cell = true;
             depth = last = state = 0; ret = OPC_NONE; mv = 0; st = 0;
-            A = B = C = make_uint2(0u, 0u); tagA = tagB = tagC = tagR = -1; rw = 0;
-            scr = reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(P.scratch) + slot) + h;
-            stride2 = 2u * (uint32_t)P.scratch_stride;            // uint2 elements between consecutive (column, unit) rows
+            A = B = C = 0u; tagA = tagB = tagC = tagR = -1; rw = 0;
+            scr = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint4*>(P.scratch) + slot) + h;
+            stride4 = 4u * (uint32_t)P.scratch_stride;            // words between consecutive (column, unit pair) rows
             colbase = (uint32_t)(first - 1);
             qc = qcodes;
             // ref[c0 + cl - 1] is the read code of window column cl; read through aligned words (the code array is padded)
@@ -333,7 +342,7 @@ struct TraceLane {
             rlead = (int)(reinterpret_cast<uintptr_t>(refw) & 3u);
             ref4 = reinterpret_cast<const uint32_t*>(refw - rlead);
             score = v.score; c0 = c0_;
-            r = v.row; cl = ncols;
+            r = v.row; cl = ncols; hv = v.score;
             budget = 6 * (v.row + ncols) + 64;
             if (c0_ > 0) {
                 // one certificate for the whole walk (see trace_slack): margin of the start cell
@@ -359,18 +368,18 @@ struct TraceLane {
                 const int tA = 16 * cl + u, tB = cl > 1 ? tA - 16 : -2;
                 const bool hitA = (tagA == tA) | (tagB == tA) | (tagC == tA);
                 const bool hitB = (tagA == tB) | (tagB == tB) | (tagC == tB) | (tB < 0);
-                uint2 nA = tagA == tA ? A : (tagB == tA ? B : C);
-                uint2 nB = tagB == tB ? B : (tagA == tB ? A : C);
-                if (!hitA) nA = scr[((colbase + (uint32_t)cl) * UNITS + (uint32_t)u) * stride2];
-                if (!hitB) nB = scr[((colbase + (uint32_t)cl - 1u) * UNITS + (uint32_t)u) * stride2];
-                if (tB < 0) nB = make_uint2(0u, 0u);
+                uint32_t nA = tagA == tA ? A : (tagB == tA ? B : C);
+                uint32_t nB = tagB == tB ? B : (tagA == tB ? A : C);
+                const uint32_t wu = 2u * ((uint32_t)u & 1u), pu = (uint32_t)u >> 1;
+                if (!hitA) nA = scr[((colbase + (uint32_t)cl) * UPAIRS + pu) * stride4 + wu];
+                if (!hitB) nB = scr[((colbase + (uint32_t)cl - 1u) * UPAIRS + pu) * stride4 + wu];
                 A = nA; B = nB; tagA = tA; tagB = tB;
                 // lookahead: most steps are diagonal, and the diagonal successor (r-1, cl-1) takes its left-hand unit
                 // from column cl-2; that load is issued now and consumed an iteration later
                 const int u2 = unit_of(i > 0 ? i - 1 : 0);
                 const int tC = 16 * (cl - 2) + u2;
                 if (cl > 2 && tC != tagC) {
-                    C = scr[((colbase + (uint32_t)cl - 2u) * UNITS + (uint32_t)u2) * stride2];
+                    C = scr[((colbase + (uint32_t)cl - 2u) * UPAIRS + ((uint32_t)u2 >> 1)) * stride4 + 2u * ((uint32_t)u2 & 1u)];
                     tagC = tC;
                 }
             }
@@ -380,23 +389,25 @@ struct TraceLane {
             const int qb = qc[i];
             const int pc = i - 7 * u;
             const int g = P.g;
-
-            const int hc = unit_byte(A, pc);
-            const int hu = i > 0 ? unit_byte(A, pc - 1) : 0;
-            const int hl = cl > 1 ? unit_byte(B, pc) : 0;
-            const int hd = (i > 0 && cl > 1) ? unit_byte(B, pc - 1) : 0;
+            // ties from the nibbles: a candidate (hl - g, hu - g, hd + sub) never exceeds hv and is less than 16 below it.
+            // Cells on the matrix boundary are handled with their true value 0.
+            const bool inner = (i > 0) & (cl > 1);
             const int sub = (qb == rb) ? P.match : P.mismatch;
-            const bool tieL = (hc == hl - g), tieU = (hc == hu - g), tieM = (hc == hd + sub);
+            const bool tieL = (cl > 1) & (((nib(B, pc) - g - hv) & 15) == 0);
+            const int pu1 = pc > 0 ? pc - 1 : 0;                     // byte of the row above (i > 0 implies pc >= 1)
+            const bool tieU = (i > 0) & (((nib(A, pu1) - g - hv) & 15) == 0);
+            const bool tieM = inner ? (((nib(B, pu1) + sub - hv) & 15) == 0) : (hv == sub);
             const bool s0 = state == 0, s1 = state == 1;
-            if (depth == 0 && s0 && hc == 0 && !(first_cell && hc != score)) return false;   // path ends at the first zero cell
+            if (depth == 0 && s0 && hv == 0) return false;           // path ends at the first zero cell
             budget -= s0 ? 1 : 0;
             const bool retD = ret == OPC_D, retI = ret == OPC_I;
-            const bool pushL = s0 & tieL & (tieU | tieM);          // need left's op (left value is hc + g > 0, exact because of the tie)
+            const bool pushL = s0 & tieL & (tieU | tieM);          // need left's op (left value is hv + g > 0, exact because of the tie)
             const bool pushU = (s0 & !tieL & tieU & tieM) | (s1 & !retD & tieU);
             const bool push = pushL | pushU;
-            // rare exits: window too short for the best cell; a cell next to the artificial left boundary (its left /
-            // diagonal value is unknown); evaluation budget or nesting limit; no tie at all (cannot happen for an exact cell)
-            const bool bad = (first_cell & (hc != score)) | ((cl <= 1) & (c0 > 0)) | (budget < 0) |
+            // rare exits: the stored nibble disagrees with the tracked value (e.g. window too short for the best cell);
+            // a cell next to the artificial left boundary (its left / diagonal value is unknown); evaluation budget or
+            // nesting limit; no tie at all (cannot happen for an exact cell)
+            const bool bad = (((nib(A, pc) - hv) & 15) != 0) | ((cl <= 1) & (c0 > 0)) | (budget < 0) |
                              (s0 & !tieL & !tieU & !tieM) | (push & (depth + 1 >= MAXD));
             if (bad) { failed = true; return false; }
             first_cell = false;
@@ -415,6 +426,7 @@ struct TraceLane {
             depth += push ? 1 : (isret ? -1 : 0);
             ret = push ? ret : res;
             r += dr; cl += dc;
+            hv += push ? g : (isret ? -g : (res == OPC_M ? -sub : g));
             const bool ismatch = (res == OPC_M) & (sub == P.match);
             po.nrun += (isres & (res != last)) ? 1 : 0;
             po.m += (isres & ismatch) ? 1 : 0;
@@ -506,20 +518,27 @@ struct TraceLane {
                             u = hh - G2; M[2 * r2 + 1] = u; d = mold;
                         }
                         if (!(P.debug & 2)) {
-                            // H of row r: byte 1 (low task) and byte 3 (high task) of M[r]
-                            uint4* col = sbase + (int64_t)(s0 + j) * UNITS * P.scratch_stride;
+                            // H of row r: byte 1 (low task) and byte 3 (high task) of M[r]; their low nibbles are kept
+                            uint4* col = sbase + (int64_t)(s0 + j) * UPAIRS * P.scratch_stride;
+                            uint32_t lo[2 * UPAIRS], hi[2 * UPAIRS];
 #pragma unroll
-                            for (int un = 0; un < UNITS; un++) {
+                            for (int un = 0; un < 2 * UPAIRS; un++) {
                                 uint32_t pr[4];
 #pragma unroll
                                 for (int k = 0; k < 4; k++) {
+                                    // bytes 1 and 3 of pr[k]: nibbles of rows (ra, ra + 1) of the low / high task
                                     const int ra = 7 * un + 2 * k, rb = ra + 1;
-                                    pr[k] = prmt(ra < NR ? M[ra < NR ? ra : 0] : 0u, rb < NR ? M[rb < NR ? rb : 0] : 0u, 0x7531u);
+                                    const uint32_t va = (un < UNITS && ra < NR) ? M[ra < NR ? ra : 0] : 0u;
+                                    const uint32_t vb = (un < UNITS && rb < NR) ? M[rb < NR ? rb : 0] : 0u;
+                                    pr[k] = (va & 0x0F000F00u) | ((vb << 4) & 0xF000F000u);
                                 }
-                                col[(int64_t)un * P.scratch_stride] =
-                                    make_uint4(prmt(pr[0], pr[1], 0x6420u), prmt(pr[2], pr[3], 0x6420u),
-                                               prmt(pr[0], pr[1], 0x7531u), prmt(pr[2], pr[3], 0x7531u));
+                                const uint32_t p01 = prmt(pr[0], pr[1], 0x7531u), p23 = prmt(pr[2], pr[3], 0x7531u);
+                                lo[un] = prmt(p01, p23, 0x6420u);
+                                hi[un] = prmt(p01, p23, 0x7531u);
                             }
+#pragma unroll
+                            for (int up = 0; up < UPAIRS; up++)
+                                col[(int64_t)up * P.scratch_stride] = make_uint4(lo[2 * up], hi[2 * up], lo[2 * up + 1], hi[2 * up + 1]);
                         }
                     }
                 }
@@ -659,7 +678,12 @@ k_trace_fast(const TraceParams P) {
             const long long i = (long long)__shfl_sync(0xFFFFFFFFu, first, 0) + 2 * lane;
             const bool active = i < cnt;
             if (!__any_sync(0xFFFFFFFFu, active)) break;
-            if (active) {
+            if (active && P.all_fallback) {                       // scoring outside the nibble walk's range
+                for (int k = 0; k < 2 && i + k < cnt; k++) {
+                    const unsigned long long j = atomicAdd(P.nfallback, 1ull);
+                    P.fallback[j] = (uint32_t)P.cand_rec[P.cand[lo + i + k]].t;
+                }
+            } else if (active) {
                 const int c0 = (int)P.cand[lo + i];
                 const int c1 = (i + 1 < cnt) ? (int)P.cand[lo + i + 1] : -1;
                 L.template run_pair<OPS>(P, prof, qsm, q, c0, c1, slot, [&](int t) {

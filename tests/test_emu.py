@@ -186,3 +186,29 @@ def test_emu_find_all_random_schemas_and_block_edges(seed):
         assert np.array_equal(hits_matrix(hits), want), (seed, reuse)
         assert (cnt["tasks"], cnt["cells"]) == (calls, cells)
     assert len(want) > 50
+
+
+@pytest.mark.parametrize("scoring", [(7, -5, -5), (5, -12, -2)])
+def test_emu_scoring_outside_the_short_window_range(scoring):
+    # neighbouring cells may differ by 16 or more: the short-window kernel (H modulo 16) hands every candidate to the
+    # full-window kernel
+    rng = random.Random(sum(scoring) + 5)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(n)) for n in (8, 12, 15, 17)]
+    reads = []
+    for i in range(40):
+        n = rng.randrange(1, 300)
+        r = [rng.choice("ACGT") for _ in range(n)]
+        for _ in range(3):
+            s = seqs[rng.randrange(len(seqs))]
+            if n > len(s) + 2:
+                p = rng.randrange(0, n - len(s))
+                for k, ch in enumerate(s):
+                    if rng.random() > 0.1:
+                        r[p + k] = ch
+        reads.append("".join(r))
+    tasks = np.array([(i, 0, len(r), q) for i, r in enumerate(reads) for q in range(len(seqs))], dtype=TASK_DT)
+    _check_tasks(reads, seqs, tasks, scoring)
+    want, calls, cells = _oracle_rows(reads, seqs, 0.7, scoring)
+    hits, cnt = emu_lib.find_all(reads, seqs, 0.7, *scoring)
+    assert np.array_equal(hits_matrix(hits), want)
+    assert (cnt["tasks"], cnt["cells"]) == (calls, cells) and cnt["fallbacks"] == cnt["traced"] > 0

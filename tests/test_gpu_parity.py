@@ -353,3 +353,38 @@ def test_error_behaviour_of_the_engine(engine):
     with pytest.raises(ValueError):
         engine.find_all(0.0)                            # the reference would recurse forever
     engine.set_scoring(2, -1, -1, -1)
+
+
+@pytest.mark.parametrize("scoring", [(7, -5, -5), (5, -12, -2)])
+def test_scoring_outside_the_short_window_range(engine, scoring):
+    # neighbouring cells may differ by 16 or more: the short-window kernel (H modulo 16) hands every candidate to the
+    # full-window kernel
+    rng = random.Random(sum(scoring) + 5)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(n)) for n in (8, 12, 15, 17)]
+    reads = []
+    for i in range(40):
+        n = rng.randrange(1, 300)
+        r = [rng.choice("ACGT") for _ in range(n)]
+        for _ in range(3):
+            s = seqs[rng.randrange(len(seqs))]
+            if n > len(s) + 2:
+                p = rng.randrange(0, n - len(s))
+                for k, ch in enumerate(s):
+                    if rng.random() > 0.1:
+                        r[p + k] = ch
+        reads.append("".join(r))
+    tasks = np.array([(i, 0, len(r), q) for i, r in enumerate(reads) for q in range(len(seqs))], dtype=TASK_DT)
+    _check_tasks(engine, reads, seqs, tasks, scoring)
+    rows = []
+    for i, r in enumerate(reads):
+        h, _ = c_oracle.find_all(r, seqs, 0.7, scoring[0], scoring[1], scoring[2], scoring[2])
+        h = h[np.argsort(h["start"], kind="stable")]
+        rows += [(i, x["seq"], x["start"], x["end"], x["matches"], x["mismatches"], x["score"], x["q_pos"], x["q_end"],
+                  x["depth"]) for x in h]
+    engine.set_scoring(scoring[0], scoring[1], scoring[2], scoring[2])
+    engine.set_queries(seqs)
+    engine.upload_read_list(reads)
+    hits = engine.find_all(0.7)
+    assert np.array_equal(hits_matrix(hits), np.array(rows, np.int32).reshape(-1, 10))
+    assert engine.last_counters["fallbacks"] == engine.last_counters["traced"] > 0
+    engine.set_scoring(2, -1, -1, -1)
