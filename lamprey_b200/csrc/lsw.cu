@@ -357,7 +357,7 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     const int64_t threads2 = (int64_t)blocks2 * TRACE_THREADS;
     const int64_t W = trace_window_full(qmax, ctx->match, ctx->g);
     constexpr int UNITS = TraceLane<NR>::UPAIRS;         // 16 bytes per (window column, unit pair, lane): both tasks of the lane
-    if ((size_t)threads2 * (size_t)W * (NR2 / 16) >= (1ull << 31))
+    if ((size_t)threads2 * (size_t)W * (NR2 / 16) >= (1ull << 31) || (size_t)threads * (size_t)(Wf + 4) * UNITS * 4 >= (1ull << 31))
         return fail(ctx, LSW_E_INTERNAL, "traceback scratch exceeds the 32-bit index range");
     const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * UNITS * 16, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
     CK(ctx->d_scratch.ensure(need));

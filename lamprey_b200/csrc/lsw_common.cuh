@@ -204,7 +204,7 @@ struct TraceParams {
     unsigned long long* ncigar;
     int32_t* errflag;
     int32_t all_fallback;     // 1: the scoring is outside the short-window kernel's range (nibble_walk_ok), every candidate takes the full window
-    int32_t debug;            // timing experiments only (LSW_K2_DEBUG): 1 = fill only, 2 = fill without the scratch stores
+    int32_t debug;            // timing experiments only (LSW_K2_DEBUG): 1 = fill only, 2 = fill without the scratch stores, 4 = no output
 };
 
 }  // namespace lsw

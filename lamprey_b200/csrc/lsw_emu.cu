@@ -194,8 +194,8 @@ void emu_round(Emu& E, TraceParams T) {
     P.push_cands = 1; P.count_ref = 1; P.block_steps = BLOCK_STEPS;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);
-    // one lane: fast layout = 16 B per (column, unit), at most 9 units; full layout = 4 words per column
-    std::vector<uint4> scratch((size_t)std::max(trace_window_full(qmax, E.match, E.g), (trace_window_fast_max(qmax, E.match, E.g) + 4) * 9) + 4);
+    // one lane (slot 0): fast layout = rows of TRACE_THREADS x 16 B per (column, unit pair), at most 5 pairs; full layout = 4 words per column
+    std::vector<uint4> scratch((size_t)std::max(trace_window_full(qmax, E.match, E.g), (trace_window_fast_max(qmax, E.match, E.g) + 4) * 5 * TRACE_THREADS) + 4);
     T.codes = E.codes.data(); T.roff = E.roff.data(); T.t = view(E); T.res = E.res.data();
     T.qcodes = E.qcodes.data(); T.qlen = E.qlen.data();
     T.match = E.match; T.mismatch = E.mismatch; T.g = E.g;

@@ -39,6 +39,8 @@
 
 namespace lsw {
 
+constexpr int TRACE_THREADS = 128;       // block size of both kernels; also the lane stride of the fast kernel's scratch rows
+
 LSW_HD int trace_window_full(int Q, int match, int g) {
     const int dmax = (match * Q) / g;          // >= number of 'D' moves on any positive-prefix path
     const int span = Q + dmax;
@@ -315,7 +317,7 @@ struct TraceLane {
     template <bool OPS>
     struct Walker {
         // constants of the task
-        const uint32_t* scr; uint32_t stride4, colbase;
+        const uint32_t* scr0; uint32_t base, colbase;   // scratch array, word index of the lane's first word in it
         const uint8_t* qc; const uint32_t* ref4; int rlead;
         int score, c0;
         // state
@@ -333,8 +335,8 @@ struct TraceLane {
             failed = false; first_cell = true;
             depth = last = state = 0; ret = OPC_NONE; mv = 0; st = 0;
             A = B = C = 0u; tagA = tagB = tagC = tagR = -1; rw = 0;
-            scr = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint4*>(P.scratch) + slot) + h;
-            stride4 = 4u * (uint32_t)P.scratch_stride;            // words between consecutive (column, unit pair) rows
+            scr0 = P.scratch;                                     // 32-bit index arithmetic: the host keeps the scratch under 2^31 words
+            base = 4u * (uint32_t)slot + (uint32_t)h;
             colbase = (uint32_t)(first - 1);
             qc = qcodes;
             // ref[c0 + cl - 1] is the read code of window column cl; read through aligned words (the code array is padded)
@@ -370,16 +372,19 @@ struct TraceLane {
                 const bool hitB = (tagA == tB) | (tagB == tB) | (tagC == tB) | (tB < 0);
                 uint32_t nA = tagA == tA ? A : (tagB == tA ? B : C);
                 uint32_t nB = tagB == tB ? B : (tagA == tB ? A : C);
-                const uint32_t wu = 2u * ((uint32_t)u & 1u), pu = (uint32_t)u >> 1;
-                if (!hitA) nA = scr[((colbase + (uint32_t)cl) * UPAIRS + pu) * stride4 + wu];
-                if (!hitB) nB = scr[((colbase + (uint32_t)cl - 1u) * UPAIRS + pu) * stride4 + wu];
+                // word (column c, unit v) of this lane: base + (c * UPAIRS + v / 2) * COLW + 2 * (v % 2); the fast kernel's
+                // scratch rows are TRACE_THREADS lanes of 16 bytes
+                constexpr uint32_t COLW = 4u * 128u;
+                const uint32_t wA = base + ((colbase + (uint32_t)cl) * UPAIRS + ((uint32_t)u >> 1)) * COLW + 2u * ((uint32_t)u & 1u);
+                if (!hitA) nA = scr0[wA];
+                if (!hitB) nB = scr0[wA - UPAIRS * COLW];
                 A = nA; B = nB; tagA = tA; tagB = tB;
                 // lookahead: most steps are diagonal, and the diagonal successor (r-1, cl-1) takes its left-hand unit
                 // from column cl-2; that load is issued now and consumed an iteration later
                 const int u2 = unit_of(i > 0 ? i - 1 : 0);
                 const int tC = 16 * (cl - 2) + u2;
                 if (cl > 2 && tC != tagC) {
-                    C = scr[((colbase + (uint32_t)cl - 2u) * UPAIRS + ((uint32_t)u2 >> 1)) * stride4 + 2u * ((uint32_t)u2 & 1u)];
+                    C = scr0[base + ((colbase + (uint32_t)cl - 2u) * UPAIRS + ((uint32_t)u2 >> 1)) * COLW + 2u * ((uint32_t)u2 & 1u)];
                     tagC = tC;
                 }
             }
@@ -519,7 +524,7 @@ struct TraceLane {
                         }
                         if (!(P.debug & 2)) {
                             // H of row r: byte 1 (low task) and byte 3 (high task) of M[r]; their low nibbles are kept
-                            uint4* col = sbase + (int64_t)(s0 + j) * UPAIRS * P.scratch_stride;
+                            uint4* col = sbase + (int64_t)(s0 + j) * UPAIRS * TRACE_THREADS;
                             uint32_t lo[2 * UPAIRS], hi[2 * UPAIRS];
 #pragma unroll
                             for (int un = 0; un < 2 * UPAIRS; un++) {
@@ -538,7 +543,7 @@ struct TraceLane {
                             }
 #pragma unroll
                             for (int up = 0; up < UPAIRS; up++)
-                                col[(int64_t)up * P.scratch_stride] = make_uint4(lo[2 * up], hi[2 * up], lo[2 * up + 1], hi[2 * up + 1]);
+                                col[up * TRACE_THREADS] = make_uint4(lo[2 * up], hi[2 * up], lo[2 * up + 1], hi[2 * up + 1]);
                         }
                     }
                 }
@@ -577,6 +582,7 @@ struct TraceLane {
 #if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
             g_walks++; if (h == 0) g_fill_steps += n;
 #endif
+            if (P.debug & 4) { if (po.m == 0x7FFFFFFF) fb(v.t); continue; }      // timing experiments only: no output
             if (ok) emit(P, v.t, v, po);
             else fb(v.t);
         }
@@ -604,7 +610,6 @@ LSW_HD void prune_overlaps_read(lsw_hit* hits, long long lo, long long hi, int a
 }
 
 #if defined(__CUDACC__)
-constexpr int TRACE_THREADS = 128;
 
 template <int NR>
 __host__ __device__ constexpr size_t trace_prof_bytes() {
