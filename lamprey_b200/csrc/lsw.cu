@@ -721,8 +721,8 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     }
     ctx->n_reads = n;
     ctx->total_bases = n ? offs[n] - offs[0] : 0;
-    ctx->h_bb_off.assign((size_t)n + 1, 0);                       // 64-column blocks of every read (lsw_reuse.cuh)
-    for (int64_t i = 0; i < n; i++) ctx->h_bb_off[i + 1] = ctx->h_bb_off[i] + (ctx->h_rlen[i] + 63) / 64;
+    ctx->h_bb_off.assign((size_t)n + 1, 0);                       // BB_BLOCK-column blocks of every read (lsw_reuse.cuh)
+    for (int64_t i = 0; i < n; i++) ctx->h_bb_off[i + 1] = ctx->h_bb_off[i] + (ctx->h_rlen[i] + BB_BLOCK - 1) / BB_BLOCK;
     ctx->bb_total = ctx->h_bb_off[n];
     CK(ctx->d_bb_off.ensure((size_t)(n + 1) * 8));
     CK(cudaMemcpyAsync(ctx->d_bb_off.p, ctx->h_bb_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -823,7 +823,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         cnt.other_launches++;
     }
 
-    // block bests of round 0 for the child tasks: 4 B per 64 columns per (read, sequence)
+    // block bests of round 0 for the child tasks: 4 B per BB_BLOCK columns per (read, sequence)
     const bool reuse = ctx->reuse && !getenv("LSW_NO_REUSE");
     if (reuse) CK(ctx->d_blockbest.ensure((size_t)std::max<int64_t>(1, ctx->bb_total) * ctx->nseq * 4));
     int64_t n = n0;

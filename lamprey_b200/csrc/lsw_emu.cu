@@ -278,7 +278,7 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
     }
     if (E.reuse) {
         E.bb_off.assign((size_t)n_reads + 1, 0);
-        for (int64_t i = 0; i < n_reads; i++) E.bb_off[i + 1] = E.bb_off[i] + (E.rlen[i] + 63) / 64;
+        for (int64_t i = 0; i < n_reads; i++) E.bb_off[i + 1] = E.bb_off[i] + (E.rlen[i] + BB_BLOCK - 1) / BB_BLOCK;
         E.bb_total = E.bb_off[n_reads];
         E.blockbest.assign((size_t)std::max<int64_t>(1, E.bb_total * nseq), 0u);
     }

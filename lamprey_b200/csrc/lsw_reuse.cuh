@@ -5,10 +5,10 @@
 // aligned in round 0.  They are the SAME cells: an alignment whose every prefix scores > 0 spans fewer than
 // Wx = Q + M*Q/g read columns, so for read positions p >= a + Wx the child's H(r, p) equals the whole read's
 // H(r, p) (both have a zero boundary at their start, and no alignment ending at p can reach back to it).
-// Round 0 therefore stores, for every 64-column block of every (read, sequence), the block's best cell
+// Round 0 therefore stores, for every BB_BLOCK = 32 columns of every (read, sequence), the block's best cell
 // (value, row, column) -- 4 bytes -- and a child task whose slice is long enough is computed as
 //     HEAD   [a, hb)            the child's own DP up to the first block boundary hb >= a + Wx
-//     MIDDLE blocks hb/64 .. te/64-1 of the whole read, looked up                  (te = last boundary <= b)
+//     MIDDLE blocks hb/32 .. te/32-1 of the whole read, looked up                  (te = last boundary <= b)
 //     TAIL   [te - Wxa, b)      a DP that warms up for Wxa >= Wx columns (not counted) and counts (te, b];
 //                               Wxa is a multiple of the 32-column lane block the segment launches use
 // and the three bests are merged with swalign's tie rule (value, then row, then the LAST column).
@@ -25,7 +25,7 @@ struct SegPlan {
     int nseg;        // K1 segments of the task: 1 (direct, or head only) or 2 (head + tail)
     bool split;
     int hb;          // head = [a, hb)
-    int te;          // middle = whole-read blocks hb/64 .. te/64 - 1
+    int te;          // middle = whole-read blocks hb/BB_BLOCK .. te/BB_BLOCK - 1
     int ts, skip;    // tail = [ts, b), its first `skip` lane blocks (SEG_BLOCK columns each) are warm-up
     bool tail;
 };
@@ -35,8 +35,8 @@ LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable, int
     p.nseg = 1; p.split = false; p.hb = b; p.te = b; p.ts = 0; p.skip = 0; p.tail = false;
     if (!enable) return p;
     const int Wx = Q + (match * Q) / g;
-    const int hb = ((a + Wx + 63) / 64) * 64;
-    const int te = (b / 64) * 64;
+    const int hb = ((a + Wx + BB_BLOCK - 1) / BB_BLOCK) * BB_BLOCK;
+    const int te = (b / BB_BLOCK) * BB_BLOCK;
     if (hb > te) return p;
     const int Wxa = ((Wx + tb - 1) / tb) * tb;
     int ts = te - Wxa;
@@ -112,10 +112,10 @@ LSW_HD bool combine_task(const ReuseParams& R, int64_t t, int& o_score, int& o_r
     }
     if (p.split) {
         const uint32_t* bb = R.blockbest + (size_t)q * R.bb_total + R.bb_off[rd];
-        for (int j = p.hb / 64; j < p.te / 64; j++) {
-            const uint32_t v = bb[j];
+        for (int j = p.hb / BB_BLOCK; j < p.te / BB_BLOCK; j++) {
+            const uint32_t v = bb[j];                 // the column is stored as the step within K1's 64-step lane block
             const int s = (int)(v >> 16) - R.g;
-            consider(s, (int)((v >> 8) & 0xFF) + (int)((v >> 6) & 1) + 1, 64 * j + (int)(v & 63) + 1 - a);
+            consider(s, (int)((v >> 8) & 0xFF) + (int)((v >> 6) & 1) + 1, BLOCK_STEPS * (j * BB_BLOCK / BLOCK_STEPS) + (int)(v & 63) + 1 - a);
         }
         if (p.tail) {
             const int2 h = R.res_s[i + 1];

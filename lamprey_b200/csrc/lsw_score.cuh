@@ -172,78 +172,84 @@ struct ScoreLane {
             if (tid[h] >= 0) { end[h] = begin[h] + rem[h]; if (end[h] > P.block_steps) end[h] = P.block_steps; }
             else begin[h] = 0;
         }
-#pragma unroll
-        for (int r = 0; r < NR / 2; r++) K[r] = 0;
-
+        // Round 0 (P.blockbest set; whole reads, 64-step blocks) remembers the best cell of every BB_BLOCK = 32 columns for the
+        // child tasks (lsw_reuse.cuh): the block is folded twice, after each half.  Otherwise one fold per block.
+        const int nparts = P.blockbest ? 2 : 1;
+        const int kper = P.block_steps / (16 * nparts);
         uint32_t tvec = 0;
 #pragma unroll 1
-        for (int k = 0; k < P.block_steps / 16; k++) {
-            U4 c[2];
+        for (int part = 0; part < nparts; part++) {
+#pragma unroll
+            for (int r = 0; r < NR / 2; r++) K[r] = 0;
+#pragma unroll 1
+            for (int k = part * kper; k < (part + 1) * kper; k++) {
+                U4 c[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    U4 v = nx[h];
+                    // fetch the next chunk now (the first chunk of the next block when k == 3: the buffer is
+                    // padded, and start() reloads if the half switches task); its latency hides behind 16 columns
+                    if (tid[h] >= 0) nx[h] = *reinterpret_cast<const U4*>(P.codes + pos[h] + 16 * (k + 1));
+                    int nl = begin[h] - 16 * k; nl = nl < 0 ? 0 : (nl > 16 ? 16 : nl);
+                    int ne = end[h] - 16 * k;   ne = ne < 0 ? 0 : (ne > 16 ? 16 : ne);
+                    const U4 kg = keep_ge[nl], kl = keep_lt[ne];
+                    const uint32_t OTH = 0x01010101u * (h ? CODE_OTHER_HI : CODE_OTHER);
+                    if (h) {      // a real non-ACGT base is stored as 4; the high half indexes it as 20
+                        v.x |= (v.x & 0x04040404u) << 2; v.y |= (v.y & 0x04040404u) << 2;
+                        v.z |= (v.z & 0x04040404u) << 2; v.w |= (v.w & 0x04040404u) << 2;
+                    }
+                    uint32_t kp;
+                    kp = kg.x & kl.x; v.x = (v.x & kp) | (OTH & ~kp);
+                    kp = kg.y & kl.y; v.y = (v.y & kp) | (OTH & ~kp);
+                    kp = kg.z & kl.z; v.z = (v.z & kp) | (OTH & ~kp);
+                    kp = kg.w & kl.w; v.w = (v.w & kp) | (OTH & ~kp);
+                    c[h] = v;
+                }
+#pragma unroll 1
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t idx4 = c[0].x * 4u + c[1].x;          // four profile row indices, bytes <= 36
+                    c[0].x = c[0].y; c[0].y = c[0].z; c[0].z = c[0].w;
+                    c[1].x = c[1].y; c[1].y = c[1].z; c[1].z = c[1].w;
+#pragma unroll
+                    for (int j = 0; j < 4; j += 2) {
+                        const uint32_t ia = (idx4 >> (8 * j)) & 0xFFu, ib = (idx4 >> (8 * j + 8)) & 0xFFu;
+                        column2(prof + ia * PROF_STRIDE, prof + ib * PROF_STRIDE, tvec, tvec + 0x00010001u, G2, FLOOR2, P.one);
+                        tvec += 0x00020002u;
+                    }
+                }
+            }
+
+            // fold: per half, lexicographic max of (H, row, step) over the rows of the query
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                U4 v = nx[h];
-                // fetch the next chunk now (the first chunk of the next block when k == 3: the buffer is
-                // padded, and start() reloads if the half switches task); its latency hides behind 16 columns
-                if (tid[h] >= 0) nx[h] = *reinterpret_cast<const U4*>(P.codes + pos[h] + 16 * (k + 1));
-                int nl = begin[h] - 16 * k; nl = nl < 0 ? 0 : (nl > 16 ? 16 : nl);
-                int ne = end[h] - 16 * k;   ne = ne < 0 ? 0 : (ne > 16 ? 16 : ne);
-                const U4 kg = keep_ge[nl], kl = keep_lt[ne];
-                const uint32_t OTH = 0x01010101u * (h ? CODE_OTHER_HI : CODE_OTHER);
-                if (h) {      // a real non-ACGT base is stored as 4; the high half indexes it as 20
-                    v.x |= (v.x & 0x04040404u) << 2; v.y |= (v.y & 0x04040404u) << 2;
-                    v.z |= (v.z & 0x04040404u) << 2; v.w |= (v.w & 0x04040404u) << 2;
-                }
-                uint32_t kp;
-                kp = kg.x & kl.x; v.x = (v.x & kp) | (OTH & ~kp);
-                kp = kg.y & kl.y; v.y = (v.y & kp) | (OTH & ~kp);
-                kp = kg.z & kl.z; v.z = (v.z & kp) | (OTH & ~kp);
-                kp = kg.w & kl.w; v.w = (v.w & kp) | (OTH & ~kp);
-                c[h] = v;
-            }
-#pragma unroll 1
-            for (int w = 0; w < 4; w++) {
-                const uint32_t idx4 = c[0].x * 4u + c[1].x;          // four profile row indices, bytes <= 36
-                c[0].x = c[0].y; c[0].y = c[0].z; c[0].z = c[0].w;
-                c[1].x = c[1].y; c[1].y = c[1].z; c[1].z = c[1].w;
+                uint32_t bb = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j += 2) {
-                    const uint32_t ia = (idx4 >> (8 * j)) & 0xFFu, ib = (idx4 >> (8 * j + 8)) & 0xFFu;
-                    column2(prof + ia * PROF_STRIDE, prof + ib * PROF_STRIDE, tvec, tvec + 0x00010001u, G2, FLOOR2, P.one);
-                    tvec += 0x00020002u;
+                for (int r2 = 0; r2 < NR / 2; r2++) {
+                    if (2 * r2 < Q) {
+                        // bytes of K[r2]: [low_lo, H_lo, low_hi, H_hi] with low = 64 * (row & 1) + step
+                        //   ->  [low, 2 * r2, H, 0]: ordered by (H, row, step) because 256 * (2 r2) + low is monotone in (row, step).
+                        // (If Q is odd the padding row Q can be the pair's best only with a value below a real cell's: see DESIGN.md.)
+                        const uint32_t key = prmt(K[r2], (uint32_t)(2 * r2), h ? 0x5342u : 0x5140u);
+                        bb = key > bb ? key : bb;
+                    }
+                }
+                if (tid[h] >= 0 && P.blockbest) {
+                    // first column of this half block, 0-based on the read; a half block that starts past the read's end is not stored
+                    const int col0 = cbase[h] - 1 + part * BB_BLOCK;
+                    const int t = tid[h];
+                    if (col0 < len[h])
+                        P.blockbest[(size_t)P.t.seq[t] * P.bb_total + P.bb_off[P.t.read[t]] + (col0 / BB_BLOCK)] = bb;
+                }
+                if (tid[h] >= 0 && skipb[h] == 0 && (bb >> 6) >= (best[h] >> 6)) {   // >= : a later block wins ties on (H, row); bits 6.. hold (H, row)
+                    best[h] = bb;                                                    // (warm-up blocks of a tail segment are not counted)
+                    bestc[h] = cbase[h] + (int32_t)(bb & 0x3F);
                 }
             }
         }
-
-        // fold: per half, lexicographic max of (H, row, step) over the rows of the query
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            uint32_t bb = 0;
-#pragma unroll
-            for (int r2 = 0; r2 < NR / 2; r2++) {
-                if (2 * r2 < Q) {
-                    // bytes of K[r2]: [low_lo, H_lo, low_hi, H_hi] with low = 64 * (row & 1) + step
-                    //   ->  [low, 2 * r2, H, 0]: ordered by (H, row, step) because 256 * (2 r2) + low is monotone in (row, step).
-                    // (If Q is odd the padding row Q can be the pair's best only with a value below a real cell's: see DESIGN.md.)
-                    const uint32_t key = prmt(K[r2], (uint32_t)(2 * r2), h ? 0x5342u : 0x5140u);
-                    bb = key > bb ? key : bb;
-                }
-            }
-            if (tid[h] >= 0 && P.blockbest) {
-                // round 0 (whole reads, block grid = the read's): remember the block's best for the child tasks
-                const int t = tid[h];
-                P.blockbest[(size_t)P.t.seq[t] * P.bb_total + P.bb_off[P.t.read[t]] + ((cbase[h] - 1) >> 6)] = bb;
-            }
-            if (tid[h] >= 0 && skipb[h] > 0) {                 // warm-up block of a tail segment: not counted
-                skipb[h]--;
-                rem[h] -= end[h] - begin[h];
-                begin[h] = 0;
-                pos[h] += P.block_steps;
-                cbase[h] += P.block_steps;
-            } else if (tid[h] >= 0) {
-                if ((bb >> 6) >= (best[h] >> 6)) {       // >= : a later block wins ties on (H, row); bits 6.. hold (H, row)
-                    best[h] = bb;
-                    bestc[h] = cbase[h] + (int32_t)(bb & 0x3F);
-                }
+            if (tid[h] >= 0) {
+                if (skipb[h] > 0) skipb[h]--;
                 rem[h] -= end[h] - begin[h];
                 begin[h] = 0;
                 pos[h] += P.block_steps;
