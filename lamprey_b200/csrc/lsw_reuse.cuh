@@ -18,7 +18,7 @@
 
 namespace lsw {
 
-constexpr int SEG_BLOCK = 32;             // lane block (columns between task-switch points) of segment launches
+constexpr int SEG_BLOCK = 16;             // lane block (columns between task-switch points) of segment launches
 constexpr int REUSE_MIN_SAVING = 96;      // columns a split must save (two extra task starts / block tails)
 
 struct SegPlan {
