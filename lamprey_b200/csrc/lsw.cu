@@ -243,7 +243,7 @@ __global__ void k_prune_overlaps(lsw_hit* __restrict__ hits, int64_t n_hits, int
 // ---- reuse of the round-0 DP (lsw_reuse.cuh): plan, fill, merge ----------------------------------------
 __global__ void k_plan_segments(ReuseParams R) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= R.n; t += (int64_t)gridDim.x * blockDim.x)
-        R.nseg[t] = t < R.n ? plan_task(R.t.a[t], R.t.b[t], R.qlen[R.t.seq[t]], R.match, R.g, R.enable != 0).nseg : 0;
+        R.nseg[t] = t < R.n ? plan_of(R, t).nseg : 0;
 }
 
 __global__ void k_fill_segments(ReuseParams R, const int64_t* __restrict__ seg_t, int64_t* __restrict__ seg_s, int nseq) {
@@ -462,6 +462,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         // child tasks: K1 runs on the segment list (own head + warm-started tail), the whole-read blocks in between are looked up
         Span sp(ctx, 2);
         R.t = cur.view(); R.n = n; R.qlen = ctx->d_qlen.as<int32_t>(); R.match = ctx->match; R.g = ctx->g; R.enable = 1;
+        R.blockbest = ctx->d_blockbest.as<uint32_t>(); R.bb_off = ctx->d_bb_off.as<int64_t>(); R.bb_total = ctx->bb_total;
         CK(ctx->d_nseg.ensure((size_t)(n + 1) * 4)); CK(ctx->d_segpos.ensure((size_t)(n + 1) * 4));
         CK(ctx->segs.ensure((size_t)2 * n, false)); CK(ctx->d_seg_skip.ensure((size_t)2 * n));
         CK(ctx->d_res_s.ensure((size_t)2 * n * sizeof(int2))); CK(ctx->d_seg_s.ensure((size_t)(ctx->nseq + 1) * 8));

@@ -219,9 +219,10 @@ void emu_round(Emu& E, TraceParams T) {
     ReuseParams R;
     memset(&R, 0, sizeof R);
     R.t = view(E); R.n = n; R.qlen = E.qlen.data(); R.match = E.match; R.g = E.g; R.enable = 1;
+    R.blockbest = E.blockbest.data(); R.bb_off = E.bb_off.data(); R.bb_total = E.bb_total;
     std::vector<int32_t> segpos((size_t)n + 1, 0);
     for (int64_t t = 0; t < n; t++)
-        segpos[t + 1] = segpos[t] + plan_task(E.t_a[t], E.t_b[t], E.qlen[E.t_seq[t]], E.match, E.g, true).nseg;
+        segpos[t + 1] = segpos[t] + plan_of(R, t).nseg;
     const int64_t ns = segpos[n];
     std::vector<int32_t> s_read(ns), s_a(ns), s_b(ns);
     std::vector<int16_t> s_seq(ns);

@@ -25,14 +25,19 @@ struct SegPlan {
     int nseg;        // K1 segments of the task: 1 (direct, or head only) or 2 (head + tail)
     bool split;
     int hb;          // head = [a, hb)
-    int te;          // middle = whole-read blocks hb/BB_BLOCK .. te/BB_BLOCK - 1
+    int te;          // last block boundary <= b
+    int mid_end;     // middle = whole-read blocks hb/BB_BLOCK .. mid_end - 1
     int ts, skip;    // tail = [ts, b), its first `skip` lane blocks (SEG_BLOCK columns each) are warm-up
     bool tail;
 };
 
-LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable, int tb = SEG_BLOCK /* lane block of the segment launch */) {
+// bbrow: the (read, sequence) row of the round-0 block bests (may be null: no look-ahead into the last block).
+// The last, partial block [te, b) needs no DP when the whole block's best cell lies before b -- it is then also the best
+// of [te, b), last-column tie rule included -- or when the block holds no positive cell at all.
+LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable, const uint32_t* bbrow = nullptr,
+                         int tb = SEG_BLOCK /* lane block of the segment launch */) {
     SegPlan p;
-    p.nseg = 1; p.split = false; p.hb = b; p.te = b; p.ts = 0; p.skip = 0; p.tail = false;
+    p.nseg = 1; p.split = false; p.hb = b; p.te = b; p.mid_end = 0; p.ts = 0; p.skip = 0; p.tail = false;
     if (!enable) return p;
     const int Wx = Q + (match * Q) / g;
     const int hb = ((a + Wx + BB_BLOCK - 1) / BB_BLOCK) * BB_BLOCK;
@@ -41,10 +46,17 @@ LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable, int
     const int Wxa = ((Wx + tb - 1) / tb) * tb;
     int ts = te - Wxa;
     if (ts < 0) ts = 0;
-    const bool tail = b > te;
+    bool tail = b > te;
+    int mid_end = te / BB_BLOCK;
+    if (tail && bbrow) {
+        const uint32_t v = bbrow[te / BB_BLOCK];
+        const int s = (int)(v >> 16) - g;
+        const int col1 = BLOCK_STEPS * (te / BLOCK_STEPS) + (int)(v & 63) + 1;      // 1-based read column of the block's best cell
+        if (s <= 0 || col1 <= b) { tail = false; mid_end++; }
+    }
     const int computed = (hb - a) + (tail ? b - ts : 0);
     if (computed + REUSE_MIN_SAVING > b - a) return p;
-    p.split = true; p.hb = hb; p.te = te; p.ts = ts; p.skip = (te - ts) / tb; p.tail = tail;
+    p.split = true; p.hb = hb; p.te = te; p.mid_end = mid_end; p.ts = ts; p.skip = (te - ts) / tb; p.tail = tail;
     p.nseg = tail ? 2 : 1;
     return p;
 }
@@ -73,9 +85,15 @@ struct ReuseParams {
     unsigned long long* counters;   // [0] += tasks, [1] += reference cells
 };
 
+LSW_HD SegPlan plan_of(const ReuseParams& R, int64_t t) {
+    const int q = R.t.seq[t];
+    return plan_task(R.t.a[t], R.t.b[t], R.qlen[q], R.match, R.g, R.enable != 0,
+                     R.blockbest ? R.blockbest + (size_t)q * R.bb_total + R.bb_off[R.t.read[t]] : nullptr);
+}
+
 LSW_HD void fill_segments(const ReuseParams& R, int64_t t) {
     const int a = R.t.a[t], b = R.t.b[t], q = R.t.seq[t];
-    const SegPlan p = plan_task(a, b, R.qlen[q], R.match, R.g, R.enable != 0);
+    const SegPlan p = plan_of(R, t);
     const int64_t i = R.segpos[t];
     R.s.read[i] = R.t.read[t]; R.s.seq[i] = (int16_t)q; R.s.skip[i] = 0;
     R.s.a[i] = a; R.s.b[i] = p.split ? p.hb : b;
@@ -100,7 +118,7 @@ LSW_HD int cand_window(int score, int row, int col, int match, int g) {
 LSW_HD bool combine_task(const ReuseParams& R, int64_t t, int& o_score, int& o_row, int& o_col) {
     const int a = R.t.a[t], b = R.t.b[t], q = R.t.seq[t], rd = R.t.read[t];
     const int Q = R.qlen[q];
-    const SegPlan p = plan_task(a, b, Q, R.match, R.g, R.enable != 0);
+    const SegPlan p = plan_of(R, t);
     const int64_t i = R.segpos[t];
     int score = 0, row = 0, col = 0;
     auto consider = [&](int s, int r, int c) {       // regions are visited in ascending column order: >= keeps the last
@@ -112,7 +130,7 @@ LSW_HD bool combine_task(const ReuseParams& R, int64_t t, int& o_score, int& o_r
     }
     if (p.split) {
         const uint32_t* bb = R.blockbest + (size_t)q * R.bb_total + R.bb_off[rd];
-        for (int j = p.hb / BB_BLOCK; j < p.te / BB_BLOCK; j++) {
+        for (int j = p.hb / BB_BLOCK; j < p.mid_end; j++) {
             const uint32_t v = bb[j];                 // the column is stored as the step within K1's 64-step lane block
             const int s = (int)(v >> 16) - R.g;
             consider(s, (int)((v >> 8) & 0xFF) + (int)((v >> 6) & 1) + 1, BLOCK_STEPS * (j * BB_BLOCK / BLOCK_STEPS) + (int)(v & 63) + 1 - a);
