@@ -147,6 +147,25 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+def ncu_traffic():
+    """DRAM bytes of the dominant K1 launch from the committed `ncu --set full` capture (profiles/, a 32768-read run:
+    per-launch sizes differ from the bench's, so it is reported beside `traffic`, not as it).  HBM is not the bound here."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_score_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        h = rows[0]
+        r = max(rows[2:], key=lambda x: float(x[h.index("gpu__time_duration.sum")]))
+        rd, wr = float(r[h.index("dram__bytes_read.sum")]), float(r[h.index("dram__bytes_write.sum")])
+        unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[rows[1][h.index("dram__bytes_read.sum")]]
+        ms = float(r[h.index("gpu__time_duration.sum")])
+        return {"kernel": r[h.index("Kernel Name")].replace("void ", ""), "workload_reads": 32768,
+                "dram_bytes_per_launch": (rd + wr) * unit, "launch_ms_under_ncu": ms,
+                "hbm_gb_per_s": (rd + wr) * unit / 1e9 / (ms / 1e3), "source": "profiles/r01_score_raw.csv"}
+    except Exception:
+        return None
+
+
 def workload_reads(args, rank, world, workers):
     from lamprey_b200 import synth
     kw = dict(synth.CONFIGS[args.workload])
@@ -340,13 +359,21 @@ def main():
         got = [0] * n_eng
         h2d_lock, d2h_lock = threading.Lock(), threading.Lock()       # one transfer per direction at a time
 
+        phase = {"upload": [], "find_all": [], "fetch": []}          # host wall clock of every call (s), all contexts
+
         def e2e_worker(k, my_steps):
             for _ in range(my_steps):
                 with h2d_lock:
+                    t0 = time.perf_counter()
                     engines[k].upload_reads(ascii_np, offs_np)       # H2D of this step's reads (+ re-coding)
+                    t1 = time.perf_counter()
                 engines[k].find_all(args.thr, fetch=False)           # overlaps the other context's copies
+                t2 = time.perf_counter()
                 with d2h_lock:
+                    t3 = time.perf_counter()
                     got[k] = len(engines[k].fetch_hits(out=bufs[k]))  # D2H of this step's hits
+                    t4 = time.perf_counter()
+                phase["upload"].append(t1 - t0); phase["find_all"].append(t2 - t1); phase["fetch"].append(t4 - t3)
 
         def run_steps(total):
             per = [total // n_eng + (1 if k < total % n_eng else 0) for k in range(n_eng)]
@@ -357,6 +384,8 @@ def main():
                 t.join()
 
         run_steps(max(n_eng, args.warmup - 2))
+        for v in phase.values():
+            del v[:]
         barrier()
         e0.record(stream)
         run_steps(args.steps)
@@ -368,6 +397,7 @@ def main():
         e2e = {"value": reads_e2e / t_e2e, "unit": "reads/s",
                "h2d_bytes_per_step": int(ascii_np.nbytes + offs_np.nbytes), "d2h_bytes_per_step": int(max(got) * 32),
                "ms_per_step": 1e3 * t_e2e / args.steps, "engines": n_eng, "hits_per_step": int(max(got)),
+               "host_ms_per_call": {k: 1e3 * float(np.mean(v)) for k, v in phase.items() if v},
                "call": "per step: lsw_upload_reads + lsw_find_all + lsw_fetch_hits from/to pinned host buffers; %d contexts "
                        "(CUDA streams, one host thread each) take alternate steps so one step's copies overlap another's kernels" % n_eng}
         for e2 in engines[1:]:
@@ -385,7 +415,7 @@ def main():
         roofline = {"bound": "int_alu", "kernel": "k_score<NR> (K1: DP fill + arg-max)",
                     "achieved": k1_gcups, "peak": peak_gcups, "unit": "GCUPS",
                     "frac": (k1_gcups / peak_gcups) if (k1_gcups and peak_gcups) else None,
-                    "traffic": None,
+                    "traffic": None, "traffic_ncu": ncu_traffic(),
                     "peak_source": "lsw_measure_int_peak on this box (MEASURED_PEAKS.json has no integer rate): "
                                    "VIADDMNMX.S16x2 lane-ops/s x 2 cells / %d algorithmic ops per cell" % ALG_OPS_PER_CELL,
                     "int_peak_glaneops": peak, "launches": acc["score_launches"],

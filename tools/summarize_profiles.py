@@ -39,8 +39,8 @@ def ncu_csv(rep, page):
     return list(csv.reader(io.StringIO(out)))
 
 
-def launches(tag, md):
-    path = os.path.join(GP, "launches.csv")
+def launches(tag, md, fname="launches.csv", suffix="", cmd="python bench.py --reads 32768 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e", first=400):
+    path = os.path.join(GP, fname)
     if not os.path.exists(path):
         return
     rows = list(csv.reader(open(path)))
@@ -54,19 +54,20 @@ def launches(tag, md):
         v = float(r[iv].replace(",", ""))
         v = v / 1e3 if r[iu] in ("ns", "nsecond") else v * 1e3 if r[iu] in ("ms", "msecond") else v
         name = r[ik].split("(")[0].replace("void ", "").replace("lsw::", "").replace("<unnamed>::", "")
+        if name.startswith("cub::"):
+            name = name.split("<")[0] + ("<u16 keys>" if "unsigned short" in r[ik] else "<u64 keys>" if "unsigned long" in r[ik] else "")
         tot[name] += v
         cnt[name] += 1
         seq.append((r[0], name, v))
-    with open(os.path.join(OUT, tag + "_launches.csv"), "w") as fp:
+    with open(os.path.join(OUT, tag + "_launches%s.csv" % suffix), "w") as fp:
         fp.write("id,kernel,duration_us\n")
         for i, n, v in seq:
             fp.write("%s,%s,%.3f\n" % (i, n, v))
     step = {k: v for k, v in tot.items() if not k.startswith("k_intpeak")}
     total = sum(step.values())
-    md.append("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold cache, serialised)\n")
-    md.append("Command: `python bench.py --reads 32768 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e` "
-              "(first 400 launches). Shares are of the launches that belong to a step "
-              "(the `k_intpeak` roofline microbenchmark is excluded).\n")
+    md.append("## Launch list%s (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold cache, serialised)\n" % suffix.replace("_", " "))
+    md.append("Command: `%s` (first %d launches: roofline microbenchmark, warm-up step, timed step). Shares are of the "
+              "launches that belong to a step (the `k_intpeak` roofline microbenchmark is excluded).\n" % (cmd, first))
     md.append("| kernel | launches | total ms | share |\n|---|---|---|---|")
     for k, v in sorted(step.items(), key=lambda x: -x[1]):
         md.append("| `%s` | %d | %.3f | %.1f %% |" % (k, cnt[k], v / 1e3, 100 * v / total))
@@ -113,6 +114,7 @@ def main():
           "Produced by `tools/profile_cmd.sh` under gpurun and `tools/summarize_profiles.py` here. "
           "Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes.\n"]
     launches(tag, md)
+    launches(tag, md, "launches_1M.csv", "_1M", "python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e", 1200)
     kernel(tag, "score", md)
     kernel(tag, "trace", md)
     with open(os.path.join(OUT, tag + "_kernels.md"), "w") as fp:
