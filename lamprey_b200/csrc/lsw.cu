@@ -207,11 +207,12 @@ __global__ void k_scatter_children(TaskArrays child, const uint8_t* __restrict__
 }
 
 // sort key of a hit: (read, start, query) -- the order lamprey.py:722's stable sort yields
+// (the fields are packed as tightly as the batch allows: every 8 key bits saved is one radix pass over all hits)
 __global__ void k_hit_keys(const lsw_hit* __restrict__ hits, int64_t n, unsigned long long* __restrict__ keys,
-                           uint32_t* __restrict__ vals) {
+                           uint32_t* __restrict__ vals, int qbits, int sbits) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const lsw_hit h = hits[i];
-        keys[i] = ((unsigned long long)(uint32_t)h.read << 35) | ((unsigned long long)(uint32_t)h.start << 8) |
+        keys[i] = ((unsigned long long)(uint32_t)h.read << (qbits + sbits)) | ((unsigned long long)(uint32_t)h.start << qbits) |
                   (unsigned long long)(uint16_t)h.query;
         vals[i] = (uint32_t)i;
     }
@@ -929,15 +930,21 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         CK(ctx->d_keys[0].ensure((size_t)nh * 8)); CK(ctx->d_keys[1].ensure((size_t)nh * 8));
         CK(ctx->d_vals[0].ensure((size_t)nh * 4)); CK(ctx->d_vals[1].ensure((size_t)nh * 4));
         CK(ctx->d_hits_sorted.ensure((size_t)nh * sizeof(lsw_hit)));
+        auto bits_for = [](int64_t v) { int b = 1; while ((1ll << b) <= v) b++; return b; };      // bits that hold 0..v
+        int max_len = 1;
+        for (int32_t l : ctx->h_rlen) max_len = std::max(max_len, (int)l);
+        const int qbits = bits_for(ctx->nseq - 1), sbits = bits_for(max_len), rbits = bits_for(ctx->n_reads - 1);
+        const int key_bits = qbits + sbits + rbits;
+        if (key_bits > 64) return fail(ctx, LSW_E_ARG, "batch too large for the 64-bit hit sort key (reads x longest read x sequences)");
         k_hit_keys<<<grid_for(nh, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
-            ctx->d_hits.as<lsw_hit>(), nh, ctx->d_keys[0].as<unsigned long long>(), ctx->d_vals[0].as<uint32_t>());
+            ctx->d_hits.as<lsw_hit>(), nh, ctx->d_keys[0].as<unsigned long long>(), ctx->d_vals[0].as<uint32_t>(), qbits, sbits);
         CK(cudaGetLastError());
         size_t tmp = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_keys[0].as<unsigned long long>(), ctx->d_keys[1].as<unsigned long long>(),
-                                           ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>(), (int)nh, 0, 61, ctx->stream));
+                                           ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>(), (int)nh, 0, key_bits, ctx->stream));
         CK(ctx->d_cubtemp.ensure(tmp));
         CK(cub::DeviceRadixSort::SortPairs(ctx->d_cubtemp.p, tmp, ctx->d_keys[0].as<unsigned long long>(), ctx->d_keys[1].as<unsigned long long>(),
-                                           ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>(), (int)nh, 0, 61, ctx->stream));
+                                           ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>(), (int)nh, 0, key_bits, ctx->stream));
         k_gather_hits<<<grid_for(nh, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
             ctx->d_hits.as<lsw_hit>(), ctx->d_vals[1].as<uint32_t>(), nh, ctx->d_hits_sorted.as<lsw_hit>(), ctx->read_base);
         CK(cudaGetLastError());

@@ -634,7 +634,7 @@ __device__ __forceinline__ long long lower_bound_u16(const uint16_t* keys, long 
 #define LSW_K2_OCC_SMALL 6
 #endif
 template <int NR> struct TraceOcc {
-    static constexpr int value = NR <= 24 ? LSW_K2_OCC_SMALL : NR <= 32 ? (LSW_K2_OCC_SMALL > 5 ? 5 : LSW_K2_OCC_SMALL) : NR <= 48 ? 3 : 2;
+    static constexpr int value = NR <= 24 ? LSW_K2_OCC_SMALL : NR <= 32 ? (LSW_K2_OCC_SMALL > 5 ? 5 : LSW_K2_OCC_SMALL) : 3;
 };
 
 template <int NR, bool OPS>
