@@ -102,9 +102,10 @@ struct lsw_ctx {
     int32_t read_base = 0;
     // reuse of the round-0 DP by child tasks (lsw_reuse.cuh)
     bool reuse = true;
-    std::vector<int64_t> h_bb_off;
-    int64_t bb_total = 0;
-    DevBuf d_blockbest, d_bb_off, d_nseg, d_segpos, d_res_s, d_seg_s, d_class_of, d_kt;
+    std::vector<int64_t> h_bb_off, h_bb1_off;
+    int64_t bb_total = 0, bb1_total = 0;
+    bool use_bb1 = false;        // second-level block bests: built when the reads are long enough for slices to span whole groups
+    DevBuf d_blockbest, d_bb_off, d_bb1, d_bb1_off, d_nseg, d_segpos, d_res_s, d_seg_s, d_class_of, d_kt;
     TaskBuf segs;
     DevBuf d_seg_skip;
     int32_t allowed_overlap = -1;
@@ -251,6 +252,21 @@ __global__ void k_fill_segments(ReuseParams R, const int64_t* __restrict__ seg_t
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid <= nseq) seg_s[gid] = R.segpos[seg_t[gid]];
     for (int64_t t = gid; t < R.n; t += (int64_t)gridDim.x * blockDim.x) fill_segments(R, t);
+}
+
+// second-level block bests (lsw_reuse.cuh): one thread per (sequence, read, group of BB_GROUP blocks)
+__global__ void k_build_bb1(const uint32_t* __restrict__ bb, const int64_t* __restrict__ bb_off, int64_t bb_total,
+                            uint32_t* __restrict__ bb1, const int64_t* __restrict__ bb1_off, int64_t bb1_total,
+                            int64_t n_reads, int nseq, int g) {
+    const int64_t n = bb1_total * nseq;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i / bb1_total);
+        const int64_t G1 = i - (int64_t)q * bb1_total;            // group index over all reads
+        int64_t lo = 0, hi = n_reads;                              // read that owns it: last rd with bb1_off[rd] <= G1
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (bb1_off[mid] <= G1) lo = mid; else hi = mid; }
+        const int64_t rd = lo;
+        bb1[i] = reduce_block_group(bb + (size_t)q * bb_total + bb_off[rd], (int)(bb_off[rd + 1] - bb_off[rd]), (int)(G1 - bb1_off[rd]), g);
+    }
 }
 
 __global__ void k_merge_segments(ReuseParams R) {
@@ -464,6 +480,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         Span sp(ctx, 2);
         R.t = cur.view(); R.n = n; R.qlen = ctx->d_qlen.as<int32_t>(); R.match = ctx->match; R.g = ctx->g; R.enable = 1;
         R.blockbest = ctx->d_blockbest.as<uint32_t>(); R.bb_off = ctx->d_bb_off.as<int64_t>(); R.bb_total = ctx->bb_total;
+        if (ctx->use_bb1) { R.bb1 = ctx->d_bb1.as<uint32_t>(); R.bb1_off = ctx->d_bb1_off.as<int64_t>(); R.bb1_total = ctx->bb1_total; }
         CK(ctx->d_nseg.ensure((size_t)(n + 1) * 4)); CK(ctx->d_segpos.ensure((size_t)(n + 1) * 4));
         CK(ctx->segs.ensure((size_t)2 * n, false)); CK(ctx->d_seg_skip.ensure((size_t)2 * n));
         CK(ctx->d_res_s.ensure((size_t)2 * n * sizeof(int2))); CK(ctx->d_seg_s.ensure((size_t)(ctx->nseq + 1) * 8));
@@ -616,7 +633,7 @@ void lsw_destroy(lsw_ctx* ctx) {
     for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); ctx->d_cand_rec[c].release(); }
     ctx->d_nfallback.release();
     ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release(); ctx->segs.release();
-    for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_seg_skip, &ctx->d_kt}) b->release();
+    for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_bb1, &ctx->d_bb1_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_seg_skip, &ctx->d_kt}) b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -728,6 +745,15 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     ctx->bb_total = ctx->h_bb_off[n];
     CK(ctx->d_bb_off.ensure((size_t)(n + 1) * 8));
     CK(cudaMemcpyAsync(ctx->d_bb_off.p, ctx->h_bb_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_bb1_off.assign((size_t)n + 1, 0);
+    for (int64_t i = 0; i < n; i++)
+        ctx->h_bb1_off[i + 1] = ctx->h_bb1_off[i] + (ctx->h_bb_off[i + 1] - ctx->h_bb_off[i] + BB_GROUP - 1) / BB_GROUP;
+    ctx->bb1_total = ctx->h_bb1_off[n];
+    CK(ctx->d_bb1_off.ensure((size_t)(n + 1) * 8));
+    CK(cudaMemcpyAsync(ctx->d_bb1_off.p, ctx->h_bb1_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // a slice must span more than two groups (2048 columns) before the second level saves lookups
+    ctx->use_bb1 = n > 0 && ctx->total_bases / n >= 4 * BB_GROUP * BB_BLOCK;
+    if (const char* e = getenv("LSW_BB_L1")) ctx->use_bb1 = atoi(e) != 0;
     // 256 B front pad (K2 reads a few codes before a window start, masked) and 256 B tail pad (K1 reads
     // whole 64-byte blocks past a slice end)
     ctx->codes_bytes = 256 + padded_total + 256;
@@ -849,6 +875,15 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         T.child = ctx->child.view();
         rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse ? (round == 0 ? 1 : 2) : 0);
         if (rc) break;
+        if (reuse && round == 0 && ctx->use_bb1 && ctx->bb1_total > 0) {
+            Span sp(ctx, 2);
+            CK(ctx->d_bb1.ensure((size_t)ctx->bb1_total * ctx->nseq * 4));
+            k_build_bb1<<<grid_for(ctx->bb1_total * ctx->nseq, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+                ctx->d_blockbest.as<uint32_t>(), ctx->d_bb_off.as<int64_t>(), ctx->bb_total, ctx->d_bb1.as<uint32_t>(),
+                ctx->d_bb1_off.as<int64_t>(), ctx->bb1_total, ctx->n_reads, ctx->nseq, ctx->g);
+            CK(cudaGetLastError());
+            cnt.other_launches++;
+        }
 
         {
             Span sp(ctx, 2);

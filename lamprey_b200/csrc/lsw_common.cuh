@@ -17,6 +17,7 @@ constexpr int SC         = 1 << SC_SHIFT;   // ... so the low byte can carry the
 constexpr int BLOCK_STEPS = 64;        // columns a lane advances between two task-switch points
 constexpr int MAXQ       = 63;         // LSW_MAX_QUERY_LEN
 constexpr int BB_BLOCK   = 32;         // columns per stored block best of round 0 (lsw_reuse.cuh)
+constexpr int BB_GROUP   = 32;         // block bests per second-level entry (long slices are merged group by group)
 constexpr int QSTRIDE    = 64;         // bytes per query in the device query-code table
 constexpr int CODE_OTHER = 4;          // read code of any byte that is not A/C/G/T (never matches)
 constexpr int CODE_OTHER_HI = 20;      // ... as seen by the task in the HIGH half of a K1 lane (see profile index)

@@ -44,8 +44,9 @@ struct Emu {
     bool reuse = false;
     int round = 0;
     std::vector<uint32_t> blockbest;
-    std::vector<int64_t> bb_off;
-    int64_t bb_total = 0;
+    std::vector<int64_t> bb_off, bb1_off;
+    int64_t bb_total = 0, bb1_total = 0;
+    std::vector<uint32_t> bb1;       // second-level block bests (always used by the emulation when reuse is on)
     unsigned long long comp_cells = 0;
 };
 
@@ -220,6 +221,17 @@ void emu_round(Emu& E, TraceParams T) {
     memset(&R, 0, sizeof R);
     R.t = view(E); R.n = n; R.qlen = E.qlen.data(); R.match = E.match; R.g = E.g; R.enable = 1;
     R.blockbest = E.blockbest.data(); R.bb_off = E.bb_off.data(); R.bb_total = E.bb_total;
+    if (E.round == 1 && E.bb1_total > 0) {           // built once, after round 0
+        E.bb1.assign((size_t)E.bb1_total * E.nseq, 0u);
+        const int64_t nr = (int64_t)E.bb_off.size() - 1;
+        for (int q = 0; q < E.nseq; q++)
+            for (int64_t rd = 0; rd < nr; rd++)
+                for (int64_t G = 0; G < E.bb1_off[rd + 1] - E.bb1_off[rd]; G++)
+                    E.bb1[(size_t)q * E.bb1_total + E.bb1_off[rd] + G] =
+                        reduce_block_group(E.blockbest.data() + (size_t)q * E.bb_total + E.bb_off[rd],
+                                           (int)(E.bb_off[rd + 1] - E.bb_off[rd]), (int)G, E.g);
+    }
+    if (E.bb1_total > 0) { R.bb1 = E.bb1.data(); R.bb1_off = E.bb1_off.data(); R.bb1_total = E.bb1_total; }
     std::vector<int32_t> segpos((size_t)n + 1, 0);
     for (int64_t t = 0; t < n; t++)
         segpos[t + 1] = segpos[t] + plan_of(R, t).nseg;
@@ -281,6 +293,9 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
         E.bb_off.assign((size_t)n_reads + 1, 0);
         for (int64_t i = 0; i < n_reads; i++) E.bb_off[i + 1] = E.bb_off[i] + (E.rlen[i] + BB_BLOCK - 1) / BB_BLOCK;
         E.bb_total = E.bb_off[n_reads];
+        E.bb1_off.assign((size_t)n_reads + 1, 0);
+        for (int64_t i = 0; i < n_reads; i++) E.bb1_off[i + 1] = E.bb1_off[i] + (E.bb_off[i + 1] - E.bb_off[i] + BB_GROUP - 1) / BB_GROUP;
+        E.bb1_total = E.bb1_off[n_reads];
         E.blockbest.assign((size_t)std::max<int64_t>(1, E.bb_total * nseq), 0u);
     }
     unsigned long long nhits = 0;

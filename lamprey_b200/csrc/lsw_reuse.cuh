@@ -74,8 +74,11 @@ struct ReuseParams {
     const int2* res_s;           // K1 results per segment
     int2* res_t;                 // merged result per task
     const uint32_t* blockbest;   // [n_seq][bb_total]
-    const int64_t* bb_off;       // [n_reads] first block of each read
+    const int64_t* bb_off;       // [n_reads + 1] first block of each read
     int64_t bb_total;
+    const uint32_t* bb1;         // second level, [n_seq][bb1_total]: best of every BB_GROUP blocks of a read (null: not built)
+    const int64_t* bb1_off;      // [n_reads + 1] first group of each read
+    int64_t bb1_total;
     const uint8_t* cand_ok;      // [n_seq][128]
     const int32_t* class_of;     // [n_seq] register-row class
     uint32_t* cand[16];          // per class: candidate list / sort key
@@ -108,6 +111,28 @@ LSW_HD void fill_segments(const ReuseParams& R, int64_t t) {
     }
 }
 
+// A stored block best -> (score, row, 1-based read column).  j: block index within the read.
+LSW_HD void decode_block_best(uint32_t v, int j, int g, int& s, int& r, int& c1) {
+    s = (int)(v >> 16) - g;                            // the column is stored as the step within K1's 64-step lane block
+    r = (int)((v >> 8) & 0xFF) + (int)((v >> 6) & 1) + 1;
+    c1 = BLOCK_STEPS * (j * BB_BLOCK / BLOCK_STEPS) + (int)(v & 63) + 1;
+}
+
+// Second level: the best of blocks [BB_GROUP * G, BB_GROUP * (G + 1)) of one (read, sequence) under swalign's tie rule
+// (value, then row, then the LAST column -- the blocks are visited in ascending order and >= keeps the later one), as
+// score << 16 | row << 10 | column offset within the group's BB_GROUP * BB_BLOCK = 1024 columns.  0: no positive cell.
+LSW_HD uint32_t reduce_block_group(const uint32_t* bbrow, int nblocks, int G, int g) {
+    int score = 0, row = 0, col1 = 0;
+    const int j1 = (G + 1) * BB_GROUP < nblocks ? (G + 1) * BB_GROUP : nblocks;
+    for (int j = G * BB_GROUP; j < j1; j++) {
+        int s, r, c1;
+        decode_block_best(bbrow[j], j, g, s, r, c1);
+        if (s > 0 && (s > score || (s == score && r >= row))) { score = s; row = r; col1 = c1; }
+    }
+    if (score <= 0) return 0u;
+    return ((uint32_t)score << 16) | ((uint32_t)row << 10) | (uint32_t)(col1 - 1 - G * BB_GROUP * BB_BLOCK);
+}
+
 // sort key of a K2 candidate: the number of window columns its traceback will fill
 LSW_HD int cand_window(int score, int row, int col, int match, int g) {
     int w = score > 0 ? row + (match * row - score) / g + 8 : 0;
@@ -130,11 +155,26 @@ LSW_HD bool combine_task(const ReuseParams& R, int64_t t, int& o_score, int& o_r
     }
     if (p.split) {
         const uint32_t* bb = R.blockbest + (size_t)q * R.bb_total + R.bb_off[rd];
-        for (int j = p.hb / BB_BLOCK; j < p.mid_end; j++) {
-            const uint32_t v = bb[j];                 // the column is stored as the step within K1's 64-step lane block
-            const int s = (int)(v >> 16) - R.g;
-            consider(s, (int)((v >> 8) & 0xFF) + (int)((v >> 6) & 1) + 1, BLOCK_STEPS * (j * BB_BLOCK / BLOCK_STEPS) + (int)(v & 63) + 1 - a);
+        auto block = [&](int j) {
+            int s, r, c1;
+            decode_block_best(bb[j], j, R.g, s, r, c1);
+            consider(s, r, c1 - a);
+        };
+        int j = p.hb / BB_BLOCK;
+        const int j1 = p.mid_end;
+        if (R.bb1) {
+            // whole groups in the middle of a long slice come from the second level
+            const uint32_t* b1 = R.bb1 + (size_t)q * R.bb1_total + R.bb1_off[rd];
+            int ja = ((j + BB_GROUP - 1) / BB_GROUP) * BB_GROUP;
+            if (ja > j1) ja = j1;
+            for (; j < ja; j++) block(j);
+            for (; j + BB_GROUP <= j1; j += BB_GROUP) {
+                const int G = j / BB_GROUP;
+                const uint32_t v = b1[G];
+                consider((int)(v >> 16), (int)((v >> 10) & 63), G * BB_GROUP * BB_BLOCK + (int)(v & 1023) + 1 - a);
+            }
         }
+        for (; j < j1; j++) block(j);
         if (p.tail) {
             const int2 h = R.res_s[i + 1];
             consider(h.x & 0xFFFF, h.x >> 16, p.ts + h.y - a);

@@ -212,3 +212,27 @@ def test_emu_scoring_outside_the_short_window_range(scoring):
     hits, cnt = emu_lib.find_all(reads, seqs, 0.7, *scoring)
     assert np.array_equal(hits_matrix(hits), want)
     assert (cnt["tasks"], cnt["cells"]) == (calls, cells) and cnt["fallbacks"] == cnt["traced"] > 0
+
+
+def test_emu_long_sparse_reads_use_second_level_block_bests():
+    # few primer copies in long reads: child slices span thousands of columns, so the merge takes whole groups of block
+    # bests from the second level (lsw_reuse.cuh); slice ends fall on and around the 1024-column group grid
+    rng = random.Random(77)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(q)) for q in (18, 22, 24, 31, 50)]
+    reads = []
+    for n in (1023, 1024, 1025, 2047, 2048, 2049, 3500, 5000, 7000, 9000, 4096, 6144):
+        r = [rng.choice("ACGT") for _ in range(n)]
+        for _ in range(rng.randrange(2, 7)):
+            sq = seqs[rng.randrange(len(seqs))]
+            p = rng.choice([0, 1024 - len(sq), 1024, 2048 - 5, n - len(sq), rng.randrange(0, n - len(sq))])
+            p = max(0, min(n - len(sq), p))
+            for k, ch in enumerate(sq):
+                if rng.random() > 0.06:
+                    r[p + k] = ch
+        reads.append("".join(r))
+    want, calls, cells = _oracle_rows(reads, seqs, 0.7)
+    for reuse in (True, False):
+        hits, cnt = emu_lib.find_all(reads, seqs, 0.7, 2, -1, -1, reuse=reuse)
+        assert np.array_equal(hits_matrix(hits), want), reuse
+        assert (cnt["tasks"], cnt["cells"]) == (calls, cells)
+    assert len(want) > 20

@@ -388,3 +388,38 @@ def test_scoring_outside_the_short_window_range(engine, scoring):
     assert np.array_equal(hits_matrix(hits), np.array(rows, np.int32).reshape(-1, 10))
     assert engine.last_counters["fallbacks"] == engine.last_counters["traced"] > 0
     engine.set_scoring(2, -1, -1, -1)
+
+
+def test_long_sparse_reads_use_second_level_block_bests(engine, monkeypatch):
+    # few primer copies in long reads: child slices span thousands of columns, so the merge takes whole groups of block
+    # bests from the second level (lsw_reuse.cuh); slice ends fall on and around the 1024-column group grid
+    rng = random.Random(77)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(q)) for q in (18, 22, 24, 31, 50)]
+    reads = []
+    for n in (1023, 1024, 1025, 2047, 2048, 2049, 3500, 5000, 7000, 9000, 4096, 6144):
+        r = [rng.choice("ACGT") for _ in range(n)]
+        for _ in range(rng.randrange(2, 7)):
+            sq = seqs[rng.randrange(len(seqs))]
+            p = rng.choice([0, 1024 - len(sq), 1024, 2048 - 5, n - len(sq), rng.randrange(0, n - len(sq))])
+            p = max(0, min(n - len(sq), p))
+            for k, ch in enumerate(sq):
+                if rng.random() > 0.06:
+                    r[p + k] = ch
+        reads.append("".join(r))
+    rows, calls, cells = [], 0, 0
+    for i, r in enumerate(reads):
+        h, st = c_oracle.find_all(r, seqs, 0.7, 2, -1, -1, -1)
+        h = h[np.argsort(h["start"], kind="stable")]
+        calls += st["calls"]; cells += st["cells"]
+        rows += [(i, x["seq"], x["start"], x["end"], x["matches"], x["mismatches"], x["score"], x["q_pos"], x["q_end"],
+                  x["depth"]) for x in h]
+    want = np.array(rows, np.int32).reshape(-1, 10)
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(seqs)
+    for l1 in ("1", "0"):                       # read by lsw_upload_reads
+        monkeypatch.setenv("LSW_BB_L1", l1)
+        engine.upload_read_list(reads)
+        hits = engine.find_all(0.7)
+        assert np.array_equal(hits_matrix(hits), want), l1
+        assert (engine.last_counters["tasks"], engine.last_counters["cells"]) == (calls, cells)
+    assert len(want) > 20
