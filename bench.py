@@ -15,6 +15,7 @@ SURVEY.md section 8d), cpu_baseline (Cython swalign on the host cores, N=1 only)
 buffers -> hits on the host through the C ABI, H2D/D2H inside the timed region), clocks.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -358,6 +359,9 @@ def main():
             bufs.append(hb.numpy().view(_native.HIT_DT))
         got = [0] * n_eng
         h2d_lock, d2h_lock = threading.Lock(), threading.Lock()       # one transfer per direction at a time
+        # one find_all at a time: two contexts computing side by side share SMs and L2 and each runs at less than half
+        # speed, while the copies of the waiting context overlap the running one's kernels either way
+        gpu_lock = threading.Lock() if os.environ.get("LSW_E2E_COMPUTE_LOCK", "1") != "0" else contextlib.nullcontext()
 
         phase = {"upload": [], "find_all": [], "fetch": []}          # host wall clock of every call (s), all contexts
 
@@ -367,13 +371,15 @@ def main():
                     t0 = time.perf_counter()
                     engines[k].upload_reads(ascii_np, offs_np)       # H2D of this step's reads (+ re-coding)
                     t1 = time.perf_counter()
-                engines[k].find_all(args.thr, fetch=False)           # overlaps the other context's copies
-                t2 = time.perf_counter()
+                with gpu_lock:
+                    t1b = time.perf_counter()
+                    engines[k].find_all(args.thr, fetch=False)       # overlaps the other context's copies
+                    t2 = time.perf_counter()
                 with d2h_lock:
                     t3 = time.perf_counter()
                     got[k] = len(engines[k].fetch_hits(out=bufs[k]))  # D2H of this step's hits
                     t4 = time.perf_counter()
-                phase["upload"].append(t1 - t0); phase["find_all"].append(t2 - t1); phase["fetch"].append(t4 - t3)
+                phase["upload"].append(t1 - t0); phase["find_all"].append(t2 - t1b); phase["fetch"].append(t4 - t3)
 
         def run_steps(total):
             per = [total // n_eng + (1 if k < total % n_eng else 0) for k in range(n_eng)]
@@ -399,7 +405,8 @@ def main():
                "ms_per_step": 1e3 * t_e2e / args.steps, "engines": n_eng, "hits_per_step": int(max(got)),
                "host_ms_per_call": {k: 1e3 * float(np.mean(v)) for k, v in phase.items() if v},
                "call": "per step: lsw_upload_reads + lsw_find_all + lsw_fetch_hits from/to pinned host buffers; %d contexts "
-                       "(CUDA streams, one host thread each) take alternate steps so one step's copies overlap another's kernels" % n_eng}
+                       "(CUDA streams, one host thread each) take alternate steps so one step's copies overlap another's kernels; "
+                       "one lsw_find_all runs at a time" % n_eng}
         for e2 in engines[1:]:
             e2.close()
 
