@@ -419,7 +419,6 @@ void fill_score_params(lsw_ctx* ctx, ScoreParams& P, const TaskBuf& cur, int seg
     P.s_mis = SC * (ctx->mismatch + ctx->g);
     P.g = ctx->g;
     P.match = ctx->match;
-    P.one = 1u;
 }
 
 void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {

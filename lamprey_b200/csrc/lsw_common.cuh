@@ -35,17 +35,6 @@ LSW_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) {       // max(a + b
 LSW_HD uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) {        // max(a, b, c) per s16 half
     return __vimax3_s16x2(a, b, c);
 }
-// a + b issued as IMAD (a * one + b, `one` is a kernel parameter holding 1 so ptxas cannot fold it): the
-// FMA pipe is nearly idle in K1 while the ALU pipe, which runs the DPX ops, is the bottleneck.
-LSW_HD uint32_t add_on_fma_pipe(uint32_t a, uint32_t b, uint32_t one) {
-#if defined(__CUDA_ARCH__)
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
-    return d;
-#else
-    return a * one + b;
-#endif
-}
 LSW_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #if defined(__CUDA_ARCH__)
     return __byte_perm(a, b, sel);
@@ -161,7 +150,6 @@ struct ScoreParams {
     int32_t s_mis;            // SC * (mismatch + |gap|)
     int32_t g;                // |gap|
     int32_t match;
-    uint32_t one;             // 1 (see add_on_fma_pipe)
     uint32_t* blockbest;      // round 0: best cell of every 64-column block, [n_seq][bb_total] (lsw_reuse.cuh); else null
     const int64_t* bb_off;    // [n_reads] first block of each read
     int64_t bb_total;

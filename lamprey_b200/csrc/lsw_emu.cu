@@ -191,7 +191,7 @@ void emu_round(Emu& E, TraceParams T) {
     P.codes = E.codes.data(); P.roff = E.roff.data(); P.t = view(E); P.seg = E.seg.data();
     P.res = E.res.data(); P.qcodes = E.qcodes.data(); P.qlen = E.qlen.data();
     P.cand_ok = E.cand_ok.data();
-    P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g; P.match = E.match; P.one = 1u;
+    P.s_match = SC * (E.match + E.g); P.s_mis = SC * (E.mismatch + E.g); P.g = E.g; P.match = E.match;
     P.push_cands = 1; P.count_ref = 1; P.block_steps = BLOCK_STEPS;
     int qmax = 1;
     for (int s = 0; s < E.nseq; s++) qmax = std::max(qmax, (int)E.qlen[s]);

@@ -133,9 +133,8 @@ struct ScoreLane {
 
     // TWO DP columns (c, c+1) for both halves, row by row.  prowA / prowB: profile rows of the two columns'
     // (code_lo, code_hi) pairs.  Doing two columns per sweep lets one VIMNMX3 fold both arg-max keys into K[r]
-    // (the key adds are plain adds and go to the FMA pipe), i.e. 5 ALU-pipe ops per four cells instead of 6.
-    LSW_HD void column2(const U2* prowA, const U2* prowB, uint32_t tvA, uint32_t tvB, uint32_t G2, uint32_t FLOOR2,
-                        uint32_t one) {
+    // (the key adds are plain adds), i.e. 5 DPX ops and 4 adds per four cells.
+    LSW_HD void column2(const U2* prowA, const U2* prowB, uint32_t tvA, uint32_t tvB, uint32_t G2, uint32_t FLOOR2) {
         uint32_t dOld = 0, uA = 0, uB = 0;
 #pragma unroll
         for (int r2 = 0; r2 < NR / 2; r2++) {
@@ -149,8 +148,8 @@ struct ScoreLane {
                 const uint32_t T2 = addmax2(uA, SB, m1);         \
                 const uint32_t h2 = max3_2(T2, uB, FLOOR2);      \
                 const uint32_t m2 = h2 - G2;                     \
-                K[(R) >> 1] = max3_2(K[(R) >> 1], add_on_fma_pipe(h1, tvA + ((R) & 1) * 0x00400040u, one),       \
-                                     add_on_fma_pipe(h2, tvB + ((R) & 1) * 0x00400040u, one)); \
+                K[(R) >> 1] = max3_2(K[(R) >> 1], h1 + (tvA + ((R) & 1) * 0x00400040u), \
+                                     h2 + (tvB + ((R) & 1) * 0x00400040u)); \
                 M[R] = m2;                                       \
                 dOld = mold; uA = m1; uB = m2;                   \
             }
@@ -213,7 +212,7 @@ struct ScoreLane {
 #pragma unroll
                     for (int j = 0; j < 4; j += 2) {
                         const uint32_t ia = (idx4 >> (8 * j)) & 0xFFu, ib = (idx4 >> (8 * j + 8)) & 0xFFu;
-                        column2(prof + ia * PROF_STRIDE, prof + ib * PROF_STRIDE, tvec, tvec + 0x00010001u, G2, FLOOR2, P.one);
+                        column2(prof + ia * PROF_STRIDE, prof + ib * PROF_STRIDE, tvec, tvec + 0x00010001u, G2, FLOOR2);
                         tvec += 0x00020002u;
                     }
                 }
