@@ -423,6 +423,13 @@ def main():
                     "achieved": k1_gcups, "peak": peak_gcups, "unit": "GCUPS",
                     "frac": (k1_gcups / peak_gcups) if (k1_gcups and peak_gcups) else None,
                     "traffic": None, "traffic_ncu": ncu_traffic(),
+                    # K1's real instruction mix: 5 packed DPX lane-ops per 4 cells (SASS-checked) -> the rate at which the
+                    # DPX pipe alone would saturate, and the rate a register-only microbenchmark of the row mix reaches
+                    "peak_dpx_only": peak_ops * 4.0 / 5.0 if peak_ops else None,
+                    "frac_dpx_only": (k1_gcups / (peak_ops * 4.0 / 5.0)) if (k1_gcups and peak_ops) else None,
+                    # (9 instructions per 4 cells at the lane-op rate the mixed DPX/add chain measures)
+                    "peak_row_mix_microbench": peak.get("k1_mix", 0.0) * 4.0 / 9.0 if peak.get("k1_mix") else None,
+                    "frac_row_mix_microbench": (k1_gcups / (peak["k1_mix"] * 4.0 / 9.0)) if (k1_gcups and peak.get("k1_mix")) else None,
                     "peak_source": "lsw_measure_int_peak on this box (MEASURED_PEAKS.json has no integer rate): "
                                    "VIADDMNMX.S16x2 lane-ops/s x 2 cells / %d algorithmic ops per cell" % ALG_OPS_PER_CELL,
                     "int_peak_glaneops": peak, "launches": acc["score_launches"],
