@@ -423,3 +423,39 @@ def test_long_sparse_reads_use_second_level_block_bests(engine, monkeypatch):
         assert np.array_equal(hits_matrix(hits), want), l1
         assert (engine.last_counters["tasks"], engine.last_counters["cells"]) == (calls, cells)
     assert len(want) > 20
+
+
+def _oracle_chunk(args):
+    reads, seqs, thr, base = args
+    rows, calls, cells = [], 0, 0
+    for i, r in enumerate(reads):
+        h, st = c_oracle.find_all(r, seqs, thr)
+        h = h[np.argsort(h["start"], kind="stable")]
+        calls += st["calls"]
+        cells += st["cells"]
+        rows += [(base + i, x["seq"], x["start"], x["end"], x["matches"], x["mismatches"], x["score"], x["q_pos"], x["q_end"],
+                  x["depth"]) for x in h]
+    return rows, calls, cells
+
+
+def test_find_all_1024_synthetic_reads_vs_oracle(engine):
+    # hits, call count and cell count cross-checked against the oracle on >= 1000 reads of the
+    # headline workload (the C oracle runs one process per host core)
+    import multiprocessing as mp
+    n, thr = 1024, 0.7
+    concat, offs = synth.generate(n, **synth.CONFIGS["synth_2kb_8pct"])
+    seqs = _seqs("H33")
+    reads = synth.reads_as_strings(concat, offs)
+    cores = max(1, min(32, os.cpu_count() or 1))
+    step = (n + cores - 1) // cores
+    with mp.get_context("fork").Pool(cores) as pool:
+        parts = pool.map(_oracle_chunk, [(reads[k:k + step], seqs, thr, k) for k in range(0, n, step)])
+    rows = [r for p in parts for r in p[0]]
+    calls, cells = sum(p[1] for p in parts), sum(p[2] for p in parts)
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(seqs)
+    engine.upload_reads(concat, offs)
+    hits = engine.find_all(thr)
+    assert np.array_equal(hits_matrix(hits), np.array(rows, np.int32).reshape(-1, 10))
+    assert (engine.last_counters["tasks"], engine.last_counters["cells"]) == (calls, cells)
+    assert len(rows) > 100000
