@@ -10,7 +10,8 @@ Mirrors, name for name and argument for argument (same ordering and error behavi
 
 and adds the batched form the reference lacks: ``seed_reads(reads, primer_set, threshold)`` seeds a
 whole FASTQ in one device pass (recursion included) and returns a ``SeedBatch`` (struct of arrays;
-``batch[i]`` gives exactly what ``findAllPrimerAlignments`` returns for read ``i``).
+``batch[i]`` gives exactly what ``findAllPrimerAlignments`` returns for read ``i``); ``seed_fastq(path, ...)`` does the
+same straight from a FASTQ file.
 The arithmetic runs only in liblsw.so; nothing here computes an alignment on the CPU.
 """
 import numpy as np
@@ -153,6 +154,17 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
     hits = eng.find_all(threshold)
     eng.set_overlap(None)
     return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters)
+
+
+def seed_fastq(path, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None, with_names=False):
+    """Seed one FASTQ file as one batch -- what the online FastqHandler.process_file does per file
+    (/root/reference/lamprey.py:451-507) and the offline loader per run (lamprey.py:2145-2155), without Biopython.
+    -> SeedBatch [, read names]."""
+    from . import fastq as _fastq
+    got = _fastq.read_fastq(path, with_names=with_names)
+    batch = seed_reads((got[0], got[1]), primer_set, threshold, aligner=aligner, device=device, engine=engine,
+                       allowed_overlap=allowed_overlap)
+    return (batch, got[2]) if with_names else batch
 
 
 def _preorder(hits, identity, name):

@@ -459,3 +459,16 @@ def test_find_all_1024_synthetic_reads_vs_oracle(engine):
     assert np.array_equal(hits_matrix(hits), np.array(rows, np.int32).reshape(-1, 10))
     assert (engine.last_counters["tasks"], engine.last_counters["cells"]) == (calls, cells)
     assert len(rows) > 100000
+
+
+def test_seed_fastq_one_file_one_batch(engine, tmp_path):
+    # FASTQ file -> seeds in one call (the online mode's one file = one batch), against the golden seeding result
+    reads = load_reads("50")
+    path = tmp_path / "batch.fastq"
+    with open(path, "w") as fp:
+        for i, r in enumerate(reads):
+            fp.write("@read%d runid=x\n%s\n+\n%s\n" % (i, r, "I" * len(r)))
+    batch, names = seeding.seed_fastq(str(path), seeding.PrimerSet(schema_path("H33")), 0.75, with_names=True)
+    gold = load_seed_golden("50", "H33", 0.75)
+    assert np.array_equal(hits_matrix(batch.hits), gold["hits"])
+    assert names[:2] == ["read0", "read1"] and len(batch) == len(reads)
