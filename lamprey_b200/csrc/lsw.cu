@@ -106,8 +106,6 @@ struct lsw_ctx {
     int64_t bb_total = 0, bb1_total = 0;
     bool use_bb1 = false;        // second-level block bests: built when the reads are long enough for slices to span whole groups
     DevBuf d_blockbest, d_bb_off, d_bb1, d_bb1_off, d_nseg, d_segpos, d_res_s, d_seg_s, d_class_of, d_kt;
-    TaskBuf segs;
-    DevBuf d_seg_skip;
     int32_t allowed_overlap = -1;
     int64_t n_hits = 0;
     std::vector<Timed> timed;
@@ -481,10 +479,8 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         R.blockbest = ctx->d_blockbest.as<uint32_t>(); R.bb_off = ctx->d_bb_off.as<int64_t>(); R.bb_total = ctx->bb_total;
         if (ctx->use_bb1) { R.bb1 = ctx->d_bb1.as<uint32_t>(); R.bb1_off = ctx->d_bb1_off.as<int64_t>(); R.bb1_total = ctx->bb1_total; }
         CK(ctx->d_nseg.ensure((size_t)(n + 1) * 4)); CK(ctx->d_segpos.ensure((size_t)(n + 1) * 4));
-        CK(ctx->segs.ensure((size_t)2 * n, false)); CK(ctx->d_seg_skip.ensure((size_t)2 * n));
         CK(ctx->d_res_s.ensure((size_t)2 * n * sizeof(int2))); CK(ctx->d_seg_s.ensure((size_t)(ctx->nseq + 1) * 8));
         R.nseg = ctx->d_nseg.as<int32_t>(); R.segpos = ctx->d_segpos.as<int32_t>();
-        R.s = ctx->segs.view(); R.s.skip = ctx->d_seg_skip.as<uint8_t>();
         CK(ctx->d_kt.ensure((size_t)2 * n * sizeof(KTask)));
         R.s_kt = ctx->d_kt.as<KTask>(); R.roff = ctx->d_roff.as<int64_t>();
         k_plan_segments<<<grid_for(n + 1, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(R);
@@ -497,7 +493,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             R, ctx->d_seg[segi].as<int64_t>(), ctx->d_seg_s.as<int64_t>(), ctx->nseq);
         CK(cudaGetLastError());
         if (cnt) cnt->other_launches += 4;
-        P.t = R.s; P.kt = ctx->d_kt.as<KTask>(); P.seg = ctx->d_seg_s.as<int64_t>(); P.res = ctx->d_res_s.as<int2>();
+        P.t = TaskArrays(); P.kt = ctx->d_kt.as<KTask>(); P.seg = ctx->d_seg_s.as<int64_t>(); P.res = ctx->d_res_s.as<int2>();
         P.push_cands = 0; P.count_ref = 0; P.block_steps = SEG_BLOCK;
     }
     {
@@ -631,8 +627,8 @@ void lsw_destroy(lsw_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); ctx->d_cand_rec[c].release(); }
     ctx->d_nfallback.release();
-    ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release(); ctx->segs.release();
-    for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_bb1, &ctx->d_bb1_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_seg_skip, &ctx->d_kt}) b->release();
+    ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release();
+    for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_bb1, &ctx->d_bb1_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_kt}) b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

@@ -236,19 +236,15 @@ void emu_round(Emu& E, TraceParams T) {
     for (int64_t t = 0; t < n; t++)
         segpos[t + 1] = segpos[t] + plan_of(R, t).nseg;
     const int64_t ns = segpos[n];
-    std::vector<int32_t> s_read(ns), s_a(ns), s_b(ns);
-    std::vector<int16_t> s_seq(ns);
-    std::vector<uint8_t> s_skip(ns);
     std::vector<int2> res_s((size_t)ns, make_int2(0, 0));
     std::vector<int64_t> seg_s(E.nseq + 1);
     for (int s = 0; s <= E.nseq; s++) seg_s[s] = segpos[E.seg[s]];
     R.segpos = segpos.data();
-    R.s.read = s_read.data(); R.s.a = s_a.data(); R.s.b = s_b.data(); R.s.seq = s_seq.data(); R.s.skip = s_skip.data();
     std::vector<KTask> s_kt((size_t)ns);
     R.s_kt = s_kt.data(); R.roff = E.roff.data();
     for (int64_t t = 0; t < n; t++) fill_segments(R, t);
     ScoreParams PS = P;
-    PS.t = R.s; PS.kt = s_kt.data(); PS.seg = seg_s.data(); PS.res = res_s.data(); PS.push_cands = 0; PS.count_ref = 0; PS.block_steps = SEG_BLOCK;
+    PS.t = TaskArrays(); PS.kt = s_kt.data(); PS.seg = seg_s.data(); PS.res = res_s.data(); PS.push_cands = 0; PS.count_ref = 0; PS.block_steps = SEG_BLOCK;
     for (int s = 0; s < E.nseq; s++) {
         if (seg_s[s + 1] == seg_s[s]) continue;
         std::vector<uint32_t> none;

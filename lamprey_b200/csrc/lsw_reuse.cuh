@@ -68,7 +68,6 @@ struct ReuseParams {
     int32_t match, g, enable;
     int32_t* nseg;               // plan: segments per task (scanned into segpos)
     const int32_t* segpos;       // [n + 1]
-    TaskArrays s;                // segment list K1 runs on (s.skip set)
     KTask* s_kt;                 // its start descriptors
     const int64_t* roff;         // [n_reads] byte offset of each read in codes
     const int2* res_s;           // K1 results per segment
@@ -94,18 +93,16 @@ LSW_HD SegPlan plan_of(const ReuseParams& R, int64_t t) {
                      R.blockbest ? R.blockbest + (size_t)q * R.bb_total + R.bb_off[R.t.read[t]] : nullptr);
 }
 
+// K1 needs nothing but the start descriptor of a segment (its results go to res_s[segment], the task list is not read
+// in segment mode), so that is all that is written.
 LSW_HD void fill_segments(const ReuseParams& R, int64_t t) {
-    const int a = R.t.a[t], b = R.t.b[t], q = R.t.seq[t];
+    const int a = R.t.a[t], b = R.t.b[t];
     const SegPlan p = plan_of(R, t);
     const int64_t i = R.segpos[t];
-    R.s.read[i] = R.t.read[t]; R.s.seq[i] = (int16_t)q; R.s.skip[i] = 0;
-    R.s.a[i] = a; R.s.b[i] = p.split ? p.hb : b;
     const int64_t r0 = R.roff[R.t.read[t]];
-    KTask k; k.p0 = r0 + a; k.len = R.s.b[i] - a; k.skip = 0;
+    KTask k; k.p0 = r0 + a; k.len = (p.split ? p.hb : b) - a; k.skip = 0;
     R.s_kt[i] = k;
     if (p.split && p.tail) {
-        R.s.read[i + 1] = R.t.read[t]; R.s.seq[i + 1] = (int16_t)q; R.s.skip[i + 1] = (uint8_t)p.skip;
-        R.s.a[i + 1] = p.ts; R.s.b[i + 1] = b;
         k.p0 = r0 + p.ts; k.len = b - p.ts; k.skip = p.skip;
         R.s_kt[i + 1] = k;
     }
