@@ -4,8 +4,10 @@
 //   lsw_align_tasks  <->  swalign.LocalAlignment.align(ref, query)        (/root/reference/lamprey.py:563)
 //   lsw_find_all     <->  findAllPrimerAlignments / findPrimerAlignments  (/root/reference/lamprey.py:596-645, 699-733)
 // The recursion of findPrimerAlignments runs on the device as level-synchronous rounds:
-//   round k:  K1 (score + arg-max of every task)  ->  K2 (traceback, hit test, left/right children)
-//             ->  scan + scatter of the children into the task list of round k+1.
+//   round 0:  K1 (score + arg-max of every whole read, block bests stored)  ->  K2 (traceback, hit test, children)
+//   round k:  plan / fill the head + tail segments of every child slice  ->  K1 on the segments  ->  merge with the
+//             stored block bests (lsw_reuse.cuh)  ->  K2
+//   each followed by a scan + scatter of the children into the task list of round k+1.
 // No CPU fallback exists: every entry point needs the CUDA device the context was created on.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>

@@ -13,18 +13,19 @@
 //
 // Two kernels:
 //
-//  k_trace_fast  (every candidate)  VALUES ONLY on a short window W1 = 3*max_row - score + 8
-//      columns, one byte per cell in scratch; the walk then evaluates the op rule LAZILY, only
-//      at the cells it visits, and proves each decision exact with a per-cell certificate:
+//  k_trace_fast  (every candidate)  VALUES ONLY on a short window of W1 = max_row + (M max_row - score)/g + SLACK
+//      columns (trace_window_fast), H modulo 16 per cell in scratch; the walk then evaluates the op rule
+//      LAZILY, only at the cells it visits, and every decision it takes is exact:
 //        * a windowed value Hw(r,c) can only be too small if the true optimal path into the cell
 //          starts left of the window; such a path spans at most r + (M*r - h)/g columns, so
 //          c - c0 >= r + (M*r - Hw - 1)/g  =>  Hw == H                      ("certified");
-//        * a windowed TIE (H == L - g etc.) is always a true tie (Hw <= H <= the tying value),
-//          and makes the neighbour's windowed value exact; only a windowed NON-tie needs the
-//          neighbour certified;
+//        * the window is long enough that the start cell's certificate covers every cell the walk
+//          can consult (see trace_slack), so it is checked once, at the start;
+//        * the walker knows the value of the cell it stands on and neighbouring values differ from
+//          it by less than 16, so the stored nibbles decide every tie exactly (nibble_walk_ok);
 //        * the run flags ("left is a 'd' cell") are obtained by evaluating the same rule at
 //          the neighbour, recursively, within an evaluation budget.
-//      Anything it cannot prove (uncertified neighbour, budget exhausted, window too short) is
+//      Anything it cannot prove (certificate fails, budget exhausted, window too short) is
 //      pushed to a fallback list -- never guessed.
 //
 //  k_trace_full  (fallback list)  the op rule for every cell of a window that is long enough
