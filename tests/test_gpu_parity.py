@@ -472,3 +472,25 @@ def test_seed_fastq_one_file_one_batch(engine, tmp_path):
     gold = load_seed_golden("50", "H33", 0.75)
     assert np.array_equal(hits_matrix(batch.hits), gold["hits"])
     assert names[:2] == ["read0", "read1"] and len(batch) == len(reads)
+
+
+def test_hit_buffer_overflow_is_reported_and_retried(engine):
+    # a hit buffer that is too small: the C ABI reports LSW_E_OVERFLOW with the number of hits needed (nothing is
+    # written past the buffer), the Python shim enlarges the buffer and runs again
+    import ctypes
+    from lamprey_b200 import _native
+    reads = load_reads("50")
+    seqs = _seqs("H33")
+    gold = load_seed_golden("50", "H33", 0.75)
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(seqs)
+    engine.upload_read_list(reads)
+    lib, h = engine._lib, engine._h
+    assert lib.lsw_set_hit_capacity(h, 16) == 0
+    n = ctypes.c_int64(0)
+    cnt = np.zeros(1, _native.COUNTERS_DT)
+    rc = lib.lsw_find_all(h, 0.75, ctypes.byref(n), cnt.ctypes.data_as(ctypes.c_void_p))
+    assert rc == _native.LSW_E_OVERFLOW and n.value == len(gold["hits"])
+    hits = engine.find_all(0.75)                       # still 16: overflows once more, then retried with room
+    assert np.array_equal(hits_matrix(hits), gold["hits"])
+    assert lib.lsw_set_hit_capacity(h, 0) == 0         # back to the default sizing
