@@ -142,6 +142,8 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
         c.res_x = T.res[t].x; c.col = T.res[t].y; c.t = t;
     }
     TraceParams TR = T;
+    static uint8_t dtab[128];
+    for (int k = 0; k < 128; k++) dtab[k] = decision_entry(k);
     TR.cand_rec = recs.data();
     for (size_t i = 0; i < cand.size(); i += 2) {
         const int t0 = (int)cand[i], t1 = i + 1 < cand.size() ? (int)cand[i + 1] : -1;
@@ -152,9 +154,9 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
             if (t1 >= 0) trace_full_task<NR2>(T, t1, 0);
         } else {
             if (T.mode == 1)
-                L.template run_pair<true>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
+                L.template run_pair<true>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
             else
-                L.template run_pair<false>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
+                L.template run_pair<false>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
         }
     }
 }

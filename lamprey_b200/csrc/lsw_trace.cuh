@@ -278,6 +278,24 @@ LSW_HD void trace_full_task(const TraceParams& P, const int t, const int64_t slo
 //          neighbouring values differ from it by less than 16 (see nibble_walk_ok), so the nibbles decide
 //          every tie exactly.  A cell needs the unit of its own column and of the column to the left: the
 //          walker keeps both and, because it moves one cell at a time, loads about one new unit per step.
+// swalign's op rule for one cell evaluation of the walk, tabulated.  idx: bits 0-1 state (0 fresh, 1 left's op known, 2 up's op
+// known), bit 2 / 3 the known op is 'd' / 'i', bits 4-6 the ties with left / up / diagonal.  Entry: bits 0-1 the cell's op
+// (0: not decided yet), bit 2 / 3 descend to the left / upper neighbour first, bit 4 no tie at all (never, for an exact cell),
+// bit 5 / 6 the op is 'd' / 'i' (what the asking cell will look at).
+LSW_HD uint8_t decision_entry(int idx) {
+    const int state = idx & 3;
+    const bool retD = (idx & 4) != 0, retI = (idx & 8) != 0, tieL = (idx & 16) != 0, tieU = (idx & 32) != 0, tieM = (idx & 64) != 0;
+    const bool s0 = state == 0, s1 = state == 1;
+    const bool pushL = s0 && tieL && (tieU || tieM);          // need left's op (the left value is exact because of the tie)
+    const bool pushU = (s0 && !tieL && tieU && tieM) || (s1 && !retD && tieU);
+    const bool notie = s0 && !tieL && !tieU && !tieM;
+    const int res0 = tieL ? OPC_D : (tieU ? OPC_I : OPC_M);
+    const int res1 = retD ? OPC_D : (tieM ? OPC_M : OPC_D);
+    const int res2 = retI ? OPC_I : (tieM ? OPC_M : (tieL ? OPC_D : OPC_I));
+    const int res = (pushL || pushU) ? 0 : (s0 ? res0 : (s1 ? res1 : res2));
+    return (uint8_t)(res | (pushL ? 4 : 0) | (pushU ? 8 : 0) | (notie ? 16 : 0) | (res == OPC_D ? 32 : 0) | (res == OPC_I ? 64 : 0));
+}
+
 #if defined(LSW_EMU_STATS)
 static unsigned long long g_walk_iters = 0, g_walks = 0, g_fill_steps = 0;
 static unsigned long long g_extra_hist[64] = {0}, g_ncols_sum = 0;   // columns a walk touched beyond max_row; window columns
@@ -322,7 +340,8 @@ struct TraceLane {
         const uint8_t* qc; const uint32_t* ref4; int rlead;
         int score, c0;
         // state
-        int r, cl, hv, depth, ret, last, state, budget;   // hv: H of the cell (r, cl)
+        int r, cl, hv, depth, retc, last, state, budget;  // hv: H of the cell (r, cl); retc: 4 / 8 if the op just returned is 'd' / 'i'
+        const uint8_t* dtab;
         uint32_t mv;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
         uint32_t st;                  // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
         bool failed, first_cell;
@@ -332,9 +351,10 @@ struct TraceLane {
 
         // false: nothing to walk (or the start certificate fails: see `failed`)
         LSW_HD bool init(const TraceParams& P, const TaskView& v, int c0_, int ncols, int first, int h, int64_t slot,
-                         const uint8_t* qcodes) {
+                         const uint8_t* qcodes, const uint8_t* table) {
+            dtab = table;
             failed = false; first_cell = true;
-            depth = last = state = 0; ret = OPC_NONE; mv = 0; st = 0;
+            depth = last = state = 0; retc = 0; mv = 0; st = 0;
             A = B = C = 0u; tagA = tagB = tagC = tagR = -1; rw = 0;
             scr0 = P.scratch;                                     // 32-bit index arithmetic: the host keeps the scratch under 2^31 words
             base = 4u * (uint32_t)slot + (uint32_t)h;
@@ -403,24 +423,20 @@ struct TraceLane {
             const int pu1 = pc > 0 ? pc - 1 : 0;                     // byte of the row above (i > 0 implies pc >= 1)
             const bool tieU = (i > 0) & (((nib(A, pu1) - g - hv) & 15) == 0);
             const bool tieM = inner ? (((nib(B, pu1) + sub - hv) & 15) == 0) : (hv == sub);
-            const bool s0 = state == 0, s1 = state == 1;
+            const bool s0 = state == 0;
             if (depth == 0 && s0 && hv == 0) return false;           // path ends at the first zero cell
             budget -= s0 ? 1 : 0;
-            const bool retD = ret == OPC_D, retI = ret == OPC_I;
-            const bool pushL = s0 & tieL & (tieU | tieM);          // need left's op (left value is hv + g > 0, exact because of the tie)
-            const bool pushU = (s0 & !tieL & tieU & tieM) | (s1 & !retD & tieU);
-            const bool push = pushL | pushU;
+            // the op rule as a table over (state, op returned by the neighbour, the three ties): see decision_entry()
+            const int e = dtab[state | retc | (tieL ? 16 : 0) | (tieU ? 32 : 0) | (tieM ? 64 : 0)];
+            const int res = e & 3;
+            const bool pushL = (e & 4) != 0, pushU = (e & 8) != 0, push = (e & 12) != 0;
             // rare exits: the stored nibble disagrees with the tracked value (e.g. window too short for the best cell);
             // a cell next to the artificial left boundary (its left / diagonal value is unknown); evaluation budget or
             // nesting limit; no tie at all (cannot happen for an exact cell)
             const bool bad = (((nib(A, pc) - hv) & 15) != 0) | ((cl <= 1) & (c0 > 0)) | (budget < 0) |
-                             (s0 & !tieL & !tieU & !tieM) | (push & (depth + 1 >= MAXD));
+                             ((e & 16) != 0) | (push & (depth + 1 >= MAXD));
             if (bad) { failed = true; return false; }
             first_cell = false;
-            const int res0 = tieL ? OPC_D : (tieU ? OPC_I : OPC_M);
-            const int res1 = retD ? OPC_D : (tieM ? OPC_M : OPC_D);
-            const int res2 = retI ? OPC_I : (tieM ? OPC_M : (tieL ? OPC_D : OPC_I));
-            const int res = s0 ? res0 : (s1 ? res1 : res2);
             const bool isret = !push & (depth > 0);                  // return to the cell that asked
             const bool isres = !push & (depth == 0);                 // a path cell is resolved
             const int up1 = (int)(mv & 1u);
@@ -430,7 +446,7 @@ struct TraceLane {
             st = push ? ((st << 2) | (pushU ? 2u : 1u)) : (isret ? st >> 2 : st);
             mv = push ? ((mv << 1) | (pushU ? 1u : 0u)) : (isret ? mv >> 1 : mv);
             depth += push ? 1 : (isret ? -1 : 0);
-            ret = push ? ret : res;
+            retc = push ? retc : ((e >> 3) & 12);
             r += dr; cl += dc;
             hv += push ? g : (isret ? -g : (res == OPC_M ? -sub : g));
             const bool ismatch = (res == OPC_M) & (sub == P.match);
@@ -453,7 +469,7 @@ struct TraceLane {
 
     // fill + walk for the pair of candidate records (ci0, ci1) of sequence q; ci1 may be -1.  fb(t): push a task to the fallback list.
     template <bool OPS, class Fallback>
-    LSW_HD void run_pair(const TraceParams& P, const U2* prof, const uint8_t* qcodes, int q, int ci0, int ci1, int64_t slot, Fallback fb) {
+    LSW_HD void run_pair(const TraceParams& P, const U2* prof, const uint8_t* qcodes, const uint8_t* dtab, int q, int ci0, int ci1, int64_t slot, Fallback fb) {
         Half hf[2];
         const int ci[2] = {ci0, ci1};
 #pragma unroll
@@ -573,7 +589,7 @@ struct TraceLane {
 #if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
                 g_min_cl = ncols; g_ncols_sum += ncols;
 #endif
-                if (w.init(P, v, c0, ncols, n - ncols, h, slot, qcodes))
+                if (w.init(P, v, c0, ncols, n - ncols, h, slot, qcodes, dtab))
                     while (w.step(P, po)) { }
 #if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
                 { int e = (ncols - g_min_cl) - v.row; e = e < -20 ? -20 : (e > 40 ? 40 : e); g_extra_hist[e + 20]++; }
@@ -653,6 +669,8 @@ k_trace_fast(const TraceParams P) {
     long long* seg_lo = reinterpret_cast<long long*>(smem_raw + trace_prof_bytes<NR>());
     long long* seg_hi = seg_lo + 256;
     uint8_t* qsm = reinterpret_cast<uint8_t*>(seg_hi + 256) + warp * QSTRIDE;          // the warp's query codes
+    uint8_t* dtab = reinterpret_cast<uint8_t*>(seg_hi + 256) + (TRACE_THREADS / 32) * QSTRIDE;
+    dtab[threadIdx.x] = decision_entry((int)threadIdx.x);                              // 128 threads, 128 entries
     for (int i = threadIdx.x; i < P.n_class_seqs; i += blockDim.x) {
         const int q = P.class_seqs[i];
         seg_lo[i] = lower_bound_u16(P.cand_key, ncand, (uint32_t)q << 8);
@@ -692,7 +710,7 @@ k_trace_fast(const TraceParams P) {
             } else if (active) {
                 const int c0 = (int)P.cand[lo + i];
                 const int c1 = (i + 1 < cnt) ? (int)P.cand[lo + i + 1] : -1;
-                L.template run_pair<OPS>(P, prof, qsm, q, c0, c1, slot, [&](int t) {
+                L.template run_pair<OPS>(P, prof, qsm, dtab, q, c0, c1, slot, [&](int t) {
                     const unsigned long long j = atomicAdd(P.nfallback, 1ull);
                     P.fallback[j] = (uint32_t)t;
                 });
@@ -703,7 +721,7 @@ k_trace_fast(const TraceParams P) {
 }
 
 template <int NR>
-inline size_t trace_smem_bytes() { return trace_prof_bytes<NR>() + 2 * 256 * sizeof(long long) + (TRACE_THREADS / 32) * QSTRIDE; }
+inline size_t trace_smem_bytes() { return trace_prof_bytes<NR>() + 2 * 256 * sizeof(long long) + (TRACE_THREADS / 32) * QSTRIDE + 128; }
 
 template <int NR>
 __global__ void __launch_bounds__(TRACE_THREADS)
