@@ -344,7 +344,7 @@ struct TraceLane {
         const uint8_t* dtab;
         uint32_t mv;                  // bit k: move that entered nesting level k (0 = left, 1 = up)
         uint32_t st;                  // 2 bits per level below the current one: 1 waiting for left's op, 2 for up's
-        bool failed, first_cell;
+        bool failed;
         // operands: the units of column cl (A) and cl - 1 (B) that hold rows r-1 and r-2, four read codes
         uint32_t A, B, C; int tagA, tagB, tagC;   // tag = 16 * column + unit, -1 = empty; C: lookahead unit
         uint32_t rw; int tagR;
@@ -353,7 +353,7 @@ struct TraceLane {
         LSW_HD bool init(const TraceParams& P, const TaskView& v, int c0_, int ncols, int first, int h, int64_t slot,
                          const uint8_t* qcodes, const uint8_t* table) {
             dtab = table;
-            failed = false; first_cell = true;
+            failed = false;
             depth = last = state = 0; retc = 0; mv = 0; st = 0;
             A = B = C = 0u; tagA = tagB = tagC = tagR = -1; rw = 0;
             scr0 = P.scratch;                                     // 32-bit index arithmetic: the host keeps the scratch under 2^31 words
@@ -389,9 +389,9 @@ struct TraceLane {
             const int i = r - 1, u = unit_of(i);
             {   // operands: from the cached units, else from scratch
                 const int tA = 16 * cl + u, tB = cl > 1 ? tA - 16 : -2;
-                const bool hitA = (tagA == tA) | (tagB == tA) | (tagC == tA);
+                const bool hitA = (tagA == tA) | (tagB == tA);      // (the lookahead unit is two columns away: never this cell's)
                 const bool hitB = (tagA == tB) | (tagB == tB) | (tagC == tB) | (tB < 0);
-                uint32_t nA = tagA == tA ? A : (tagB == tA ? B : C);
+                uint32_t nA = tagA == tA ? A : B;
                 uint32_t nB = tagB == tB ? B : (tagA == tB ? A : C);
                 // word (column c, unit v) of this lane: base + (c * UPAIRS + v / 2) * COLW + 2 * (v % 2); the fast kernel's
                 // scratch rows are TRACE_THREADS lanes of 16 bytes
@@ -436,7 +436,6 @@ struct TraceLane {
             const bool bad = (((nib(A, pc) - hv) & 15) != 0) | ((cl <= 1) & (c0 > 0)) | (budget < 0) |
                              ((e & 16) != 0) | (push & (depth + 1 >= MAXD));
             if (bad) { failed = true; return false; }
-            first_cell = false;
             const bool isret = !push & (depth > 0);                  // return to the cell that asked
             const bool isres = !push & (depth == 0);                 // a path cell is resolved
             const int up1 = (int)(mv & 1u);
@@ -459,7 +458,7 @@ struct TraceLane {
         }
         // after the loop: false = the task must go to the fallback list
         LSW_HD bool finish(PathOutT<OPS>& po) const {
-            if (failed || first_cell) return false;
+            if (failed) return false;                                // (a started walk has evaluated at least its first cell)
             if (cl == 0 && c0 > 0 && r > 0) return false;            // ran into the artificial boundary
             po.q_pos = r;
             po.r_pos = c0 + cl;
