@@ -849,8 +849,13 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     }
 
     // block bests of round 0 for the child tasks: 4 B per BB_BLOCK columns per (read, sequence)
-    const bool reuse = ctx->reuse && !getenv("LSW_NO_REUSE");
-    if (reuse) CK(ctx->d_blockbest.ensure((size_t)std::max<int64_t>(1, ctx->bb_total) * ctx->nseq * 4));
+    bool reuse = ctx->reuse && !getenv("LSW_NO_REUSE");
+    // the block bests are an optimisation (4 B per 32 columns per sequence): without room for them every round simply
+    // aligns whole slices -- same results, more cells
+    if (reuse && ctx->d_blockbest.ensure((size_t)std::max<int64_t>(1, ctx->bb_total) * ctx->nseq * 4) != cudaSuccess) {
+        (void)cudaGetLastError();
+        reuse = false;
+    }
     int64_t n = n0;
     int round = 0;
     size_t dbg_from = 0;
