@@ -57,16 +57,20 @@ def gather_max_and_sum(t_local, sums, device="cuda"):
 _CPU = {}
 
 
-def _cpu_init(schema_path, n_names=None):
+def _cpu_init(schema_path, n_names=None, pure_python=False):
     import importlib.util
-    from oracle import build_cython
-    out = build_cython.build()
     mods = {}
-    for name in ("swalign_cy", "seeding_cy"):
-        so = [f for f in os.listdir(out) if f.startswith(name) and f.endswith(".so")][0]
-        spec = importlib.util.spec_from_file_location(name, os.path.join(out, so))
-        mods[name] = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mods[name])
+    if pure_python:      # the same two files, interpreted (SURVEY.md section 8d asks for this figure as well)
+        from oracle import swalign_ref, seeding_ref
+        mods = {"swalign_cy": swalign_ref, "seeding_cy": seeding_ref}
+    else:
+        from oracle import build_cython
+        out = build_cython.build()
+        for name in ("swalign_cy", "seeding_cy"):
+            so = [f for f in os.listdir(out) if f.startswith(name) and f.endswith(".so")][0]
+            spec = importlib.util.spec_from_file_location(name, os.path.join(out, so))
+            mods[name] = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mods[name])
     _CPU["sw"] = mods["swalign_cy"].LocalAlignment(mods["swalign_cy"].NucleotideScoringMatrix(2, -1))
     _CPU["seed"] = mods["seeding_cy"]
     _CPU["ps"] = mods["seeding_cy"].PrimerSet(schema_path)
@@ -81,12 +85,12 @@ def _cpu_seed(args):
     return len(hits), st.calls, st.cells
 
 
-def cpu_seed_sample(reads, thr, cores, pool=None, n_names=None):
+def cpu_seed_sample(reads, thr, cores, pool=None, n_names=None, pure_python=False):
     """-> (seconds, hits, calls, cells) for seeding `reads` on `cores` processes."""
     import multiprocessing as mp
     own = pool is None
     if own:
-        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(SCHEMA, n_names))
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(SCHEMA, n_names, pure_python))
         pool.map(_cpu_seed, [("ACGT" * 8, thr)] * cores)        # start-up (imports) outside the timing
     t0 = time.perf_counter()
     res = pool.map(_cpu_seed, [(r, thr) for r in reads], chunksize=1)
@@ -256,6 +260,11 @@ def main():
                         "sample": "first %d reads of the workload, Cython build of oracle/swalign_ref.py + "
                                   "seeding_ref.py (README.md:18-25 recipe), one process per core" % sample,
                         "_hits": hits_cpu, "_calls": calls_cpu, "_cells": cells_cpu, "_n": sample}
+        # the interpreted figure beside it: one read per core
+        dt_py, _, _, cells_py = cpu_seed_sample(reads[:cores], args.thr, cores, n_names=synth.SCHEMA_NAMES.get(args.workload),
+                                                pure_python=True)
+        cpu_baseline["pure_python"] = {"value": min(cores, len(reads)) / dt_py, "unit": "reads/s", "gcups": cells_py / dt_py / 1e9,
+                                       "sample": "first %d reads, oracle/swalign_ref.py + seeding_ref.py interpreted" % min(cores, len(reads))}
 
     import torch
     if not torch.cuda.is_available():
