@@ -25,6 +25,7 @@
 #include "lsw_common.cuh"
 #include "lsw_score.cuh"
 #include "lsw_trace.cuh"
+#include "lsw_band.cuh"
 #include "lsw_reuse.cuh"
 #include "intpeak.cuh"
 #include "lsw_host.hpp"
@@ -96,6 +97,7 @@ struct lsw_ctx {
     DevBuf d_ascii, d_offs_in, d_codes, d_roff, d_rlen, d_order, d_order_tmp, d_len_tmp[2];
 
     TaskBuf tb[2], child;
+    DevBuf d_fb2[NCLASS], d_fb2cnt, d_head2;
     DevBuf d_fallback[NCLASS], d_nfallback, d_cand_key[NCLASS], d_cand_sorted[NCLASS], d_cand_key_sorted[NCLASS], d_cand_rec[NCLASS];
     DevBuf d_res, d_seg[2], d_head, d_cand[NCLASS], d_ncand, d_counters, d_child_flag, d_pos,
            d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_nhits, d_keys[2], d_vals[2], d_err,
@@ -352,36 +354,51 @@ int launch_score_class(lsw_ctx* ctx, int c, const ScoreParams& P, int64_t n) {
     }
 }
 
+#ifndef LSW_BAND_WORDS
+#define LSW_BAND_WORDS 2       // 16-row band (lsw_band.cuh): ~1 % of the walks leave it and take the full-window kernel; 8 rows: ~19 %
+#endif
+
 template <int NR, int NR2>
 int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
-    // short-window kernel over every candidate of the class: one lane per PAIR of candidates
-    const size_t smem = trace_smem_bytes<NR>();
+    // tier 1, every candidate of the class: one lane per PAIR of candidates, window bands in shared memory (lsw_band.cuh)
+    constexpr int BW = LSW_BAND_WORDS;
+    const size_t smem = BandSmem<NR, BW>::total;
     // find_all never needs the op list of a path, align_tasks (CIGAR output) does
-    auto kernel = P.mode == 1 ? k_trace_fast<NR, true> : k_trace_fast<NR, false>;
+    auto kernel = P.mode == 1 ? k_trace_band<NR, BW, true> : k_trace_band<NR, BW, false>;
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TRACE_THREADS, smem));
     if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
     if (getenv("LSW_K2_BLOCKS_PER_SM")) occ = std::max(1, std::min(occ, atoi(getenv("LSW_K2_BLOCKS_PER_SM"))));
     const int blocks = grid_for((n_class_tasks + 1) / 2, TRACE_THREADS, ctx->num_sms * occ);
-    const int64_t threads = (int64_t)blocks * TRACE_THREADS;
+    // tier 2, the ~1 % whose walk left the band: the whole window in a global scratch (k_trace_fast); a small grid, the list is short
+    const size_t smem1 = trace_smem_bytes<NR>();
+    auto kernel1 = P.mode == 1 ? k_trace_fast<NR, true> : k_trace_fast<NR, false>;
+    CK(cudaFuncSetAttribute(kernel1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    const int blocks1 = grid_for((n_class_tasks + 1) / 2, TRACE_THREADS, ctx->num_sms * 2);
+    const int64_t threads1 = (int64_t)blocks1 * TRACE_THREADS;
     const int64_t Wf = trace_window_fast_max(qmax, ctx->match, ctx->g);
-    // full-window kernel over the (normally empty) fallback list: one thread per task
+    constexpr int UNITS = TraceLane<NR>::UPAIRS;         // 16 bytes per (window column, unit pair, lane): both tasks of the lane
+    // tier 3, what even that could not prove: one thread per task, 2-bit ops of a window that is exact a priori
     int occ2 = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_trace_full<NR2>, TRACE_THREADS, 0));
     if (occ2 < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
     const int blocks2 = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * std::min(occ2, 2));
     const int64_t threads2 = (int64_t)blocks2 * TRACE_THREADS;
     const int64_t W = trace_window_full(qmax, ctx->match, ctx->g);
-    constexpr int UNITS = TraceLane<NR>::UPAIRS;         // 16 bytes per (window column, unit pair, lane): both tasks of the lane
-    if ((size_t)threads2 * (size_t)W * (NR2 / 16) >= (1ull << 31) || (size_t)threads * (size_t)(Wf + 4) * UNITS * 4 >= (1ull << 31))
+    if ((size_t)threads2 * (size_t)W * (NR2 / 16) >= (1ull << 31) || (size_t)threads1 * (size_t)(Wf + 4) * UNITS * 4 >= (1ull << 31))
         return fail(ctx, LSW_E_INTERNAL, "traceback scratch exceeds the 32-bit index range");
-    const size_t need = std::max((size_t)threads * (size_t)(Wf + 4) * UNITS * 16, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
+    const size_t need = std::max((size_t)threads1 * (size_t)(Wf + 4) * UNITS * 16, (size_t)threads2 * (size_t)W * (NR2 / 16) * 4);
     CK(ctx->d_scratch.ensure(need));
     P.scratch = ctx->d_scratch.as<uint32_t>();
-    P.scratch_stride = TRACE_THREADS;
-    P.scratch_block_words = (int64_t)(Wf + 4) * UNITS * TRACE_THREADS;
     kernel<<<blocks, TRACE_THREADS, smem, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    TraceParams P1 = P;
+    P1.head = ctx->d_head2.as<unsigned long long>();
+    P1.fb_in = P.fb2; P1.fb_in_cnt = P.fb2_cnt;
+    P1.scratch_stride = TRACE_THREADS;
+    P1.scratch_block_words = (int64_t)(Wf + 4) * UNITS * TRACE_THREADS;
+    kernel1<<<blocks1, TRACE_THREADS, smem1, ctx->stream>>>(P1);
     CK(cudaGetLastError());
     P.scratch_stride = threads2;
     k_trace_full<NR2><<<blocks2, TRACE_THREADS, 0, ctx->stream>>>(P);
@@ -429,6 +446,7 @@ void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {
     T.res = ctx->d_res.as<int2>();
     T.qcodes = ctx->d_qcodes.as<uint8_t>();
     T.qlen = ctx->d_qlen.as<int32_t>();
+    T.cand_ok = ctx->d_cand_ok.as<uint8_t>();
     T.match = ctx->match; T.mismatch = ctx->mismatch; T.g = ctx->g;
     T.errflag = ctx->d_err.as<int32_t>();
     T.all_fallback = nibble_walk_ok(ctx->match, ctx->mismatch, ctx->g) ? 0 : 1;
@@ -445,13 +463,16 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
     CK(cudaMemsetAsync(ctx->d_ncand.p, 0, NCLASS * 8, ctx->stream));
     CK(ctx->d_nfallback.ensure(NCLASS * 8));
     CK(cudaMemsetAsync(ctx->d_nfallback.p, 0, NCLASS * 8, ctx->stream));
+    CK(ctx->d_fb2cnt.ensure((size_t)ctx->nseq * 8)); CK(ctx->d_head2.ensure((size_t)ctx->nseq * 8));
+    CK(cudaMemsetAsync(ctx->d_fb2cnt.p, 0, (size_t)ctx->nseq * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_head2.p, 0, (size_t)ctx->nseq * 8, ctx->stream));
     int64_t ncls[NCLASS];
     int qmax[NCLASS];
     for (int c = 0; c < NCLASS; c++) {
         ncls[c] = 0; qmax[c] = 0;
         for (int s : ctx->class_seqs[c]) { ncls[c] += h_seg[s + 1] - h_seg[s]; qmax[c] = std::max(qmax[c], ctx->qlen[s]); }
         if (ncls[c]) {
-            CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4)); CK(ctx->d_fallback[c].ensure((size_t)ncls[c] * 4));
+            CK(ctx->d_cand[c].ensure((size_t)ncls[c] * 4)); CK(ctx->d_fallback[c].ensure((size_t)ncls[c] * 4)); CK(ctx->d_fb2[c].ensure((size_t)ncls[c] * 4));
             CK(ctx->d_cand_sorted[c].ensure((size_t)ncls[c] * 4));
             CK(ctx->d_cand_rec[c].ensure((size_t)ncls[c] * sizeof(CandRec)));
             CK(ctx->d_cand_key[c].ensure((size_t)ncls[c] * 2)); CK(ctx->d_cand_key_sorted[c].ensure((size_t)ncls[c] * 2));
@@ -554,11 +575,12 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
             T.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
             T.n_class_seqs = (int)ctx->class_seqs[c].size();
             T.ncand = ctx->d_ncand.as<unsigned long long>() + c;
+            T.fb2 = ctx->d_fb2[c].as<uint32_t>(); T.fb2_cnt = ctx->d_fb2cnt.as<unsigned long long>();
             T.fallback = ctx->d_fallback[c].as<uint32_t>();
             T.nfallback = ctx->d_nfallback.as<unsigned long long>() + c;
             int rc = launch_trace_class(ctx, c, T, ncls[c], qmax[c]);
             if (rc) return rc;
-            if (cnt) cnt->trace_launches += 2;
+            if (cnt) cnt->trace_launches += 3;
         }
     }
     return LSW_OK;
@@ -627,8 +649,8 @@ void lsw_destroy(lsw_ctx* ctx) {
                       &ctx->d_keys[1], &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_err, &ctx->d_results,
                       &ctx->d_cigar, &ctx->d_ncigar};
     for (DevBuf* b : bufs) b->release();
-    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); ctx->d_cand_rec[c].release(); }
-    ctx->d_nfallback.release();
+    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); ctx->d_cand_rec[c].release(); ctx->d_fb2[c].release(); }
+    ctx->d_nfallback.release(); ctx->d_fb2cnt.release(); ctx->d_head2.release();
     ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release();
     for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_bb1, &ctx->d_bb1_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_kt}) b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);

@@ -140,7 +140,7 @@ struct ScoreParams {
     const int32_t*  qlen;     // [n_seq]
     const int32_t*  class_seqs; // sequences served by this launch (same register-row class)
     int             n_class_seqs;
-    const uint8_t*  cand_ok;  // [n_seq][128] 1 if a task with that score can still pass the hit test
+    const uint8_t*  cand_ok;  // [n_seq][128] non-zero if a task with that score can still pass the hit test (lsw_host.hpp)
     uint32_t*       cand;     // out: tasks that need a traceback
     uint16_t*       cand_key; // out: sequence << 8 | K2 window length (sort key; preset to 0xFFFF)
     CandRec*        cand_rec; // out: the candidates themselves; cand[] holds indices into this array
@@ -165,6 +165,7 @@ struct TraceParams {
     const int2*     res;
     const uint8_t*  qcodes;
     const int32_t*  qlen;
+    const uint8_t*  cand_ok;      // [n_seq][128] 0, or 1 + the most errors a passing alignment with that score can have (lsw_host.hpp)
     const uint32_t* cand;         // candidate task ids, sorted by (sequence, window length)
     const uint16_t* cand_key;     // their sort keys: sequence << 8 | window length (0xFFFF = padding)
     const CandRec*  cand_rec;     // candidate records, indexed by cand[]
@@ -172,7 +173,12 @@ struct TraceParams {
     unsigned long long* head;     // [n_seq] next unclaimed candidate of each sequence
     const int32_t*  class_seqs;   // sequences of this launch's register-row class
     int             n_class_seqs;
-    uint32_t*       fallback;     // tasks the short-window kernel could not prove exact
+    // tiers: k_trace_band (shared-memory band) -> k_trace_fast (whole window in a global scratch) -> k_trace_full
+    uint32_t*       fb2;          // out of the band kernel: candidate records that left the band, per sequence at the sequence's offset in cand[]
+    unsigned long long* fb2_cnt;  // [n_seq] their number
+    const uint32_t* fb_in;        // in of k_trace_fast: null = every candidate (cand[]), else the band kernel's fb2 / fb2_cnt
+    const unsigned long long* fb_in_cnt;
+    uint32_t*       fallback;     // tasks the short-window kernels could not prove exact
     unsigned long long* nfallback;
     uint32_t*       scratch;      // fast: H bytes, [block][window col][unit][thread] x 16 B; full: op bits, [window col][word][thread]
     int64_t         scratch_stride;   // words between consecutive (column, word) rows: threads of a block (fast) / of the launch (full)

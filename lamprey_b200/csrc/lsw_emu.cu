@@ -16,6 +16,7 @@
 #include "lsw_common.cuh"
 #include "lsw_score.cuh"
 #include "lsw_trace.cuh"
+#include "lsw_band.cuh"
 #include "lsw_reuse.cuh"
 #include "lsw_host.hpp"
 
@@ -48,6 +49,8 @@ struct Emu {
     int64_t bb_total = 0, bb1_total = 0;
     std::vector<uint32_t> bb1;       // second-level block bests (always used by the emulation when reuse is on)
     unsigned long long comp_cells = 0;
+    int tiers = 1;                   // 1: band tiers of lsw_band.cuh (what the library runs); 0: the round-1 global-scratch kernel
+    unsigned long long tier2 = 0;    // candidates the 8-row band passed on to the 16-row band
 };
 
 bool setup(Emu& E, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
@@ -145,6 +148,15 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
     static uint8_t dtab[128];
     for (int k = 0; k < 128; k++) dtab[k] = decision_entry(k);
     TR.cand_rec = recs.data();
+    BandLane<NR, 2> B2;
+    std::vector<U2> prof_lex((size_t)NIDX * Lane::PROF_STRIDE);      // the band tiers fill with the lexicographic scores
+    {
+        ScoreParams PL = P;
+        PL.s_match = BandLane<NR, 2>::lex_match(T.match, T.g); PL.s_mis = BandLane<NR, 2>::lex_mis(T.mismatch, T.g);
+        ScoreLane<NR>::build_profile(PL, q, E.qlen[q], reinterpret_cast<uint32_t*>(prof_lex.data()), 0, 1);
+    }
+    std::vector<uint32_t> band2(BandLane<NR, 2>::WORDS_PER_LANE);
+    std::vector<int> tier2;
     for (size_t i = 0; i < cand.size(); i += 2) {
         const int t0 = (int)cand[i], t1 = i + 1 < cand.size() ? (int)cand[i + 1] : -1;
         E.counters[3] += t1 >= 0 ? 2 : 1;
@@ -152,12 +164,23 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
             E.fallbacks += t1 >= 0 ? 2 : 1;
             trace_full_task<NR2>(T, t0, 0);
             if (t1 >= 0) trace_full_task<NR2>(T, t1, 0);
-        } else {
+        } else if (E.tiers == 0) {     // the round-1 kernel: whole window in a global scratch
             if (T.mode == 1)
                 L.template run_pair<true>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
             else
                 L.template run_pair<false>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
+        } else {                       // what the library runs: 16-row band in shared memory (lsw_band.cuh) ...
+            auto fb1 = [&](int ci, int) { tier2.push_back(ci); };
+            if (T.mode == 1) B2.template run_pair<true>(TR, prof_lex.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, band2.data(), 1, fb1);
+            else B2.template run_pair<false>(TR, prof_lex.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, band2.data(), 1, fb1);
         }
+    }
+    E.tier2 += tier2.size();
+    for (size_t i = 0; i < tier2.size(); i += 2) {           // ... then the whole window in a global scratch, then the full window
+        const int c0 = tier2[i], c1 = i + 1 < tier2.size() ? tier2[i + 1] : -1;
+        auto fb2 = [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); };
+        if (T.mode == 1) L.template run_pair<true>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, c0, c1, 0, fb2);
+        else L.template run_pair<false>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, c0, c1, 0, fb2);
     }
 }
 
@@ -200,7 +223,7 @@ void emu_round(Emu& E, TraceParams T) {
     // one lane (slot 0): fast layout = rows of TRACE_THREADS x 16 B per (column, unit pair), at most 5 pairs; full layout = 4 words per column
     std::vector<uint4> scratch((size_t)std::max(trace_window_full(qmax, E.match, E.g), (trace_window_fast_max(qmax, E.match, E.g) + 4) * 5 * TRACE_THREADS) + 4);
     T.codes = E.codes.data(); T.roff = E.roff.data(); T.t = view(E); T.res = E.res.data();
-    T.qcodes = E.qcodes.data(); T.qlen = E.qlen.data();
+    T.qcodes = E.qcodes.data(); T.qlen = E.qlen.data(); T.cand_ok = E.cand_ok.data();
     T.match = E.match; T.mismatch = E.mismatch; T.g = E.g;
     T.scratch = reinterpret_cast<uint32_t*>(scratch.data()); T.scratch_stride = 1;
 
@@ -272,10 +295,11 @@ extern "C" {
 
 int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
                      const int32_t* qoffs, int match, int mismatch, int gap, double thr, lsw_hit* out, int64_t cap,
-                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds, traced, fallbacks, computed cells */, int force_full,
+                     int64_t* n_out, int64_t* counters /* tasks, cells, steps, rounds, traced, fallbacks, computed cells, tier-2 candidates */, int force_full,
                      int allowed_overlap, int reuse) {
     Emu E;
-    E.force_full = force_full != 0;
+    E.force_full = force_full == 1;          // force_full: 1 = every candidate through k_trace_full's logic, 2 = the round-1 global-scratch walker
+    E.tiers = force_full == 2 ? 0 : 1;
     E.reuse = reuse != 0;
     if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, match, mismatch, gap)) return LSW_E_UNSUPPORTED;
     build_cand_ok(nseq, E.qlen.data(), match, mismatch, E.g, thr, false, E.cand_ok);
@@ -328,11 +352,23 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
     fprintf(stderr, "[emu] mean window columns %.1f; columns touched beyond max_row (histogram -20..40):", (double)g_ncols_sum / (double)(g_walks ? g_walks : 1));
     for (int i = 0; i < 61; i++) if (g_extra_hist[i]) fprintf(stderr, " %d:%llu", i - 20, g_extra_hist[i]);
     fprintf(stderr, "\n");
+    for (int b = 1; b <= 2; b++)
+        fprintf(stderr, "[emu] band BW=%d: pruned %llu walks %llu failed %llu (%.3f %%) iterations %.1f per walk\n", b, g_band_pruned[b], g_band_walks[b], g_band_fail[b],
+                100.0 * (double)g_band_fail[b] / (double)(g_band_walks[b] ? g_band_walks[b] : 1), (double)g_band_iters[b] / (double)(g_band_walks[b] ? g_band_walks[b] : 1));
+    for (int b = 1; b <= 2; b++)
+        fprintf(stderr, "[emu] band BW=%d fail reasons: out-of-band %llu (low/path %llu low/nested %llu high/path %llu high/nested %llu) nibble %llu edge %llu budget %llu notie %llu depth %llu cert %llu\n", b,
+                g_band_why[b][0], g_band_out[b][0][0], g_band_out[b][0][1], g_band_out[b][1][0], g_band_out[b][1][1], g_band_why[b][1], g_band_why[b][2], g_band_why[b][3], g_band_why[b][4], g_band_why[b][5], g_band_cert[b]);
+    for (int b = 1; b <= 2; b++) {
+        fprintf(stderr, "[emu] band BW=%d completed walks: -dmin hist:", b); for (int i = 0; i < 12; i++) fprintf(stderr, " %llu", g_dmin[b][i]);
+        fprintf(stderr, "  dmax hist:"); for (int i = 0; i < 12; i++) fprintf(stderr, " %llu", g_dmax[b][i]);
+        fprintf(stderr, "  exit row hist:"); for (int i = 0; i < 16; i++) fprintf(stderr, " %llu", g_drow[b][i]);
+        fprintf(stderr, "\n");
+    }
     fprintf(stderr, "[emu] walks %llu iters %llu (%.1f per walk) fill steps %llu (%.1f per pair)\n", g_walks, g_walk_iters, (double)g_walk_iters / (double)(g_walks ? g_walks : 1), g_fill_steps, 2.0 * g_fill_steps / (double)(g_walks ? g_walks : 1));
 #endif
     if (errflag) return LSW_E_INTERNAL;
     if (n_out) *n_out = (int64_t)nhits;
-    if (counters) { counters[0] = E.counters[0]; counters[1] = E.counters[1]; counters[2] = E.counters[2]; counters[3] = round; counters[4] = E.counters[3]; counters[5] = E.fallbacks; counters[6] = (int64_t)E.comp_cells; }
+    if (counters) { counters[0] = E.counters[0]; counters[1] = E.counters[1]; counters[2] = E.counters[2]; counters[3] = round; counters[4] = E.counters[3]; counters[5] = E.fallbacks; counters[6] = (int64_t)E.comp_cells; counters[7] = (int64_t)E.tier2; }
     if ((int64_t)nhits > cap) return LSW_E_OVERFLOW;
     // (read, start, query) order
     std::sort(out, out + nhits, [](const lsw_hit& x, const lsw_hit& y) {
@@ -357,7 +393,8 @@ int lsw_emu_align_tasks(int64_t n_reads, const uint8_t* ascii, const int64_t* of
                         lsw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used, int force_full,
                         int64_t* fallbacks) {
     Emu E;
-    E.force_full = force_full != 0;
+    E.force_full = force_full == 1;          // force_full: 1 = every candidate through k_trace_full's logic, 2 = the round-1 global-scratch walker
+    E.tiers = force_full == 2 ? 0 : 1;
     if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, match, mismatch, gap)) return LSW_E_UNSUPPORTED;
     build_cand_ok(nseq, E.qlen.data(), match, mismatch, E.g, 0.0, true, E.cand_ok);
     E.seg.assign(nseq + 1, 0);

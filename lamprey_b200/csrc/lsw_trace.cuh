@@ -681,7 +681,8 @@ k_trace_fast(const TraceParams P) {
     for (int tried = 0; tried < P.n_class_seqs; ) {
         const int q = P.class_seqs[prefer];
         const long long lo = seg_lo[prefer];
-        const long long cnt = seg_hi[prefer] - lo;
+        const long long cnt = P.fb_in ? (long long)P.fb_in_cnt[q] : seg_hi[prefer] - lo;      // second tier: what the band kernel passed on
+        const uint32_t* list = (P.fb_in ? P.fb_in : P.cand) + lo;
         const long long hd0 = (long long)*((volatile unsigned long long*)&P.head[q]);
         if (hd0 >= cnt) { prefer = (prefer + 1) % P.n_class_seqs; tried++; continue; }
         tried = 0;
@@ -704,11 +705,11 @@ k_trace_fast(const TraceParams P) {
             if (active && P.all_fallback) {                       // scoring outside the nibble walk's range
                 for (int k = 0; k < 2 && i + k < cnt; k++) {
                     const unsigned long long j = atomicAdd(P.nfallback, 1ull);
-                    P.fallback[j] = (uint32_t)P.cand_rec[P.cand[lo + i + k]].t;
+                    P.fallback[j] = (uint32_t)P.cand_rec[list[i + k]].t;
                 }
             } else if (active) {
-                const int c0 = (int)P.cand[lo + i];
-                const int c1 = (i + 1 < cnt) ? (int)P.cand[lo + i + 1] : -1;
+                const int c0 = (int)list[i];
+                const int c1 = (i + 1 < cnt) ? (int)list[i + 1] : -1;
                 L.template run_pair<OPS>(P, prof, qsm, dtab, q, c0, c1, slot, [&](int t) {
                     const unsigned long long j = atomicAdd(P.nfallback, 1ull);
                     P.fallback[j] = (uint32_t)t;

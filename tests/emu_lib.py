@@ -29,13 +29,13 @@ def find_all(reads, seqs, thr, match=2, mismatch=-1, gap=-1, force_full=False, a
     cap = max(1024, int(ro[-1]) // 4)
     out = np.zeros(cap, HIT_DT)
     n = ctypes.c_int64(0)
-    cnt = np.zeros(7, np.int64)
+    cnt = np.zeros(8, np.int64)
     rc = lib().lsw_emu_find_all(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc),
                                 _ptr(qo), ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap),
                                 ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt), ctypes.c_int(int(force_full)), ctypes.c_int(int(allowed_overlap)), ctypes.c_int(int(reuse)))
     if rc:
         raise RuntimeError("lsw_emu_find_all rc=%d" % rc)
-    return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), steps=int(cnt[2]), rounds=int(cnt[3]), traced=int(cnt[4]), fallbacks=int(cnt[5]), computed_cells=int(cnt[6]))
+    return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), steps=int(cnt[2]), rounds=int(cnt[3]), traced=int(cnt[4]), fallbacks=int(cnt[5]), computed_cells=int(cnt[6]), tier2=int(cnt[7]))
 
 
 def align_tasks(reads, seqs, tasks, match=2, mismatch=-1, gap=-1, force_full=False, stats=None):
