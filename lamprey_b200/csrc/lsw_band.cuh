@@ -51,6 +51,13 @@ struct BandLane {
     static constexpr int MAXD = 15;                          // nesting limit of run-flag evaluations
     static constexpr int WORDS_PER_LANE = KCOLS * 2 * BW;    // shared-memory words of one lane (two tasks)
 
+    // stride between a lane's consecutive band words: the warp's words are interleaved on the device, the host emulation has one lane
+#if defined(__CUDA_ARCH__)
+    static constexpr int LS = 32;
+#else
+    static constexpr int LS = 1;
+#endif
+
     uint32_t M[NR];
 
     struct Half { int ncols; int64_t code0; int row; };
@@ -86,20 +93,20 @@ struct BandLane {
     // (TraceLane::Walker, decision_entry); only the operand fetch differs.
     template <bool OPS>
     struct Walker {
-        const uint32_t* band; int LS, h;       // the lane's band words; word (k, h, w) at ((k * 2 + h) * BW + w) * LS
+        const uint32_t* band;                  // this task's band words: word (k, w) at (k * 2 * BW + w) * LS
         const uint8_t* qc; const uint32_t* ref4; int rlead;
         int score, c0, row, ncols;
         int r, cl, hv, depth, retc, last, state, budget;
         const uint8_t* dtab;
         uint32_t mv, st;
         bool failed;
-        uint32_t rw; int tagR;
+        uint32_t rw, rwn; int tagR;           // read codes: the aligned word of the current column and the one before it (fetched ahead)
 
-        LSW_HD bool init(const TraceParams& P, const TaskView& v, int c0_, int ncols_, int h_, const uint32_t* band_, int LS_,
+        LSW_HD bool init(const TraceParams& P, const TaskView& v, int c0_, int ncols_, int h_, const uint32_t* band_,
                          const uint8_t* qcodes, const uint8_t* table) {
             dtab = table; failed = false;
-            depth = last = state = 0; retc = 0; mv = 0; st = 0; tagR = -1; rw = 0;
-            band = band_; LS = LS_; h = h_;
+            depth = last = state = 0; retc = 0; mv = 0; st = 0;
+            band = band_ + h_ * BW * LS;
             qc = qcodes;
             const uint8_t* refw = v.ref + c0_ - 1;
             rlead = (int)(reinterpret_cast<uintptr_t>(refw) & 3u);
@@ -107,6 +114,8 @@ struct BandLane {
             score = v.score; c0 = c0_; row = v.row; ncols = ncols_;
             r = v.row; cl = ncols_; hv = v.score;
             budget = 6 * (v.row + ncols_) + 64;
+            tagR = (cl + rlead) >> 2;           // (the code array is padded by 256 bytes in front: word tagR - 1 always exists)
+            rw = ref4[tagR]; rwn = ref4[tagR - 1];
             if (c0_ > 0) {      // one certificate for the whole walk (trace_slack): margin of the start cell
                 const int num = P.match * r - score - 1;
                 const int margin = cl - r - (num >= 0 ? num / P.g : -1);
@@ -135,12 +144,14 @@ struct BandLane {
             uint32_t A[BW], B[BW];
 #pragma unroll
             for (int w = 0; w < BW; w++) {
-                A[w] = band[((kc * 2 + h) * BW + w) * LS];
-                B[w] = cl > 1 ? band[(((kc + 1) * 2 + h) * BW + w) * LS] : 0u;    // column 0 of a slice is the zero boundary
+                A[w] = band[(kc * 2 * BW + w) * LS];
+                B[w] = cl > 1 ? band[((kc + 1) * 2 * BW + w) * LS] : 0u;    // column 0 of a slice is the zero boundary
             }
             const int i = r - 1;
             const int off = cl + rlead;
-            if ((off >> 2) != tagR) { tagR = off >> 2; rw = ref4[tagR]; }
+            // the walk moves one column at a time: word tagR - 1 is already here when the column crosses into it
+            if ((off >> 2) < tagR) { tagR--; rw = rwn; rwn = ref4[tagR - 1]; }
+            else if ((off >> 2) > tagR) { tagR++; rwn = rw; rw = ref4[tagR]; }
             const int rb = (int)((rw >> (8 * (off & 3))) & 0xFFu);
             const int qb = qc[i];
             const int g = P.g;
@@ -219,7 +230,7 @@ struct BandLane {
     // band: this lane's shared-memory words (stride LS between consecutive words).
     // xmin[h]: fewest errors of an optimal path into the end cell; -1 = nothing to walk (score 0 or no candidate),
     // -2 = the recomputed end cell does not reproduce K1's score (never expected: next tier).
-    LSW_HD void fill_pair(const TraceParams& P, const U2* prof, int q, int ci0, int ci1, uint32_t* band, int LS, int* xmin) {
+    LSW_HD void fill_pair(const TraceParams& P, const U2* prof, int q, int ci0, int ci1, uint32_t* band, int* xmin) {
         Half hf[2];
         const int ci[2] = {ci0, ci1};
         int score[2];
@@ -243,30 +254,31 @@ struct BandLane {
         const uint32_t FLOOR2 = G2 + B2;
 #pragma unroll
         for (int r = 0; r < NR; r++) M[r] = B2;
-        // read codes: aligned words, fetched TWO words ahead of their use (the code array is padded past every read)
-        int64_t addr[2]; int lead[2]; uint32_t prev[2], nxt[2];
+        // read codes: aligned words.  Three words are in flight per task: the pair the current four steps are cut from and the
+        // word after them, which was requested one iteration (four columns) before it is looked at -- the value loaded in an
+        // iteration must not be touched in the same iteration, not even by a register move, or the warp waits for it there
+        // (ncu: a quarter of the fill's stall samples sat on exactly that move).
+        int64_t addr[2]; int lead[2]; uint32_t w0[2], w1[2], w2[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            addr[h] = 0; lead[h] = 0; prev[h] = 0; nxt[h] = 0;
-            if (hf[h].ncols > 0) {
-                const int64_t a0 = hf[h].code0 - first[h];
-                lead[h] = (int)(a0 & 3);
-                addr[h] = a0 - lead[h];
-                prev[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h]);
-                nxt[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h] + 4);
-            }
+            // (a half without a task reads the front pad of the code array: the loads are unconditional on purpose, a predicated
+            // load lands in a temporary that is then moved into the loop-carried register in the same iteration)
+            const int64_t a0 = hf[h].ncols > 0 ? hf[h].code0 - first[h] : 0;
+            lead[h] = (int)(a0 & 3);
+            addr[h] = a0 - lead[h];
+            w0[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h]);
+            w1[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h] + 4);
+            w2[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h] + 8);
         }
 #pragma unroll 1
         for (int s0 = 0; s0 < n; s0 += 4) {
             uint32_t c[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                uint32_t v = 0;
-                if (hf[h].ncols > 0) {
-                    v = prmt(prev[h], nxt[h], 0x3210u + 0x1111u * (uint32_t)lead[h]);
-                    prev[h] = nxt[h];
-                    nxt[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h] + s0 + 8);
-                }
+                uint32_t v = prmt(w0[h], w1[h], 0x3210u + 0x1111u * (uint32_t)lead[h]);
+                w0[h] = w1[h];
+                w1[h] = w2[h];                                                               // loaded one iteration ago
+                w2[h] = *reinterpret_cast<const uint32_t*>(P.codes + addr[h] + s0 + 12);     // looked at one iteration from now
                 if (h) v |= (v & 0x04040404u) << 2;
                 int nl = first[h] - s0; nl = nl < 0 ? 0 : (nl > 4 ? 4 : nl);
                 const uint32_t kp = (hf[h].ncols > 0 && nl < 4) ? (0xFFFFFFFFu << (8 * nl)) : 0u;
@@ -341,7 +353,7 @@ struct BandLane {
     // The traceback of candidate record cidx (task half h of the lane whose band this is) -> hit test / result record.
     // false: the candidate must go to the next tier.
     template <bool OPS>
-    LSW_HD bool walk_one(const TraceParams& P, const uint8_t* qcodes, const uint8_t* dtab, int q, int cidx, int h, const uint32_t* band, int LS) {
+    LSW_HD bool walk_one(const TraceParams& P, const uint8_t* qcodes, const uint8_t* dtab, int q, int cidx, int h, const uint32_t* band) {
         const TaskView v = load_cand(P, cidx, q);
         PathOutT<OPS> po;
         po.clear();
@@ -354,7 +366,7 @@ struct BandLane {
 #if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
             g_cur_dmin = g_cur_dmax = 0;
 #endif
-            if (w.init(P, v, c0, ncols, h, band, LS, qcodes, dtab))
+            if (w.init(P, v, c0, ncols, h, band, qcodes, dtab))
                 while (w.step(P, po)) {
 #if !defined(__CUDA_ARCH__) && defined(LSW_EMU_STATS)
                     g_band_iters[BW]++;
@@ -379,9 +391,9 @@ struct BandLane {
     // fill + walk of one pair, one lane at a time (host emulation and the simple device path).  fb(ci, t): next tier.
     template <bool OPS, class Fallback>
     LSW_HD void run_pair(const TraceParams& P, const U2* prof, const uint8_t* qcodes, const uint8_t* dtab, int q, int ci0, int ci1,
-                         uint32_t* band, int LS, Fallback fb) {
+                         uint32_t* band, Fallback fb) {
         int xmin[2];
-        fill_pair(P, prof, q, ci0, ci1, band, LS, xmin);
+        fill_pair(P, prof, q, ci0, ci1, band, xmin);
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const int cidx = h ? ci1 : ci0;
@@ -394,7 +406,7 @@ struct BandLane {
 #endif
                 continue;                                   // certainly not a hit: no record, no children
             }
-            if (!walk_one<OPS>(P, qcodes, dtab, q, cidx, h, band, LS)) fb(cidx, v.t);
+            if (!walk_one<OPS>(P, qcodes, dtab, q, cidx, h, band)) fb(cidx, v.t);
         }
     }
 };
@@ -483,7 +495,7 @@ k_trace_band(const TraceParams P) {
                 continue;
             }
             int xmin[2] = {-1, -1};
-            if (active) L.fill_pair(P, prof, q, c0, c1, band_warp + lane, 32, xmin);
+            if (active) L.fill_pair(P, prof, q, c0, c1, band_warp + lane, xmin);
             // what becomes of the two candidates: dropped (error count), next tier (-2), or walked
             bool walk[2];
 #pragma unroll
@@ -505,7 +517,7 @@ k_trace_band(const TraceParams P) {
                 const int s0 = __shfl_sync(0xFFFFFFFFu, c0, src), s1 = __shfl_sync(0xFFFFFFFFu, c1, src);
                 if (mine) {
                     const int ci = h ? s1 : s0;
-                    if (!L.template walk_one<OPS>(P, qsm, dtab, q, ci, h, band_warp + src, 32)) {
+                    if (!L.template walk_one<OPS>(P, qsm, dtab, q, ci, h, band_warp + src)) {
                         const unsigned long long k = atomicAdd(&P.fb2_cnt[q], 1ull);
                         P.fb2[lo + k] = (uint32_t)ci;
                     }

@@ -171,8 +171,8 @@ void emu_trace_seq(Emu& E, const TraceParams& T, const ScoreParams& P, int q, co
                 L.template run_pair<false>(TR, prof.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, 0, [&](int t) { E.fallbacks++; trace_full_task<NR2>(T, t, 0); });
         } else {                       // what the library runs: 16-row band in shared memory (lsw_band.cuh) ...
             auto fb1 = [&](int ci, int) { tier2.push_back(ci); };
-            if (T.mode == 1) B2.template run_pair<true>(TR, prof_lex.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, band2.data(), 1, fb1);
-            else B2.template run_pair<false>(TR, prof_lex.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, band2.data(), 1, fb1);
+            if (T.mode == 1) B2.template run_pair<true>(TR, prof_lex.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, band2.data(), fb1);
+            else B2.template run_pair<false>(TR, prof_lex.data(), T.qcodes + (size_t)q * QSTRIDE, dtab, q, (int)i, t1 >= 0 ? (int)i + 1 : -1, band2.data(), fb1);
         }
     }
     E.tier2 += tier2.size();

@@ -1,10 +1,14 @@
 """Summarise `ncu --page source --csv` of one kernel by SASS regions: python tools/ncu_regions.py file.csv [n_regions_by_backward_branches]
 Prints, per region between loop boundaries (backward branches), samples, executed instructions, average active threads, top stalls."""
 import csv, sys, re
-rows = list(csv.reader(open(sys.argv[1])))
+allrows = list(csv.reader(open(sys.argv[1])))
+starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"] + [len(allrows)]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # which kernel of the report
+rows = allrows[starts[which]:starts[which + 1]]
+print(rows[0][1])
 h = rows[1]
 col = {k: i for i, k in enumerate(h)}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) == len(h)]
 addr = [int(r[col["Address"]], 16) for r in data]
 base = addr[0]
 stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
