@@ -98,6 +98,8 @@ class Engine(object):
         self.n_queries = 0
         self.n_reads = 0
         self.last_counters = None
+        self._scoring = None          # what the context currently holds: repeated set_* calls with the same values are
+        self._queries = None          # free (LocalAlignment.align sets both on every call, ~65 times per read)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -122,13 +124,23 @@ class Engine(object):
         self._check(self._lib.lsw_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_ptr or 0))), "lsw_set_stream")
 
     def set_scoring(self, match=2, mismatch=-1, gap=-1, gap_ext=-1):
-        self._check(self._lib.lsw_set_scoring(self._h, int(match), int(mismatch), int(gap), int(gap_ext)), "lsw_set_scoring")
+        key = (int(match), int(mismatch), int(gap), int(gap_ext))
+        if key == self._scoring:
+            return
+        self._scoring = None
+        self._check(self._lib.lsw_set_scoring(self._h, *key), "lsw_set_scoring")
+        self._scoring = key
 
     def set_queries(self, seqs):
-        concat, offs = concat_sequences(seqs)
+        key = tuple(s if isinstance(s, str) else bytes(s).decode("ascii") for s in seqs)
+        if key == self._queries:
+            return
+        self._queries = None
+        concat, offs = concat_sequences(key)
         offs32 = offs.astype(np.int32)
-        self._check(self._lib.lsw_set_queries(self._h, len(seqs), _ptr(concat), _ptr(offs32)), "lsw_set_queries")
-        self.n_queries = len(seqs)
+        self._check(self._lib.lsw_set_queries(self._h, len(key), _ptr(concat), _ptr(offs32)), "lsw_set_queries")
+        self.n_queries = len(key)
+        self._queries = key
 
     def upload_reads(self, ascii_u8, offs_i64):
         a = np.ascontiguousarray(ascii_u8, dtype=np.uint8)
@@ -174,8 +186,13 @@ class Engine(object):
         cnt = np.zeros(1, COUNTERS_DT)
         rc = self._lib.lsw_find_all(self._h, float(threshold), ctypes.byref(n), _ptr(cnt))
         if rc == LSW_E_OVERFLOW:
+            # retry once with room for the reported count, then go back to the default capacity: a later, larger batch
+            # must not inherit this batch's number
             self._check(self._lib.lsw_set_hit_capacity(self._h, n.value + 1024), "lsw_set_hit_capacity")
-            rc = self._lib.lsw_find_all(self._h, float(threshold), ctypes.byref(n), _ptr(cnt))
+            try:
+                rc = self._lib.lsw_find_all(self._h, float(threshold), ctypes.byref(n), _ptr(cnt))
+            finally:
+                self._lib.lsw_set_hit_capacity(self._h, 0)
         self._check(rc, "lsw_find_all")
         self.last_counters = {k: cnt[0][k].item() for k in COUNTERS_DT.names}
         if not fetch:

@@ -694,6 +694,10 @@ int lsw_set_scoring(lsw_ctx* ctx, int match, int mismatch, int gap, int gap_ext)
         return fail(ctx, LSW_E_UNSUPPORTED, "need match > 0, mismatch < 0, gap < 0");
     if (match * LSW_MAX_QUERY_LEN - gap > 127 && match * 1 - gap > 127)
         return fail(ctx, LSW_E_UNSUPPORTED, "scores do not fit the packed 8.8 fixed-point cells");
+    // the profile entry of a mismatch, 256 * (mismatch + |gap|), is one s16 half (lsw_score.cuh build_profile): below -32768 it
+    // would wrap and a mismatch would score positive
+    if (mismatch - gap < -128)
+        return fail(ctx, LSW_E_UNSUPPORTED, "mismatch + |gap| must be >= -128 for the packed 8.8 fixed-point cells");
     ctx->match = match; ctx->mismatch = mismatch; ctx->g = -gap;
     return LSW_OK;          // scoring and queries may be set in either order: the pair is checked when work is submitted
 }
@@ -749,16 +753,18 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     if (!ctx || n < 0 || !offs || (n > 0 && !ascii && offs[n] > offs[0])) return ctx ? fail(ctx, LSW_E_ARG, "lsw_upload_reads: bad argument") : LSW_E_ARG;
     if (n >= (1ll << 26)) return fail(ctx, LSW_E_ARG, "at most 2^26 - 1 reads per batch");
     CK(cudaSetDevice(ctx->device));
+    // a failed upload leaves the context EMPTY (n_reads = 0), never describing the previous batch with the new lengths
+    ctx->n_reads = 0; ctx->total_bases = 0; ctx->n_hits = 0;
     ctx->h_rlen.assign((size_t)n, 0);
     int64_t padded_total = 0;
     for (int64_t i = 0; i < n; i++) {
         const int64_t len = offs[i + 1] - offs[i];
-        if (len < 0 || len >= (1ll << 27)) return fail(ctx, LSW_E_ARG, "read length must be in [0, 2^27)");
+        if (len < 0 || len >= (1ll << 27)) { ctx->h_rlen.clear(); return fail(ctx, LSW_E_ARG, "read length must be in [0, 2^27)"); }
         ctx->h_rlen[i] = (int32_t)len;
         padded_total += (len + 15) & ~15ll;
     }
-    ctx->n_reads = n;
-    ctx->total_bases = n ? offs[n] - offs[0] : 0;
+    const int64_t total_bases = n ? offs[n] - offs[0] : 0;
+    ctx->total_bases = total_bases;
     ctx->h_bb_off.assign((size_t)n + 1, 0);                       // BB_BLOCK-column blocks of every read (lsw_reuse.cuh)
     for (int64_t i = 0; i < n; i++) ctx->h_bb_off[i + 1] = ctx->h_bb_off[i] + (ctx->h_rlen[i] + BB_BLOCK - 1) / BB_BLOCK;
     ctx->bb_total = ctx->h_bb_off[n];
@@ -821,6 +827,7 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(ctx->stream));      // `rel` and the caller's buffers may go away
+    ctx->n_reads = n;                            // committed only now: every step above has succeeded
     return LSW_OK;
 }
 
@@ -884,6 +891,8 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     int rc = LSW_OK;
     unsigned long long h_nhits = 0;
     while (n > 0) {
+        // the scans, the 32-bit child positions and K1's task indices are int32: a round may hold at most 2^30 - 1 tasks
+        if (n >= (1ll << 30)) { rc = fail(ctx, LSW_E_ARG, "a recursion round exceeds 2^30 tasks: split the batch"); break; }
         const int64_t n2 = 2 * n;
         rc = ctx->child.ensure((size_t)n2, false) == cudaSuccess ? LSW_OK : LSW_E_CUDA;
         if (rc) { ctx->err = "out of device memory (child tasks)"; break; }

@@ -56,6 +56,7 @@ struct Emu {
 bool setup(Emu& E, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
            const int32_t* qoffs, int match, int mismatch, int gap) {
     if (match <= 0 || mismatch >= 0 || gap >= 0) return false;
+    if (mismatch - gap < -128) return false;          // 256 * (mismatch + |gap|) must fit an s16 half (same check as lsw_set_scoring)
     E.match = match; E.mismatch = mismatch; E.g = -gap; E.nseq = nseq;
     E.qlen.resize(nseq); E.class_of.resize(nseq);
     E.qcodes.assign((size_t)nseq * QSTRIDE, 0xFF);

@@ -5,6 +5,7 @@ Mirrors, name for name and argument for argument (same ordering and error behavi
 * ``rc``                         /root/reference/lamprey.py:649-659
 * ``PrimerSet``                  /root/reference/lamprey.py:81-136
 * ``Alignment``                  /root/reference/lamprey.py:138-161
+* ``alignSequence_swalign``      /root/reference/lamprey.py:558-569
 * ``findPrimerAlignments``       /root/reference/lamprey.py:596-645   (--swalign branch)
 * ``findAllPrimerAlignments``    /root/reference/lamprey.py:699-733
 
@@ -151,8 +152,10 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
     eng.set_queries([s for _, s in pairs])
     eng.upload_reads(concat, offs)
     eng.set_overlap(allowed_overlap)
-    hits = eng.find_all(threshold)
-    eng.set_overlap(None)
+    try:
+        hits = eng.find_all(threshold)
+    finally:
+        eng.set_overlap(None)            # the engine is shared (swalign.get_engine): never leave the pruning switched on
     return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters)
 
 
@@ -165,6 +168,13 @@ def seed_fastq(path, primer_set, threshold, aligner=None, device=0, engine=None,
     batch = seed_reads((got[0], got[1]), primer_set, threshold, aligner=aligner, device=device, engine=engine,
                        allowed_overlap=allowed_overlap)
     return (batch, got[2]) if with_names else batch
+
+
+def alignSequence_swalign(aligner, seq, primer, primer_name):
+    """Aligns a primer to a DNA sequence -- drop-in for /root/reference/lamprey.py:558-569: one
+    ``aligner.align(str(seq), primer)`` and the three fields LAMPrey keeps of it."""
+    alignment_tmp = aligner.align(str(seq), primer)
+    return Alignment(alignment_tmp.r_pos, alignment_tmp.r_end, alignment_tmp.identity, primer_name)
 
 
 def _preorder(hits, identity, name):

@@ -16,6 +16,29 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _have_gpu():
+    """True if lsw_create succeeds on device 0 (the product has no CPU fallback, so without a device every gpu test would
+    fail in lsw_create)."""
+    from lamprey_b200 import _native
+    _native.load()                       # a missing liblsw.so is NOT a reason to skip: let it raise
+    try:
+        _native.Engine(0).close()
+        return True
+    except RuntimeError as e:
+        if "no CUDA device" in str(e):
+            return False
+        raise
+
+
+def pytest_collection_modifyitems(config, items):
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if not gpu_items or _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: gpu-marked tests run on the B200 box (pytest -m gpu)")
+    for it in gpu_items:
+        it.add_marker(skip)
+
+
 def load_reads(key):
     with gzip.open(os.path.join(GOLD, "reads_%s.txt.gz" % key), "rt") as fp:
         return fp.read().split()

@@ -122,6 +122,17 @@ def test_emu_find_all_edge_reads():
 def test_emu_rejects_unsupported_scoring():
     with pytest.raises(RuntimeError):
         emu_lib.align_tasks(["ACGT"], ["ACG"], np.array([(0, 0, 4, 0)], dtype=TASK_DT), 2, 0, -1)
+    with pytest.raises(RuntimeError):        # 256 * (mismatch + |gap|) would wrap the s16 half of a profile entry
+        emu_lib.align_tasks(["ACGT"], ["ACG"], np.array([(0, 0, 4, 0)], dtype=TASK_DT), 2, -200, -1)
+
+
+def test_emu_most_negative_mismatch_that_fits():
+    # mismatch + |gap| = -128 is the edge of the packed profile entry: results must still equal the oracle's
+    rng = random.Random(77)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(n)) for n in (9, 16, 21)]
+    reads = ["".join(rng.choice("ACGT") for _ in range(n)) for n in (40, 150, 333)]
+    tasks = np.array([(i, 0, len(r), q) for i, r in enumerate(reads) for q in range(len(seqs))], dtype=TASK_DT)
+    _check_tasks(reads, seqs, tasks, (2, -129, -1))
 
 
 def test_emu_fast_traceback_equals_full_window():

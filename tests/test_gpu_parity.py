@@ -350,6 +350,9 @@ def test_error_behaviour_of_the_engine(engine):
         engine.set_scoring(2, 0, -1, -1)                # mismatch must be negative
     with pytest.raises(NotImplementedError):
         engine.set_scoring(2, -1, -2, -1)               # affine gaps
+    with pytest.raises(ValueError, match="-128"):
+        engine.set_scoring(2, -200, -1, -1)             # 256 * (mismatch + |gap|) would wrap its s16 half
+    engine.set_scoring(2, -127, -1, -1)                 # the most negative mismatch that fits
     with pytest.raises(ValueError):
         engine.find_all(0.0)                            # the reference would recurse forever
     engine.set_scoring(2, -1, -1, -1)
