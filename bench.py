@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py -- seeding throughput of the B200 engine on BASELINE.json's synthetic workload.
+"""bench.py -- seeding throughput of the B200 engine on BASELINE.json's synthetic workloads.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--workload NAME] [--thr T]
     python bench.py --impl reference ...        # the reference arm: CPU (Cython) swalign seeding
@@ -7,15 +7,23 @@
 One "step" = one pass of the hot path (findAllPrimerAlignments for every read: all 46 schema
 sequences, greedy recursion included) over one batch of synthetic reads.  At N=1 the workload is
 BASELINE.json configs[2]: 10^6 ONT-like concatemer reads, 2 kb mean, 8 % error, H3.3 schema.
-With N GPUs every rank seeds its own batch of R reads (weak scaling, no data-path collective --
-reads are independent units; only timings and counts are reduced).
+With N GPUs (one process per GPU) every rank seeds its own batch of R reads (weak scaling, no
+data-path collective -- reads are independent units; only timings and counts are reduced).
 
-Printed JSON line (rank 0): metric reads/s (whole job), plus GCUPS, roofline (integer ALU bound,
-SURVEY.md section 8d), cpu_baseline (Cython swalign on the host cores, N=1 only), e2e (host
-buffers -> hits on the host through the C ABI, H2D/D2H inside the timed region), clocks.
+Printed JSON line (rank 0): metric reads/s (whole job), plus
+  gcups         reference cells per second (all recursion tasks);
+  roofline      K1 against the DPX-pipe ceiling of its own instruction mix (integer ALU bound), the
+                survey's 6-op model and the inner-loop microbenchmark beside it, ncu pipe counters and DRAM traffic of the
+                10^6-read capture under profiles/;
+  cpu_baseline  Cython swalign on the host cores (N=1), and a parity check of the GPU hits against it tuple by tuple;
+  e2e           host buffers -> hits on the host through the library's own double-buffered pool (lsw_pool_*), a plain
+                submit/wait loop, H2D and D2H inside the timed region;
+  strong_scaling ONE fixed batch (rank 0's) split over all N GPUs by the pool of rank 0, host-side gather included;
+  extra_configs BASELINE.json configs[3] and [4] (5 kb / 12 %; 20-50 kb, 40-sequence schema) with their own timing;
+  clocks.
 """
 import argparse
-import contextlib
+import csv
 import json
 import os
 import subprocess
@@ -30,7 +38,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SCHEMA = os.path.join(ROOT, "tests", "golden", "H3.3_set1.primers")
-ALG_OPS_PER_CELL = 6          # int32-lane ops per DP cell (algorithmic)
+ALG_OPS_PER_CELL = 6          # int32-lane ops per DP cell (the survey's model)
+K1_DPX_PER_4_CELLS = 5        # K1's real mix (lsw_score.cuh column2, SASS-checked): 5 packed DPX + 4 adds + 1 LDS.64 per 4 cells
+NCU_SCORE_RAW = os.path.join(ROOT, "profiles", "r02_score24_1M_raw.csv")     # ncu --set full of round 0's k_score<24> at 10^6 reads
 
 
 def dist_env():
@@ -79,14 +89,15 @@ def _cpu_init(schema_path, n_names=None, pure_python=False):
 
 
 def _cpu_seed(args):
+    """-> (hits as the reference returns them: [(start, end, identity, name)], align() calls, cells)."""
     read, thr = args
     st = _CPU["seed"].Stats()
     hits, _ = _CPU["seed"].find_all_primer_alignments(_CPU["sw"], read, _CPU["ps"], thr, st)
-    return len(hits), st.calls, st.cells
+    return [(h.start, h.end, h.identity, h.primer_name) for h in hits], st.calls, st.cells
 
 
 def cpu_seed_sample(reads, thr, cores, pool=None, n_names=None, pure_python=False):
-    """-> (seconds, hits, calls, cells) for seeding `reads` on `cores` processes."""
+    """-> (seconds, per-read hit lists, calls, cells) for seeding `reads` on `cores` processes."""
     import multiprocessing as mp
     own = pool is None
     if own:
@@ -98,7 +109,30 @@ def cpu_seed_sample(reads, thr, cores, pool=None, n_names=None, pure_python=Fals
     if own:
         pool.close()
         pool.join()
-    return dt, sum(r[0] for r in res), sum(r[1] for r in res), sum(r[2] for r in res)
+    return dt, [r[0] for r in res], sum(r[1] for r in res), sum(r[2] for r in res)
+
+
+def _c_oracle_chunk(args):
+    """Full hit records (all ten fields) of a slice of reads from the C restatement of the oracle."""
+    from oracle import c_oracle
+    reads, seqs, thr, first = args
+    rows = []
+    for i, r in enumerate(reads):
+        h, _ = c_oracle.find_all(r, seqs, thr)
+        h = h[np.argsort(h["start"], kind="stable")]
+        rows += [(first + i, int(x["seq"]), int(x["start"]), int(x["end"]), int(x["matches"]), int(x["mismatches"]), int(x["score"]),
+                  int(x["q_pos"]), int(x["q_end"]), int(x["depth"])) for x in h]
+    return rows
+
+
+def c_oracle_rows(reads, seqs, thr, cores):
+    import multiprocessing as mp
+    from oracle import c_oracle
+    c_oracle.build()
+    step = max(1, (len(reads) + cores - 1) // cores)
+    with mp.get_context("fork").Pool(cores) as pool:
+        parts = pool.map(_c_oracle_chunk, [(reads[k:k + step], seqs, thr, k) for k in range(0, len(reads), step)])
+    return [r for p in parts for r in p]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -152,30 +186,40 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
-def ncu_traffic():
-    """DRAM bytes of the dominant K1 launch from the committed `ncu --set full` capture (profiles/, a 32768-read run:
-    per-launch sizes differ from the bench's, so it is reported beside `traffic`, not as it).  HBM is not the bound here."""
-    import csv
-    path = os.path.join(ROOT, "profiles", "r01_score_raw.csv")
+def ncu_capture():
+    """Counters of the round-0 k_score<24> launch AT THE 10^6-READ CONFIG from the committed `ncu --set full` capture
+    (profiles/, produced by tools/profile_1M.sh): DRAM bytes of the launch, pipe utilisation, issue slots."""
     try:
-        rows = list(csv.reader(open(path)))
-        h = rows[0]
-        r = max(rows[2:], key=lambda x: float(x[h.index("gpu__time_duration.sum")]))
-        rd, wr = float(r[h.index("dram__bytes_read.sum")]), float(r[h.index("dram__bytes_write.sum")])
-        unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[rows[1][h.index("dram__bytes_read.sum")]]
-        ms = float(r[h.index("gpu__time_duration.sum")])
-        return {"kernel": r[h.index("Kernel Name")].replace("void ", ""), "workload_reads": 32768,
-                "dram_bytes_per_launch": (rd + wr) * unit, "launch_ms_under_ncu": ms,
-                "hbm_gb_per_s": (rd + wr) * unit / 1e9 / (ms / 1e3), "source": "profiles/r01_score_raw.csv"}
+        rows = list(csv.reader(open(NCU_SCORE_RAW)))
+        h, units, r = rows[0], rows[1], rows[2]
+        mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+
+        def val(k):
+            return float(r[h.index(k)].replace(",", ""))
+        rd = val("dram__bytes_read.sum") * mult[units[h.index("dram__bytes_read.sum")]]
+        wr = val("dram__bytes_write.sum") * mult[units[h.index("dram__bytes_write.sum")]]
+        dur = val("gpu__time_duration.sum")
+        du = units[h.index("gpu__time_duration.sum")]
+        ms = dur / 1e6 if du in ("ns", "nsecond") else dur / 1e3 if du in ("us", "usecond") else dur if du in ("ms", "msecond") else dur * 1e3
+        out = {"kernel": r[h.index("Kernel Name")].replace("void ", "") + " <24>, round 0 (32 sequences x 10^6 whole reads)",
+               "dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr, "launch_ms_under_ncu": ms,
+               "hbm_gb_per_s": (rd + wr) / 1e9 / (ms / 1e3), "source": os.path.relpath(NCU_SCORE_RAW, ROOT)}
+        for key, name in (("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "pipe_alu_pct"),
+                          ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "pipe_fma_pct"),
+                          ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+                          ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct")):
+            if key in h:
+                out[name] = val(key)
+        return out
     except Exception:
         return None
 
 
-def workload_reads(args, rank, world, workers):
+def workload_reads(workload, n_reads, rank, workers):
     from lamprey_b200 import synth
-    kw = dict(synth.CONFIGS[args.workload])
+    kw = dict(synth.CONFIGS[workload])
     kw["seed"] = kw["seed"] + 1000 * rank            # every rank seeds its own batch (weak scaling)
-    return synth.generate(args.reads, workers=workers, **kw)
+    return synth.generate(n_reads, workers=workers, **kw)
 
 
 def run_reference(args):
@@ -218,6 +262,46 @@ def run_reference(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------
+def timed_find_all(eng, torch, stream, thr, steps, warmup, barrier, sampler_gpu=None):
+    """W warm-up + K timed passes over the batch resident in `eng` (CUDA events on the launching stream).
+    -> (seconds, counters of the last pass, accumulated per-phase ms and launches, clocks, hits of a pass)."""
+    n_hits = 0
+    for _ in range(warmup):
+        n_hits = eng.find_all(thr, fetch=False)
+    sampler = ClockSampler(sampler_gpu) if sampler_gpu is not None else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc = dict(ms_score=0.0, ms_score_round0=0.0, ms_trace=0.0, ms_other=0.0, ms_total=0.0, launches=0, score_launches=0)
+    e0.record(stream)
+    for _ in range(steps):
+        n_hits = eng.find_all(thr, fetch=False)
+        c = eng.last_counters
+        for k in ("ms_score", "ms_score_round0", "ms_trace", "ms_other", "ms_total"):
+            acc[k] += c[k]
+        acc["launches"] += c["score_launches"] + c["trace_launches"] + c["other_launches"]
+        acc["score_launches"] += c["score_launches"]
+    e1.record(stream)
+    barrier()
+    seconds = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.stop() if sampler else None
+    return seconds, dict(eng.last_counters), acc, clocks, n_hits
+
+
+def k1_rates(cnt, acc, steps):
+    """K1 GCUPS: all launches, round 0 (whole reads) and the child rounds (segments) separately."""
+    s_all, s_r0 = acc["ms_score"] / 1e3, acc["ms_score_round0"] / 1e3
+    s_ch = s_all - s_r0
+    c_all, c_r0 = cnt["computed_cells"] * steps, cnt["computed_cells_round0"] * steps
+    return {"all": c_all / s_all / 1e9 if s_all > 0 else None,
+            "round0": c_r0 / s_r0 / 1e9 if s_r0 > 0 else None,
+            "children": (c_all - c_r0) / s_ch / 1e9 if s_ch > 0 else None,
+            "ms_round0_per_step": acc["ms_score_round0"] / steps, "ms_children_per_step": (acc["ms_score"] - acc["ms_score_round0"]) / steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -230,7 +314,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-engines", type=int, default=2, help="contexts (CUDA streams) that take alternate e2e steps")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE.json configs[3] and [4]")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-batch strong-scaling leg")
+    ap.add_argument("--extra-reads-5kb", type=int, default=400000)
+    ap.add_argument("--extra-reads-long", type=int, default=100000)
+    ap.add_argument("--e2e-depth", type=int, default=2, help="contexts per device of the pool (batches in flight)")
     args = ap.parse_args()
     # stdout carries the one JSON line and nothing else: libraries that print to fd 1 (NCCL's version
     # banner, forked workers) are pointed at stderr for the whole run.
@@ -244,27 +332,41 @@ def main():
     rank, local_rank, world = dist_env()
     cores = os.cpu_count() or 1
     workers = max(1, cores // max(1, world))
+    from lamprey_b200 import synth
 
     # ---- everything that forks happens before CUDA is touched -------------------------------
-    concat, offs = workload_reads(args, rank, world, workers)
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from lamprey_b200 import synth
-        # ~2 s per 2 kb read per core for the Cython port: size the sample for about --cpu-seconds
-        per_read = 2.2 * (np.diff(offs).mean() / 2000.0) ** 1.0
-        sample = int(max(cores, min(len(offs) - 1, cores * args.cpu_seconds / per_read)))
-        reads = synth.reads_as_strings(concat[:offs[sample]], offs[:sample + 1])
-        dt, hits_cpu, calls_cpu, cells_cpu = cpu_seed_sample(reads, args.thr, cores, n_names=synth.SCHEMA_NAMES.get(args.workload))
-        cpu_baseline = {"value": sample / dt, "unit": "reads/s", "cores": cores, "kind": "port",
-                        "gcups": cells_cpu / dt / 1e9, "seconds": dt,
-                        "sample": "first %d reads of the workload, Cython build of oracle/swalign_ref.py + "
-                                  "seeding_ref.py (README.md:18-25 recipe), one process per core" % sample,
-                        "_hits": hits_cpu, "_calls": calls_cpu, "_cells": cells_cpu, "_n": sample}
-        # the interpreted figure beside it: one read per core
-        dt_py, _, _, cells_py = cpu_seed_sample(reads[:cores], args.thr, cores, n_names=synth.SCHEMA_NAMES.get(args.workload),
-                                                pure_python=True)
-        cpu_baseline["pure_python"] = {"value": min(cores, len(reads)) / dt_py, "unit": "reads/s", "gcups": cells_py / dt_py / 1e9,
-                                       "sample": "first %d reads, oracle/swalign_ref.py + seeding_ref.py interpreted" % min(cores, len(reads))}
+    concat, offs = workload_reads(args.workload, args.reads, rank, workers)
+    extra_specs = [] if args.no_extra else [("synth_5kb_12pct", args.extra_reads_5kb), ("synth_20_50kb_12pct", args.extra_reads_long)]
+    extra_reads = [(wl, n) + workload_reads(wl, n, rank, workers) for wl, n in extra_specs]
+    from lamprey_b200 import seeding
+    ps = seeding.PrimerSet(SCHEMA)
+    seqs = [s for _, s in synth.schema_sequences(ps, args.workload)]
+    names = [n for n, _ in synth.schema_sequences(ps, args.workload)]
+    cpu_baseline, cpu_ref = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        n_names = synth.SCHEMA_NAMES.get(args.workload)
+        if world == 1:
+            # ~2 s per 2 kb read per core for the Cython port: size the sample for about --cpu-seconds
+            per_read = 2.2 * (np.diff(offs).mean() / 2000.0) ** 1.0
+            sample = int(max(cores, min(len(offs) - 1, cores * args.cpu_seconds / per_read)))
+            reads = synth.reads_as_strings(concat[:offs[sample]], offs[:sample + 1])
+            dt, hits_cpu, calls_cpu, cells_cpu = cpu_seed_sample(reads, args.thr, cores, n_names=n_names)
+            cpu_baseline = {"value": sample / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                            "gcups": cells_cpu / dt / 1e9, "seconds": dt,
+                            "sample": "first %d reads of the workload, Cython build of oracle/swalign_ref.py + "
+                                      "seeding_ref.py (README.md:18-25 recipe), one process per core" % sample}
+            # the interpreted figure beside it: one read per core
+            dt_py, _, _, cells_py = cpu_seed_sample(reads[:cores], args.thr, cores, n_names=n_names, pure_python=True)
+            cpu_baseline["pure_python"] = {"value": min(cores, len(reads)) / dt_py, "unit": "reads/s", "gcups": cells_py / dt_py / 1e9,
+                                           "sample": "first %d reads, oracle/swalign_ref.py + seeding_ref.py interpreted" % min(cores, len(reads))}
+            cpu_ref = {"n": sample, "py_hits": hits_cpu, "calls": calls_cpu, "cells": cells_cpu}
+        else:
+            # N > 1: no CPU timing (rank 0 shares the host with N - 1 other ranks), but the parity check still runs, against
+            # the C restatement of the oracle on a small sample
+            sample = min(len(offs) - 1, 8 * workers)
+            reads = synth.reads_as_strings(concat[:offs[sample]], offs[:sample + 1])
+            cpu_ref = {"n": sample, "py_hits": None, "calls": None, "cells": None}
+        cpu_ref["c_rows"] = c_oracle_rows(reads, seqs, args.thr, workers if world > 1 else cores)
 
     import torch
     if not torch.cuda.is_available():
@@ -273,15 +375,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from lamprey_b200 import _native, seeding
+    from lamprey_b200 import _native
 
     eng = _native.Engine(local_rank)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     eng.set_scoring(2, -1, -1, -1)
-    ps = seeding.PrimerSet(SCHEMA)
-    from lamprey_b200 import synth as _synth
-    seqs = [s for _, s in _synth.schema_sequences(ps, args.workload)]
     eng.set_queries(seqs)
 
     def barrier():
@@ -289,163 +388,207 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    # pinned host buffers: the reference-facing call takes host memory
-    h_ascii = torch.empty(len(concat), dtype=torch.uint8, pin_memory=True)
-    h_ascii.numpy()[:] = concat
-    h_offs = torch.empty(len(offs), dtype=torch.int64, pin_memory=True)
-    h_offs.numpy()[:] = offs
-    ascii_np, offs_np = h_ascii.numpy(), h_offs.numpy()
+    # page-locked host buffers (lsw_host_alloc): the reference-facing calls take host memory
+    pin_ascii = _native.PinnedArray(len(concat), np.uint8)
+    pin_ascii.array[:] = concat
+    pin_offs = _native.PinnedArray(len(offs), np.int64)
+    pin_offs.array[:] = offs
+    ascii_np, offs_np = pin_ascii.array, pin_offs.array
 
     # integer roofline of this box (not in MEASURED_PEAKS.json)
     peak = {}
     if rank == 0:
-        for mode, name in ((0, "viaddmnmx_s16x2"), (1, "vimnmx3_s16x2"), (2, "iadd"), (3, "imad"), (4, "k1_mix"),
-                           (5, "k1_mix_imad"), (6, "lop3")):
-            ops, _ = eng.measure_int_peak(mode, 20000)
+        for mode, name in ((0, "viaddmnmx_s16x2"), (1, "vimnmx3_s16x2"), (2, "iadd"), (3, "imad"), (8, "vimnmx_s16x2_2op"),
+                           (9, "k1_inner_loop")):
+            ops, _ = eng.measure_int_peak(mode, 20000 if mode != 9 else 4000)
             peak[name] = ops / 1e9
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------
+    t_up0 = time.perf_counter()
     eng.upload_reads(ascii_np, offs_np)
-    n_hits = 0
-    for _ in range(args.warmup):
-        n_hits = eng.find_all(args.thr, fetch=False)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    acc = dict(ms_score=0.0, ms_trace=0.0, ms_other=0.0, ms_total=0.0, launches=0, score_launches=0)
-    e0.record(stream)
-    for _ in range(args.steps):
-        n_hits = eng.find_all(args.thr, fetch=False)
-        c = eng.last_counters
-        for k in ("ms_score", "ms_trace", "ms_other", "ms_total"):
-            acc[k] += c[k]
-        acc["launches"] += c["score_launches"] + c["trace_launches"] + c["other_launches"]
-        acc["score_launches"] += c["score_launches"]
-    e1.record(stream)
-    barrier()
-    t_value = e0.elapsed_time(e1) / 1e3
-    clocks = sampler.stop() if sampler else None
-    cnt = dict(eng.last_counters)
+    upload_alone_ms = 1e3 * (time.perf_counter() - t_up0)
+    t_value, cnt, acc, clocks, n_hits = timed_find_all(eng, torch, stream, args.thr, args.steps, args.warmup, barrier,
+                                                       local_rank if rank == 0 else None)
     t_value, reads_total, cells_total, hits_total = gather_max_and_sum(
         t_value, [args.reads * args.steps, cnt["cells"] * args.steps, n_hits * args.steps])
 
-    # parity spot check against the CPU baseline's own sample (same reads, same threshold)
+    # parity against the CPU sample (same reads, same threshold): every hit, field by field
     parity = None
-    if cpu_baseline is not None:
-        n = cpu_baseline.pop("_n")
+    if cpu_ref is not None:
+        n = cpu_ref["n"]
         eng.upload_reads(ascii_np[:offs_np[n]], offs_np[:n + 1])
         sub = eng.find_all(args.thr)
         c2 = eng.last_counters
-        parity = {"reads": n, "hits_match": int(len(sub)) == cpu_baseline.pop("_hits"),
-                  "calls_match": c2["tasks"] == cpu_baseline.pop("_calls"),
-                  "cells_match": c2["cells"] == cpu_baseline.pop("_cells")}
+        got_rows = [tuple(int(x[k]) for k in ("read", "query", "start", "end", "matches", "mismatches", "score", "q_pos", "q_end", "depth"))
+                    for x in sub]
+        parity = {"reads": n, "hits": len(got_rows),
+                  "hit_records_match_c_oracle": got_rows == [tuple(r) for r in cpu_ref["c_rows"]],
+                  "fields": "read, query, start, end, matches, mismatches, score, q_pos, q_end, depth"}
+        if cpu_ref["py_hits"] is not None:
+            # what the reference itself returns per read: [(start, end, identity, primer_name)] in stable start order
+            offs_h = np.searchsorted(sub["read"], np.arange(n + 1))
+            ident = sub["matches"] / np.maximum(sub["matches"].astype(np.int64) + sub["mismatches"], 1)
+            ok = True
+            for i in range(n):
+                mine = [(int(sub["start"][k]), int(sub["end"][k]), float(ident[k]), names[sub["query"][k]]) for k in range(offs_h[i], offs_h[i + 1])]
+                ok = ok and mine == [tuple(h) for h in cpu_ref["py_hits"][i]]
+            parity.update({"hit_tuples_match_cython_sample": ok, "calls_match": c2["tasks"] == cpu_ref["calls"],
+                           "cells_match": c2["cells"] == cpu_ref["cells"]})
         eng.upload_reads(ascii_np, offs_np)
 
-    # ---- e2e: host buffers in, hits on the host out, every step --------------------------------
-    # The reference-facing call sequence (lsw_upload_reads -> lsw_find_all -> lsw_fetch_hits) from pinned host
-    # memory.  With --e2e-engines 2 (default) two contexts, each on its own CUDA stream and driven by its own
-    # host thread, take alternate steps, so one batch's PCIe copies overlap the other batch's kernels -- the
-    # way a caller streaming FASTQ batches would use the library.  Every step still uploads its own input
-    # and downloads its own hits inside the timed region (transfers are serialised per direction).
+    # ---- extra configs (BASELINE.json configs[3], [4]): same engine, own timing ---------------------------------
+    extra = []
+    for wl, n_reads, x_concat, x_offs in extra_reads:
+        x_seqs = [s for _, s in synth.schema_sequences(ps, wl)]
+        eng.set_queries(x_seqs)
+        eng.upload_reads(x_concat, x_offs)
+        xs = max(2, min(args.steps, 3))
+        t_x, c_x, a_x, clk_x, h_x = timed_find_all(eng, torch, stream, args.thr, xs, 3, barrier, local_rank if rank == 0 else None)
+        t_x, r_x, cells_x = gather_max_and_sum(t_x, [n_reads * xs, c_x["cells"] * xs])
+        if rank == 0:
+            k1 = k1_rates(c_x, a_x, xs)
+            pk = peak.get("viaddmnmx_s16x2", 0.0) * 4.0 / K1_DPX_PER_4_CELLS
+            extra.append({"workload": wl, "reads_per_gpu": n_reads, "n_gpus": world, "mean_len": float(np.diff(x_offs).mean()),
+                          "schema_sequences": len(x_seqs), "steps": xs, "warmup": 3, "value": r_x / t_x, "unit": "reads/s",
+                          "ms_per_step": 1e3 * t_x / xs, "gcups": cells_x / t_x / 1e9,
+                          "gcups_computed": c_x["computed_cells"] * xs * world / t_x / 1e9,
+                          "tasks_per_step": c_x["tasks"], "hits_per_step": h_x, "rounds": c_x["rounds"], "fallbacks": c_x["fallbacks"],
+                          "breakdown_ms_per_step": {k: a_x[k] / xs for k in ("ms_score", "ms_trace", "ms_other", "ms_total")},
+                          "roofline": {"bound": "int_alu", "achieved": k1["all"], "peak": pk, "unit": "GCUPS",
+                                       "frac": k1["all"] / pk if (pk and k1["all"]) else None, "k1_gcups": k1},
+                          "device_bytes": c_x["device_bytes"], "reuse_dropped": c_x["reuse_dropped"], "clocks": clk_x})
+    del extra_reads
+    eng.set_queries(seqs)
+    eng.close()
+
+    # ---- e2e: host buffers in, hits on the host out, every step, through the library's pool --------------------
+    # lsw_pool_submit / lsw_pool_wait (include/lsw.h): the pool's worker threads run lsw_upload_reads -> lsw_find_all ->
+    # lsw_fetch_hits_compact per batch; with two contexts per device one batch's PCIe copies overlap the next batch's kernels.
+    # Every step uploads its own input and downloads its own hits inside the timed region.
     e2e = None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if not args.no_e2e:
-        import threading
-        n_eng = max(1, args.e2e_engines)
-        engines = [eng]
-        for _ in range(n_eng - 1):
-            e2 = _native.Engine(local_rank)
-            e2.set_scoring(2, -1, -1, -1)
-            e2.set_queries(seqs)
-            engines.append(e2)
-        if n_eng > 1:
-            eng.set_stream(0)                                        # back to the context's own non-blocking stream
-        bufs = []
-        for _ in engines:
-            hb = torch.empty(max(1, int(n_hits * 1.05) + 1024) * 32, dtype=torch.uint8, pin_memory=True)
-            bufs.append(hb.numpy().view(_native.HIT_DT))
-        got = [0] * n_eng
-        h2d_lock, d2h_lock = threading.Lock(), threading.Lock()       # one transfer per direction at a time
-        # one find_all at a time: two contexts computing side by side share SMs and L2 and each runs at less than half
-        # speed, while the copies of the waiting context overlap the running one's kernels either way
-        gpu_lock = threading.Lock() if os.environ.get("LSW_E2E_COMPUTE_LOCK", "1") != "0" else contextlib.nullcontext()
-
-        phase = {"upload": [], "find_all": [], "fetch": []}          # host wall clock of every call (s), all contexts
-
-        def e2e_worker(k, my_steps):
-            for _ in range(my_steps):
-                with h2d_lock:
-                    t0 = time.perf_counter()
-                    engines[k].upload_reads(ascii_np, offs_np)       # H2D of this step's reads (+ re-coding)
-                    t1 = time.perf_counter()
-                with gpu_lock:
-                    t1b = time.perf_counter()
-                    engines[k].find_all(args.thr, fetch=False)       # overlaps the other context's copies
-                    t2 = time.perf_counter()
-                with d2h_lock:
-                    t3 = time.perf_counter()
-                    got[k] = len(engines[k].fetch_hits(out=bufs[k]))  # D2H of this step's hits
-                    t4 = time.perf_counter()
-                phase["upload"].append(t1 - t0); phase["find_all"].append(t2 - t1b); phase["fetch"].append(t4 - t3)
+        depth = max(1, args.e2e_depth)
+        pool = _native.Pool([local_rank], depth)
+        pool.configure(seqs, args.thr, compact=True)
+        cap = int(n_hits * 1.05) + 4096
+        outs = [_native.PinnedArray(cap, _native.HIT16_DT) for _ in range(depth)]
 
         def run_steps(total):
-            per = [total // n_eng + (1 if k < total % n_eng else 0) for k in range(n_eng)]
-            ths = [threading.Thread(target=e2e_worker, args=(k, per[k])) for k in range(n_eng) if per[k]]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
+            tickets, last, tms = [], 0, []
+            for k in range(total):
+                tickets.append(pool.submit(ascii_np, offs_np, outs[k % depth].array))
+                if len(tickets) >= depth:
+                    h, _, tm = pool.wait(tickets.pop(0))
+                    last = len(h); tms.append(tm)
+            while tickets:
+                h, _, tm = pool.wait(tickets.pop(0))
+                last = len(h); tms.append(tm)
+            return last, tms
 
-        run_steps(max(n_eng, args.warmup - 2))
-        for v in phase.values():
-            del v[:]
+        run_steps(max(depth, args.warmup - 1))
         barrier()
         e0.record(stream)
-        run_steps(args.steps)
-        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got, tms = run_steps(args.steps)
+        t_wall = time.perf_counter() - t0          # the pool's contexts run on their own streams: wall clock around the blocking waits
         e1.record(stream)
         barrier()
-        t_e2e = e0.elapsed_time(e1) / 1e3
-        t_e2e, reads_e2e = gather_max_and_sum(t_e2e, [args.reads * args.steps])
+        t_e2e, reads_e2e = gather_max_and_sum(t_wall, [args.reads * args.steps])
         e2e = {"value": reads_e2e / t_e2e, "unit": "reads/s",
-               "h2d_bytes_per_step": int(ascii_np.nbytes + offs_np.nbytes), "d2h_bytes_per_step": int(max(got) * 32),
-               "ms_per_step": 1e3 * t_e2e / args.steps, "engines": n_eng, "hits_per_step": int(max(got)),
-               "host_ms_per_call": {k: 1e3 * float(np.mean(v)) for k, v in phase.items() if v},
-               "call": "per step: lsw_upload_reads + lsw_find_all + lsw_fetch_hits from/to pinned host buffers; %d contexts "
-                       "(CUDA streams, one host thread each) take alternate steps so one step's copies overlap another's kernels; "
-                       "one lsw_find_all runs at a time" % n_eng}
-        for e2 in engines[1:]:
-            e2.close()
+               "h2d_bytes_per_step": int(ascii_np.nbytes + offs_np.nbytes), "d2h_bytes_per_step": int(got * 16),
+               "ms_per_step": 1e3 * t_e2e / args.steps, "contexts": depth, "hits_per_step": int(got),
+               "host_ms_per_call": {k: 1e3 * float(np.mean([tm[k + "_s"] for tm in tms])) for k in ("upload", "find", "fetch")},
+               "upload_alone_ms": upload_alone_ms,
+               "call": "per step: lsw_pool_submit + lsw_pool_wait on a pool of %d contexts of this GPU (the library's worker threads run "
+                       "lsw_upload_reads -> lsw_find_all -> lsw_fetch_hits_compact; one batch's copies overlap the next batch's kernels); "
+                       "read text and 16-byte hit records in page-locked host buffers" % depth}
+        # the same loop with ONE context: no overlap at all (upload, seed, download one after the other)
+        if rank == 0 and world == 1:
+            pool.close()
+            pool = _native.Pool([local_rank], 1)
+            pool.configure(seqs, args.thr, compact=True)
+            pool.wait(pool.submit(ascii_np, offs_np, outs[0].array))
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                pool.wait(pool.submit(ascii_np, offs_np, outs[0].array))
+            t1 = time.perf_counter() - t0
+            e2e["single_context"] = {"value": args.reads * args.steps / t1, "unit": "reads/s", "ms_per_step": 1e3 * t1 / args.steps}
+        pool.close()
+        for o in outs:
+            o.close()
+
+    # ---- strong scaling: ONE fixed batch (rank 0's) over all N GPUs, host-side gather included --------------------
+    # The product path for several GPUs is one process with one thread + context per GPU (seeding.seed_reads(devices=...),
+    # lsw_pool_*): rank 0 drives all N GPUs while the other ranks, whose engines are closed, wait at the barrier.
+    strong = None
+    if not args.no_strong:
+        barrier()
+        if rank == 0:
+            ndev = min(world, torch.cuda.device_count())
+            pool = _native.Pool(list(range(ndev)), 2)
+            pool.configure(seqs, args.thr, compact=True)
+            cap = int(n_hits * 1.05) + 4096
+            outs = [_native.PinnedArray(cap, _native.HIT16_DT) for _ in range(2)]
+            for k in range(2):
+                pool.wait(pool.submit(ascii_np, offs_np, outs[k].array))           # warm-up: buffers of every context
+            lat = []
+            for _ in range(2):                                                     # latency of one batch, nothing else in flight
+                _, _, tm = pool.wait(pool.submit(ascii_np, offs_np, outs[0].array))
+                lat.append(tm)
+            t0 = time.perf_counter()
+            tickets, tms = [], []
+            for k in range(args.steps + 1):
+                tickets.append(pool.submit(ascii_np, offs_np, outs[k % 2].array))
+                if len(tickets) >= 2:
+                    _, _, tm = pool.wait(tickets.pop(0)); tms.append(tm)
+            while tickets:
+                _, _, tm = pool.wait(tickets.pop(0)); tms.append(tm)
+            t_s = time.perf_counter() - t0
+            best = min(lat, key=lambda t: t["total_s"])
+            strong = {"scaling": "strong", "n_gpus": ndev, "reads": args.reads, "workload": args.workload,
+                      "value": args.reads * (args.steps + 1) / t_s, "unit": "reads/s", "ms_per_batch_pipelined": 1e3 * t_s / (args.steps + 1),
+                      "ms_per_batch_latency": 1e3 * best["total_s"],
+                      "latency_phases_ms": {k: 1e3 * best[k + "_s"] for k in ("upload", "find", "fetch", "gather_wait")},
+                      "gather_ms": 1e3 * (best["fetch_s"] + best["gather_wait_s"]),
+                      "gather_share_of_batch": (best["fetch_s"] + best["gather_wait_s"]) / best["total_s"] if best["total_s"] > 0 else None,
+                      "reads_per_device": best["reads"][:ndev], "hits_per_device": best["hits"][:ndev],
+                      "what": "one batch split over the GPUs in contiguous read ranges balanced by bases (lsw_pool_submit), seeded with "
+                              "global read ids, hits copied from every GPU straight into their place in one host buffer (the gather: "
+                              "a range waits for the hit counts of the ranges before it, then downloads); H2D and D2H inside the timing"}
+            pool.close()
+            for o in outs:
+                o.close()
+        barrier()
 
     if rank == 0:
         gcups = cells_total / t_value / 1e9
-        score_s = acc["ms_score"] / 1e3
-        # cells K1 actually filled (child tasks reuse the round-0 blocks of their read, so this is below the
-        # reference-equivalent count that `gcups` uses)
-        k1_gcups = cnt["computed_cells"] * args.steps / score_s / 1e9 if score_s > 0 else None
+        k1 = k1_rates(cnt, acc, args.steps)
         peak_ops = peak.get("viaddmnmx_s16x2", 0.0)      # G lane-ops / s of the packed DPX instruction K1 is built from
-        # one packed (s16x2) instruction lane updates 2 cells' worth of one algorithmic op
-        peak_gcups = peak_ops * 2.0 / ALG_OPS_PER_CELL if peak_ops else None
+        # the ceiling: K1 issues 5 packed DPX lane-ops per 4 cells and the DPX (ALU) pipe retires peak_ops of them per second
+        peak_dpx = peak_ops * 4.0 / K1_DPX_PER_4_CELLS if peak_ops else None
+        peak_survey = peak_ops * 2.0 / ALG_OPS_PER_CELL if peak_ops else None
+        peak_inner = peak.get("k1_inner_loop", 0.0) * 4.0 / 9.0 if peak.get("k1_inner_loop") else None
+        ncu = ncu_capture()
         roofline = {"bound": "int_alu", "kernel": "k_score<NR> (K1: DP fill + arg-max)",
-                    "achieved": k1_gcups, "peak": peak_gcups, "unit": "GCUPS",
-                    "frac": (k1_gcups / peak_gcups) if (k1_gcups and peak_gcups) else None,
-                    "traffic": None, "traffic_ncu": ncu_traffic(),
-                    # K1's real instruction mix: 5 packed DPX lane-ops per 4 cells (SASS-checked) -> the rate at which the
-                    # DPX pipe alone would saturate, and the rate a register-only microbenchmark of the row mix reaches
-                    "peak_dpx_only": peak_ops * 4.0 / 5.0 if peak_ops else None,
-                    "frac_dpx_only": (k1_gcups / (peak_ops * 4.0 / 5.0)) if (k1_gcups and peak_ops) else None,
-                    # (9 instructions per 4 cells at the lane-op rate the mixed DPX/add chain measures)
-                    "peak_row_mix_microbench": peak.get("k1_mix", 0.0) * 4.0 / 9.0 if peak.get("k1_mix") else None,
-                    "frac_row_mix_microbench": (k1_gcups / (peak["k1_mix"] * 4.0 / 9.0)) if (k1_gcups and peak.get("k1_mix")) else None,
-                    "peak_source": "lsw_measure_int_peak on this box (MEASURED_PEAKS.json has no integer rate): "
-                                   "VIADDMNMX.S16x2 lane-ops/s x 2 cells / %d algorithmic ops per cell" % ALG_OPS_PER_CELL,
+                    "achieved": k1["all"], "peak": peak_dpx, "unit": "GCUPS",
+                    "frac": (k1["all"] / peak_dpx) if (k1["all"] and peak_dpx) else None,
+                    "peak_definition": "DPX-pipe ceiling of K1's own instruction mix: %d packed VIADDMNMX/VIMNMX3.S16x2 lane-ops per 4 cells "
+                                       "at the VIADDMNMX.S16x2 rate lsw_measure_int_peak measures on this box (MEASURED_PEAKS.json has no "
+                                       "integer rate)" % K1_DPX_PER_4_CELLS,
+                    "traffic": ncu["dram_bytes_per_launch"] if ncu else None, "ncu": ncu,
+                    "k1_gcups": k1,
+                    "frac_round0": (k1["round0"] / peak_dpx) if (k1["round0"] and peak_dpx) else None,
+                    "frac_children": (k1["children"] / peak_dpx) if (k1["children"] and peak_dpx) else None,
+                    # SURVEY.md 8d's model (6 int32-lane ops per cell, packed x2): beaten by the real mix, so not a ceiling
+                    "peak_survey_model": peak_survey, "frac_survey_model": (k1["all"] / peak_survey) if (k1["all"] and peak_survey) else None,
+                    # K1's inner loop alone (column2 with its LDS.64 profile loads, K1's launch shape; intpeak mode 9)
+                    "peak_inner_loop_microbench": peak_inner,
+                    "frac_inner_loop_microbench": (k1["all"] / peak_inner) if (k1["all"] and peak_inner) else None,
                     "int_peak_glaneops": peak, "launches": acc["score_launches"],
                     "avg_launch_ms": acc["ms_score"] / max(1, acc["score_launches"]),
                     "k1_share_of_step": acc["ms_score"] / max(1e-9, acc["ms_total"]),
                     "computed_cells_per_step": cnt["computed_cells"], "reference_cells_per_step": cnt["cells"],
-                    "k1_reference_equivalent_gcups": cnt["cells"] * args.steps / score_s / 1e9 if score_s > 0 else None,
                     "cells_per_lane_step": cnt["computed_cells"] / max(1, cnt["steps"])}
         line = {"metric": "reads_per_sec", "value": reads_total / t_value, "unit": "reads/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps,
@@ -456,11 +599,12 @@ def main():
                            "schema": "H3.3_set1 (%d sequences, %d rows)" % (len(seqs), sum(len(q) for q in seqs)), "threshold": args.thr,
                            "l2": "inputs larger than L2 (%.2f GB of read codes + task lists per step)" % (len(concat) / 1e9),
                            "tasks_per_step": cnt["tasks"], "cells_per_step": cnt["cells"], "hits_per_step": n_hits,
-                           "rounds": cnt["rounds"]},
+                           "rounds": cnt["rounds"], "fallbacks": cnt["fallbacks"]},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": acc["launches"],
                 "breakdown_ms_per_step": {k: acc[k] / args.steps for k in ("ms_score", "ms_trace", "ms_other", "ms_total")},
-                "parity_vs_cpu_sample": parity}
+                "device_bytes": cnt["device_bytes"], "reuse_dropped": cnt["reuse_dropped"],
+                "parity_vs_cpu_sample": parity, "strong_scaling": strong, "extra_configs": extra}
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -75,6 +75,21 @@ typedef struct {
     int32_t reserved2;
 } lsw_hit;                         /* 32 bytes */
 
+/* The same hit in 16 bytes (half the device -> host traffic of a batch; ~128 hits per 2 kb concatemer read).
+ * end = start + span; score = match*matches + mismatch*mm - |gap|*(I + D) with
+ *   a = span + (q_end - q_pos) - matches - mismatches   (aligned columns),   mm = a - matches,
+ *   D = span - a,   I = (q_end - q_pos) - a. */
+typedef struct {
+    uint32_t read;
+    uint32_t start;
+    uint8_t  span;                 /* end - start: a path spans < Q + match*Q/|gap| <= 190 read columns */
+    uint8_t  query;
+    uint16_t depth;                /* saturates at 65535 */
+    uint8_t  matches;              /* bits 0-6; bit 7 = the `reserved` survivor flag of lsw_set_overlap */
+    uint8_t  mismatches;
+    uint8_t  q_pos, q_end;
+} lsw_hit16;                       /* 16 bytes */
+
 typedef struct {
     int64_t tasks;        /* align() invocations the reference would have made            */
     int64_t cells;        /* sum over those of len(slice) * len(query)  (the CUPS unit)   */
@@ -94,6 +109,12 @@ typedef struct {
                              were redone by the full-window kernel                              */
     int64_t computed_cells; /* cells the score kernels actually filled: child tasks reuse the
                              round-0 matrix of their read (lsw_reuse.cuh), so this is < cells     */
+    int64_t device_bytes; /* device memory the context holds after this call (high-water: buffers only grow) */
+    int64_t reuse_dropped;/* 1 if the block bests of lsw_reuse.cuh could not be allocated and every round aligned
+                             whole slices instead (same results, more cells); 0 otherwise               */
+    float   ms_score_round0; /* part of ms_score spent on whole reads (round 0); the rest ran on child segments */
+    float   reserved3;
+    int64_t computed_cells_round0;
 } lsw_counters;
 
 /* cigar runs are (count << 2) | op with op 1 = 'M', 2 = 'I', 3 = 'D' */
@@ -136,12 +157,52 @@ int lsw_set_overlap(lsw_ctx* ctx, int allowed_overlap);
 int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap);   /* 0 = default (total bases / 8 + 4096) */
 int lsw_find_all(lsw_ctx* ctx, double identity_threshold, int64_t* n_hits, lsw_counters* counters);
 int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out);
+int lsw_fetch_hits_compact(lsw_ctx* ctx, lsw_hit16* out, int64_t cap, int64_t* n_out);   /* same hits, 16-byte records */
+
+/* Page-locked host memory for read and hit buffers: copies from / to it run at PCIe speed and asynchronously.  Any host
+ * memory works with every entry point; pageable buffers are staged by the driver (several times slower). */
+int  lsw_host_alloc(int64_t bytes, void** out);
+void lsw_host_free(void* p);
 
 /* Integer-pipe roofline microbenchmark: ops/s of independent chains of one
  * instruction mix on every SM.  mode: see lamprey_b200/csrc/intpeak.cuh.  Returns lane-ops per second. */
 int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per_s, float* ms);
 
 int lsw_version(void);
+
+/* ---- Pool: several contexts, one host thread each, behind one handle --------------------------------------------
+ * The reference deals the reads of a FASTQ over worker processes and collects their results from a queue
+ * (/root/reference/lamprey.py:2182-2207: `read_index % num_processes`, then `q.get()` per worker).  A pool does the same
+ * with GPUs: lsw_pool_submit() splits ONE batch into contiguous read ranges balanced by bases, one per device; every range
+ * is uploaded, seeded (findAllPrimerAlignments with global read ids) and fetched by its device's worker thread, and the
+ * hits of all ranges land in the caller's buffer in global (read, start, query) order -- the host-side gather; there is no
+ * device-to-device traffic.  With contexts_per_device = 2, consecutive batches alternate between two contexts of a device,
+ * so one batch's PCIe copies overlap another batch's kernels (one lsw_find_all runs on a device at a time).
+ * submit returns at once; the read and hit buffers must stay valid until lsw_pool_wait(ticket) returns. */
+typedef struct lsw_pool lsw_pool;
+
+#define LSW_HITS_WIDE    0     /* lsw_hit   (32 bytes) */
+#define LSW_HITS_COMPACT 1     /* lsw_hit16 (16 bytes) */
+
+typedef struct {
+    double upload_s, find_s, fetch_s;   /* host wall clock of the three phases, max over the batch's ranges          */
+    double gather_wait_s;               /* longest wait of a range for the hit counts of the ranges before it         */
+    double total_s;                     /* submit -> last range done                                                  */
+    int64_t reads[8], hits[8];          /* per device (first 8): reads and hits of its range                          */
+} lsw_pool_times;
+
+int  lsw_pool_create(int n_devices, const int* devices, int contexts_per_device, lsw_pool** out);
+void lsw_pool_destroy(lsw_pool* pool);
+const char* lsw_pool_last_error(const lsw_pool* pool);      /* pool may be NULL: error of the last failed lsw_pool_create */
+/* scoring + queries + hit test of every context (lsw_set_scoring, lsw_set_queries, lsw_set_overlap, the threshold of
+ * lsw_find_all) and the record format of the hit buffers */
+int  lsw_pool_configure(lsw_pool* pool, int match, int mismatch, int gap, int gap_ext, int n_queries, const uint8_t* concat,
+                        const int32_t* offs, double identity_threshold, int allowed_overlap, int hit_format);
+int  lsw_pool_submit(lsw_pool* pool, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, void* hits_out,
+                     int64_t hits_cap, int64_t* ticket);
+/* blocks until the batch is done.  *n_hits = hits of the whole batch (> hits_cap with LSW_E_OVERFLOW: nothing was copied
+ * for the ranges that did not fit); counters = sums over the ranges, ms_* = the slowest range's. */
+int  lsw_pool_wait(lsw_pool* pool, int64_t ticket, int64_t* n_hits, lsw_counters* counters, lsw_pool_times* times);
 
 #ifdef __cplusplus
 }

@@ -25,13 +25,23 @@ COUNTERS_DT = np.dtype([("tasks", "<i8"), ("cells", "<i8"), ("top_tasks", "<i8")
                         ("traced", "<i8"), ("hits", "<i8"), ("rounds", "<i4"), ("reserved", "<i4"),
                         ("ms_score", "<f4"), ("ms_trace", "<f4"), ("ms_other", "<f4"), ("ms_total", "<f4"),
                         ("score_launches", "<i8"), ("trace_launches", "<i8"), ("other_launches", "<i8"),
-                        ("steps", "<i8"), ("fallbacks", "<i8"), ("computed_cells", "<i8")])
-assert TASK_DT.itemsize == 16 and RESULT_DT.itemsize == 40 and HIT_DT.itemsize == 32 and COUNTERS_DT.itemsize == 120
+                        ("steps", "<i8"), ("fallbacks", "<i8"), ("computed_cells", "<i8"), ("device_bytes", "<i8"),
+                        ("reuse_dropped", "<i8"), ("ms_score_round0", "<f4"), ("reserved3", "<f4"),
+                        ("computed_cells_round0", "<i8")])
+# lsw_hit16: the same hit in 16 bytes (include/lsw.h)
+HIT16_DT = np.dtype([("read", "<u4"), ("start", "<u4"), ("span", "u1"), ("query", "u1"), ("depth", "<u2"),
+                     ("matches", "u1"), ("mismatches", "u1"), ("q_pos", "u1"), ("q_end", "u1")])
+assert TASK_DT.itemsize == 16 and RESULT_DT.itemsize == 40 and HIT_DT.itemsize == 32 and COUNTERS_DT.itemsize == 152
+assert HIT16_DT.itemsize == 16
 
 # every symbol include/lsw.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",
            "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_overlap", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
-           "lsw_measure_int_peak", "lsw_version")
+           "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_host_alloc", "lsw_host_free",
+           "lsw_pool_create", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_pool_configure", "lsw_pool_submit", "lsw_pool_wait")
+HITS_WIDE, HITS_COMPACT = 0, 1
+POOL_TIMES_DT = np.dtype([("upload_s", "<f8"), ("find_s", "<f8"), ("fetch_s", "<f8"), ("gather_wait_s", "<f8"), ("total_s", "<f8"),
+                          ("reads", "<i8", (8,)), ("hits", "<i8", (8,))])
 
 _lib = None
 
@@ -62,8 +72,20 @@ def load():
     lib.lsw_find_all.argtypes = [vp, dbl, ctypes.POINTER(i64), vp]
     lib.lsw_fetch_hits.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_measure_int_peak.argtypes = [vp, i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_float)]
+    lib.lsw_fetch_hits_compact.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
+    lib.lsw_host_alloc.argtypes = [i64, ctypes.POINTER(vp)]
+    lib.lsw_host_free.argtypes = [vp]
+    lib.lsw_host_free.restype = None
+    lib.lsw_pool_create.argtypes = [i32, ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
+    lib.lsw_pool_destroy.argtypes = [vp]
+    lib.lsw_pool_destroy.restype = None
+    lib.lsw_pool_last_error.argtypes = [vp]
+    lib.lsw_pool_last_error.restype = ctypes.c_char_p
+    lib.lsw_pool_configure.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, dbl, i32, i32]
+    lib.lsw_pool_submit.argtypes = [vp, i64, vp, vp, vp, i64, ctypes.POINTER(i64)]
+    lib.lsw_pool_wait.argtypes = [vp, i64, ctypes.POINTER(i64), vp, vp]
     for name in SYMBOLS:
-        if name not in ("lsw_destroy", "lsw_last_error"):
+        if name not in ("lsw_destroy", "lsw_last_error", "lsw_host_free", "lsw_pool_destroy", "lsw_pool_last_error"):
             getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -81,6 +103,129 @@ def concat_sequences(seqs):
     if bs:
         offs[1:] = np.cumsum([len(b) for b in bs])
     return concat, offs
+
+
+def expand_hits(h16, match=2, mismatch=-1, gap=-1):
+    """lsw_hit16 records -> HIT_DT records (end, score and the survivor flag are re-derived: see include/lsw.h)."""
+    out = np.zeros(len(h16), HIT_DT)
+    m = (h16["matches"] & 0x7F).astype(np.int32)
+    x = h16["mismatches"].astype(np.int32)
+    span = h16["span"].astype(np.int32)
+    qspan = h16["q_end"].astype(np.int32) - h16["q_pos"]
+    a = span + qspan - m - x                      # aligned (M) columns
+    out["read"] = h16["read"]; out["start"] = h16["start"]; out["end"] = h16["start"].astype(np.int64) + span
+    out["query"] = h16["query"]; out["depth"] = np.minimum(h16["depth"], 32767)
+    out["matches"] = m; out["mismatches"] = x
+    out["score"] = match * m + mismatch * (a - m) + gap * ((span - a) + (qspan - a))
+    out["q_pos"] = h16["q_pos"]; out["q_end"] = h16["q_end"]
+    out["reserved"] = h16["matches"] >> 7
+    return out
+
+
+class PinnedArray(object):
+    """A numpy array over page-locked host memory (lsw_host_alloc): copies from / to it run at PCIe speed.  Keep the
+    object alive while the array is in use; close() (or garbage collection) frees the memory."""
+
+    def __init__(self, count, dtype):
+        lib = load()
+        self.dtype = np.dtype(dtype)
+        nbytes = max(1, int(count) * self.dtype.itemsize)
+        p = ctypes.c_void_p(0)
+        rc = lib.lsw_host_alloc(nbytes, ctypes.byref(p))
+        if rc != LSW_OK:
+            raise MemoryError("lsw_host_alloc(%d) failed (%d)" % (nbytes, rc))
+        self._lib, self._p = lib, p
+        buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=np.uint8, count=int(count) * self.dtype.itemsize).view(self.dtype)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._lib.lsw_host_free(self._p)
+            self._p = None
+
+    __del__ = close
+
+
+class Pool(object):
+    """Several contexts behind one handle (include/lsw.h "Pool"): one batch is split over `devices` by bases and the hits come
+    back gathered in global read order; with contexts_per_device = 2 consecutive batches overlap copies and kernels."""
+
+    def __init__(self, devices=(0,), contexts_per_device=1):
+        lib = load()
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = ctypes.c_void_p(0)
+        rc = lib.lsw_pool_create(len(devices), devs, int(contexts_per_device), ctypes.byref(h))
+        if rc != LSW_OK:
+            raise RuntimeError("lsw_pool_create failed (%d): %s" % (rc, lib.lsw_pool_last_error(None).decode()))
+        self._lib, self._h = lib, h
+        self.devices = [int(d) for d in devices]
+        self.contexts_per_device = int(contexts_per_device)
+        self.hit_format = HITS_WIDE
+        self.scoring = (2, -1, -1)
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lsw_pool_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc == LSW_OK:
+            return
+        msg = "%s failed (%d): %s" % (what, rc, self._lib.lsw_pool_last_error(self._h).decode())
+        if rc == LSW_E_UNSUPPORTED:
+            raise NotImplementedError(msg) if "not implemented" in msg else ValueError(msg)
+        if rc in (LSW_E_ARG, LSW_E_STATE):
+            raise ValueError(msg)
+        if rc == LSW_E_OVERFLOW:
+            raise OverflowError(msg)
+        raise RuntimeError(msg)
+
+    def configure(self, seqs, threshold, match=2, mismatch=-1, gap=-1, gap_ext=-1, allowed_overlap=None, compact=False):
+        concat, offs = concat_sequences(seqs)
+        offs32 = offs.astype(np.int32)
+        fmt = HITS_COMPACT if compact else HITS_WIDE
+        self._check(self._lib.lsw_pool_configure(self._h, int(match), int(mismatch), int(gap), int(gap_ext), len(seqs), _ptr(concat),
+                                                 _ptr(offs32), float(threshold), -1 if allowed_overlap is None else int(allowed_overlap),
+                                                 fmt), "lsw_pool_configure")
+        self.hit_format = fmt
+        self.scoring = (int(match), int(mismatch), int(gap))
+
+    @property
+    def hit_dtype(self):
+        return HIT16_DT if self.hit_format == HITS_COMPACT else HIT_DT
+
+    def submit(self, ascii_u8, offs_i64, out):
+        """-> ticket.  `out` is a hit_dtype array the hits are written into; the three arrays must stay alive (and
+        unmodified) until wait(ticket)."""
+        a = np.ascontiguousarray(ascii_u8, dtype=np.uint8)
+        o = np.ascontiguousarray(offs_i64, dtype=np.int64)
+        assert out.dtype == self.hit_dtype and out.flags["C_CONTIGUOUS"]
+        t = ctypes.c_int64(0)
+        self._check(self._lib.lsw_pool_submit(self._h, len(o) - 1, _ptr(a), _ptr(o), _ptr(out), len(out), ctypes.byref(t)),
+                    "lsw_pool_submit")
+        self._keep[t.value] = (a, o, out)
+        return t.value
+
+    def wait(self, ticket):
+        """-> (hits view of the submitted buffer, counters dict, times dict).  OverflowError carries the needed count in
+        .needed when the buffer was too small."""
+        n = ctypes.c_int64(0)
+        cnt = np.zeros(1, COUNTERS_DT)
+        tm = np.zeros(1, POOL_TIMES_DT)
+        rc = self._lib.lsw_pool_wait(self._h, int(ticket), ctypes.byref(n), _ptr(cnt), _ptr(tm))
+        _, _, out = self._keep.pop(ticket, (None, None, None))
+        if rc == LSW_E_OVERFLOW:
+            e = OverflowError("hit buffer too small: %d records are needed" % n.value)
+            e.needed = n.value
+            raise e
+        self._check(rc, "lsw_pool_wait")
+        counters = {k: cnt[0][k].item() for k in COUNTERS_DT.names}
+        times = {k: (tm[0][k].tolist() if tm[0][k].ndim else tm[0][k].item()) for k in POOL_TIMES_DT.names}
+        return out[:n.value], counters, times
 
 
 class Engine(object):
@@ -204,6 +349,14 @@ class Engine(object):
             out = np.zeros(int(n), HIT_DT)
         got = ctypes.c_int64(0)
         self._check(self._lib.lsw_fetch_hits(self._h, _ptr(out), len(out), ctypes.byref(got)), "lsw_fetch_hits")
+        return out[:got.value]
+
+    def fetch_hits_compact(self, n=None, out=None):
+        """The hits of the last find_all as 16-byte records (HIT16_DT); expand_hits() turns them into HIT_DT."""
+        if out is None:
+            out = np.zeros(int(n), HIT16_DT)
+        got = ctypes.c_int64(0)
+        self._check(self._lib.lsw_fetch_hits_compact(self._h, _ptr(out), len(out), ctypes.byref(got)), "lsw_fetch_hits_compact")
         return out[:got.value]
 
     def measure_int_peak(self, mode, iters=20000):

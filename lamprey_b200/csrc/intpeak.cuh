@@ -12,6 +12,7 @@
 //   6  LOP3                       (two dependent 3-input logic ops per chain step)
 //   7  VIADDMNMX.S16x2.RELU
 //   8  VIMNMX.S16x2 (2-input)
+//   9  K1's real inner loop (lsw.cu k_intpeak_k1row: ScoreLane<24>::column2 with its LDS.64 profile loads, K1's launch shape)
 #pragma once
 #include <stdint.h>
 

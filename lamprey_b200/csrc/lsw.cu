@@ -75,12 +75,16 @@ struct TaskBuf {
 
 struct Timed { cudaEvent_t e0, e1; int kind; };
 
+constexpr int64_t UPLOAD_CHUNK = 64ll << 20;          // bytes of read text per staged host -> device copy (lsw_upload_reads)
+
 }  // namespace
 
 struct lsw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;               // lsw_upload_reads: host -> staging copies, one chunk ahead of the re-coding
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_coded[2] = {nullptr, nullptr};
     std::string err;
     int num_sms = 0;
 
@@ -100,7 +104,7 @@ struct lsw_ctx {
     DevBuf d_fb2[NCLASS], d_fb2cnt, d_head2;
     DevBuf d_fallback[NCLASS], d_nfallback, d_cand_key[NCLASS], d_cand_sorted[NCLASS], d_cand_key_sorted[NCLASS], d_cand_rec[NCLASS];
     DevBuf d_res, d_seg[2], d_head, d_cand[NCLASS], d_ncand, d_counters, d_child_flag, d_pos,
-           d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_nhits, d_keys[2], d_vals[2], d_err,
+           d_cubtemp, d_scratch, d_hits, d_hits_sorted, d_hits16, d_nhits, d_keys[2], d_vals[2], d_err,
            d_results, d_cigar, d_ncigar;
     int64_t hit_cap_user = 0;
     int32_t read_base = 0;
@@ -118,6 +122,30 @@ struct lsw_ctx {
 };
 
 namespace {
+
+// every device buffer of a context (lsw_destroy releases them; lsw_counters.device_bytes sums their capacities)
+std::vector<DevBuf*> all_bufs(lsw_ctx* ctx) {
+    std::vector<DevBuf*> v = {&ctx->d_qcodes, &ctx->d_qlen, &ctx->d_cand_ok, &ctx->d_ascii, &ctx->d_offs_in, &ctx->d_codes,
+                              &ctx->d_roff, &ctx->d_rlen, &ctx->d_order, &ctx->d_order_tmp, &ctx->d_len_tmp[0], &ctx->d_len_tmp[1],
+                              &ctx->d_res, &ctx->d_seg[0], &ctx->d_seg[1], &ctx->d_head, &ctx->d_ncand, &ctx->d_counters,
+                              &ctx->d_child_flag, &ctx->d_pos, &ctx->d_cubtemp, &ctx->d_scratch, &ctx->d_hits, &ctx->d_hits_sorted,
+                              &ctx->d_hits16, &ctx->d_nhits, &ctx->d_keys[0], &ctx->d_keys[1], &ctx->d_vals[0], &ctx->d_vals[1],
+                              &ctx->d_err, &ctx->d_results, &ctx->d_cigar, &ctx->d_ncigar, &ctx->d_nfallback, &ctx->d_fb2cnt,
+                              &ctx->d_head2, &ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_bb1, &ctx->d_bb1_off, &ctx->d_nseg,
+                              &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_kt};
+    for (int c = 0; c < NCLASS; c++)
+        for (DevBuf* b : {&ctx->d_class_seqs[c], &ctx->d_cand[c], &ctx->d_fallback[c], &ctx->d_cand_key[c], &ctx->d_cand_sorted[c],
+                          &ctx->d_cand_key_sorted[c], &ctx->d_cand_rec[c], &ctx->d_fb2[c]}) v.push_back(b);
+    for (TaskBuf* t : {&ctx->tb[0], &ctx->tb[1], &ctx->child})
+        for (DevBuf* b : {&t->read, &t->a, &t->b, &t->seq, &t->orig}) v.push_back(b);
+    return v;
+}
+
+int64_t device_bytes(lsw_ctx* ctx) {
+    int64_t n = 0;
+    for (DevBuf* b : all_bufs(ctx)) n += (int64_t)b->cap;
+    return n;
+}
 
 #define CK(call)                                                                              \
     do {                                                                                      \
@@ -137,13 +165,14 @@ int fail(lsw_ctx* ctx, int code, const char* msg) { ctx->err = msg; return code;
 
 // ASCII -> read codes (A,C,G,T -> 0..3 after upper-casing, anything else -> 4), one warp per read,
 // each read written at a 16-byte aligned offset.
-__global__ void k_encode_reads(const uint8_t* __restrict__ ascii, const int64_t* __restrict__ offs_in,
-                               const int64_t* __restrict__ roff, uint8_t* __restrict__ codes, int64_t n_reads) {
+// `ascii` is a staged chunk of the batch: the bases of reads [r0, r1), whose first byte is the caller's offset `base`.
+__global__ void k_encode_reads(const uint8_t* __restrict__ ascii, const int64_t* __restrict__ offs_in, int64_t base,
+                               const int64_t* __restrict__ roff, uint8_t* __restrict__ codes, int64_t r0, int64_t r1) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < n_reads; i += nwarps) {
-        const int64_t s = offs_in[i], len = offs_in[i + 1] - s, d = roff[i];
+    for (int64_t i = r0 + warp; i < r1; i += nwarps) {
+        const int64_t s = offs_in[i] - base, len = offs_in[i + 1] - offs_in[i], d = roff[i];
         const int64_t padded = (len + 15) & ~15ll;
         for (int64_t j = lane; j < padded; j += 32) {
             const uint8_t code = j < len ? encode_base(ascii[s + j]) : (uint8_t)CODE_OTHER;
@@ -232,6 +261,22 @@ __global__ void k_gather_hits(const lsw_hit* __restrict__ hits, const uint32_t* 
     }
 }
 
+// sorted 32-byte hits -> 16-byte records (lsw_hit16): one 16-byte store per hit
+__global__ void k_pack_hits16(const lsw_hit* __restrict__ hits, int64_t n, uint4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4* src = reinterpret_cast<const int4*>(hits + i);
+        const int4 a = src[0], b = src[1];          // a: read, start, end, query | depth << 16;  b: m | x << 16, score | q_pos << 16, q_end | reserved << 16
+        const uint32_t query = (uint32_t)a.w & 0xFFFFu, depth = (uint32_t)a.w >> 16;
+        const uint32_t m = (uint32_t)b.x & 0xFFFFu, x = (uint32_t)b.x >> 16;
+        const uint32_t q_pos = (uint32_t)b.y >> 16, q_end = (uint32_t)b.z & 0xFFFFu, keep = ((uint32_t)b.z >> 16) & 1u;
+        uint4 o;
+        o.x = (uint32_t)a.x; o.y = (uint32_t)a.y;
+        o.z = ((uint32_t)(a.z - a.y) & 0xFFu) | ((query & 0xFFu) << 8) | ((depth > 0x7FFFu ? 0xFFFFu : depth) << 16);
+        o.w = (m & 0x7Fu) | (keep << 7) | ((x & 0xFFu) << 8) | ((q_pos & 0xFFu) << 16) | ((q_end & 0xFFu) << 24);
+        out[i] = o;
+    }
+}
+
 // one thread per read: find the read's segment in the sorted hits and prune overlaps (lsw_set_overlap)
 __global__ void k_prune_overlaps(lsw_hit* __restrict__ hits, int64_t n_hits, int64_t n_reads, int32_t read_base, int allowed) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (int64_t)gridDim.x * blockDim.x) {
@@ -300,6 +345,34 @@ __global__ void k_merge_segments(ReuseParams R) {
 }
 
 // ---- helpers -----------------------------------------------------------------------------
+
+// lsw_measure_int_peak mode 9: K1's inner loop and nothing else -- ScoreLane<24>::column2 (per row and column pair: 2 VIADDMNMX,
+// 3 VIMNMX3, 4 adds, one LDS.64 of the profile) on a profile in shared memory, with K1's block size, register budget and
+// occupancy.  What K1 would reach if task switches, chunk loads, masks and the arg-max folds were free.
+__global__ void __launch_bounds__(SCORE_WARPS * 32, ScoreOcc<24>::value)
+k_intpeak_k1row(uint32_t* out, const uint32_t* in, int iters) {
+    using Lane = ScoreLane<24>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    U2* prof = reinterpret_cast<U2*>(smem_raw);
+    uint32_t* p32 = reinterpret_cast<uint32_t*>(prof);
+    for (int e = threadIdx.x; e < NIDX * Lane::PROF_STRIDE * 2; e += blockDim.x) p32[e] = ((e * 7 + in[0]) & 1) ? 0x03000300u : 0x00000000u;
+    __syncthreads();
+    Lane L;
+    L.init();
+    const uint32_t G2 = 0x01000100u;
+    uint32_t tvec = 0, ia = (threadIdx.x + in[1]) & 15u, ib = (threadIdx.x * 3 + in[2]) & 15u;
+    for (int it = 0; it < iters; it++) {
+        L.column2(prof + ia * Lane::PROF_STRIDE, prof + ib * Lane::PROF_STRIDE, tvec, tvec + 0x00010001u, G2, G2);
+        tvec = (tvec + 0x00020002u) & 0x003F003Fu;
+        ia = (ia + 5u) & 15u; ib = (ib + 3u) & 15u;
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int r = 0; r < 24; r++) sum += L.M[r];
+#pragma unroll
+    for (int r = 0; r < 12; r++) sum += L.K[r];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
 
 int grid_for(int64_t n, int threads, int cap_blocks) {
     int64_t b = (n + threads - 1) / threads;
@@ -520,7 +593,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         P.push_cands = 0; P.count_ref = 0; P.block_steps = SEG_BLOCK;
     }
     {
-        Span sp(ctx, 0);
+        Span sp(ctx, (Tbase.mode == 0 && Tbase.round == 0) ? 4 : 0);      // 4: K1 on whole reads (round 0 of find_all)
         for (int c = 0; c < NCLASS; c++) {
             if (!ncls[c]) continue;
             P.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
@@ -591,6 +664,7 @@ void collect_times(lsw_ctx* ctx, lsw_counters* cnt) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, t.e0, t.e1) != cudaSuccess) continue;
         if (t.kind == 0) cnt->ms_score += ms;
+        else if (t.kind == 4) { cnt->ms_score += ms; cnt->ms_score_round0 += ms; }
         else if (t.kind == 1) cnt->ms_trace += ms;
         else if (t.kind == 2) cnt->ms_other += ms;
         else cnt->ms_total += ms;
@@ -642,18 +716,10 @@ void lsw_destroy(lsw_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_qcodes, &ctx->d_qlen, &ctx->d_cand_ok, &ctx->d_ascii, &ctx->d_offs_in, &ctx->d_codes,
-                      &ctx->d_roff, &ctx->d_rlen, &ctx->d_order, &ctx->d_order_tmp, &ctx->d_len_tmp[0], &ctx->d_len_tmp[1], &ctx->d_res, &ctx->d_seg[0], &ctx->d_seg[1], &ctx->d_head,
-                      &ctx->d_ncand, &ctx->d_counters, &ctx->d_child_flag, &ctx->d_pos, &ctx->d_cubtemp,
-                      &ctx->d_scratch, &ctx->d_hits, &ctx->d_hits_sorted, &ctx->d_nhits, &ctx->d_keys[0],
-                      &ctx->d_keys[1], &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_err, &ctx->d_results,
-                      &ctx->d_cigar, &ctx->d_ncigar};
-    for (DevBuf* b : bufs) b->release();
-    for (int c = 0; c < NCLASS; c++) { ctx->d_class_seqs[c].release(); ctx->d_cand[c].release(); ctx->d_fallback[c].release(); ctx->d_cand_key[c].release(); ctx->d_cand_sorted[c].release(); ctx->d_cand_key_sorted[c].release(); ctx->d_cand_rec[c].release(); ctx->d_fb2[c].release(); }
-    ctx->d_nfallback.release(); ctx->d_fb2cnt.release(); ctx->d_head2.release();
-    ctx->tb[0].release(); ctx->tb[1].release(); ctx->child.release();
-    for (DevBuf* b : {&ctx->d_blockbest, &ctx->d_bb_off, &ctx->d_bb1, &ctx->d_bb1_off, &ctx->d_nseg, &ctx->d_segpos, &ctx->d_res_s, &ctx->d_seg_s, &ctx->d_class_of, &ctx->d_kt}) b->release();
+    for (DevBuf* b : all_bufs(ctx)) b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
+    for (int k = 0; k < 2; k++) { if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]); if (ctx->ev_coded[k]) cudaEventDestroy(ctx->ev_coded[k]); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -755,43 +821,40 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     CK(cudaSetDevice(ctx->device));
     // a failed upload leaves the context EMPTY (n_reads = 0), never describing the previous batch with the new lengths
     ctx->n_reads = 0; ctx->total_bases = 0; ctx->n_hits = 0;
-    ctx->h_rlen.assign((size_t)n, 0);
+    // one pass over the offsets: lengths, padded size, and the block-best rows of lsw_reuse.cuh (BB_BLOCK columns per block,
+    // BB_GROUP blocks per second-level entry)
+    ctx->h_rlen.resize((size_t)n);
+    ctx->h_bb_off.resize((size_t)n + 1); ctx->h_bb1_off.resize((size_t)n + 1);
+    ctx->h_bb_off[0] = 0; ctx->h_bb1_off[0] = 0;
     int64_t padded_total = 0;
     for (int64_t i = 0; i < n; i++) {
         const int64_t len = offs[i + 1] - offs[i];
         if (len < 0 || len >= (1ll << 27)) { ctx->h_rlen.clear(); return fail(ctx, LSW_E_ARG, "read length must be in [0, 2^27)"); }
         ctx->h_rlen[i] = (int32_t)len;
         padded_total += (len + 15) & ~15ll;
+        const int64_t nb = (len + BB_BLOCK - 1) / BB_BLOCK;
+        ctx->h_bb_off[i + 1] = ctx->h_bb_off[i] + nb;
+        ctx->h_bb1_off[i + 1] = ctx->h_bb1_off[i] + (nb + BB_GROUP - 1) / BB_GROUP;
     }
     const int64_t total_bases = n ? offs[n] - offs[0] : 0;
     ctx->total_bases = total_bases;
-    ctx->h_bb_off.assign((size_t)n + 1, 0);                       // BB_BLOCK-column blocks of every read (lsw_reuse.cuh)
-    for (int64_t i = 0; i < n; i++) ctx->h_bb_off[i + 1] = ctx->h_bb_off[i] + (ctx->h_rlen[i] + BB_BLOCK - 1) / BB_BLOCK;
     ctx->bb_total = ctx->h_bb_off[n];
+    ctx->bb1_total = ctx->h_bb1_off[n];
     CK(ctx->d_bb_off.ensure((size_t)(n + 1) * 8));
     CK(cudaMemcpyAsync(ctx->d_bb_off.p, ctx->h_bb_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->h_bb1_off.assign((size_t)n + 1, 0);
-    for (int64_t i = 0; i < n; i++)
-        ctx->h_bb1_off[i + 1] = ctx->h_bb1_off[i] + (ctx->h_bb_off[i + 1] - ctx->h_bb_off[i] + BB_GROUP - 1) / BB_GROUP;
-    ctx->bb1_total = ctx->h_bb1_off[n];
     CK(ctx->d_bb1_off.ensure((size_t)(n + 1) * 8));
     CK(cudaMemcpyAsync(ctx->d_bb1_off.p, ctx->h_bb1_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     // a slice must span more than two groups (2048 columns) before the second level saves lookups
-    ctx->use_bb1 = n > 0 && ctx->total_bases / n >= 4 * BB_GROUP * BB_BLOCK;
+    ctx->use_bb1 = n > 0 && total_bases / n >= 4 * BB_GROUP * BB_BLOCK;
     if (const char* e = getenv("LSW_BB_L1")) ctx->use_bb1 = atoi(e) != 0;
     // 256 B front pad (K2 reads a few codes before a window start, masked) and 256 B tail pad (K1 reads
     // whole 64-byte blocks past a slice end)
     ctx->codes_bytes = 256 + padded_total + 256;
-    const int64_t in_bytes = ctx->total_bases;
-    CK(ctx->d_ascii.ensure((size_t)std::max<int64_t>(in_bytes, 1)));
     CK(ctx->d_offs_in.ensure((size_t)(n + 1) * 8));
     CK(ctx->d_roff.ensure((size_t)(n + 1) * 8));
     CK(ctx->d_rlen.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     CK(ctx->d_codes.ensure((size_t)ctx->codes_bytes));
-    if (in_bytes) CK(cudaMemcpyAsync(ctx->d_ascii.p, ascii + offs[0], (size_t)in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<int64_t> rel((size_t)n + 1);
-    for (int64_t i = 0; i <= n; i++) rel[i] = offs[i] - offs[0];
-    CK(cudaMemcpyAsync(ctx->d_offs_in.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_offs_in.p, offs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));   // absolute; the kernel subtracts the chunk's base
     if (n) CK(cudaMemcpyAsync(ctx->d_rlen.p, ctx->h_rlen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_codes.as<uint8_t>() + 256 + padded_total, CODE_OTHER, 256, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_codes.as<uint8_t>(), CODE_OTHER, 256, ctx->stream));
@@ -821,12 +884,42 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
         k_scatter_offsets<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
             ctx->d_order.as<int32_t>(), ctx->d_pos.as<long long>(), ctx->d_roff.as<int64_t>(), n);
         CK(cudaGetLastError());
-        const int blocks = grid_for(n * 32, 256, ctx->num_sms * 16);
-        k_encode_reads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ascii.as<uint8_t>(), ctx->d_offs_in.as<int64_t>(),
-                                                        ctx->d_roff.as<int64_t>(), ctx->d_codes.as<uint8_t>(), n);
-        CK(cudaGetLastError());
+        // The bases stream through two staging buffers of UPLOAD_CHUNK bytes: the copy stream brings chunk k + 1 in while chunk
+        // k is re-coded into its place in the sorted layout, so the ASCII text never exists on the device as a whole (it used to:
+        // a second buffer the size of the batch).  Chunks end on read boundaries; a read longer than a chunk is a chunk of its own.
+        int64_t max_chunk = 0;
+        std::vector<int64_t> cuts(1, 0);
+        while (cuts.back() < n) {
+            const int64_t r0 = cuts.back();
+            int64_t r1 = std::upper_bound(offs + r0, offs + n + 1, offs[r0] + UPLOAD_CHUNK) - offs - 1;
+            if (r1 <= r0) r1 = r0 + 1;
+            cuts.push_back(r1);
+            max_chunk = std::max(max_chunk, offs[r1] - offs[r0]);
+        }
+        const int nchunks = (int)cuts.size() - 1;
+        const int nbuf = nchunks > 1 ? 2 : 1;
+        CK(ctx->d_ascii.ensure((size_t)std::max<int64_t>(max_chunk, 1) * nbuf));
+        if (!ctx->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; k++) { CK(cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_coded[k], cudaEventDisableTiming)); }
+        }
+        CK(cudaEventRecord(ctx->ev_coded[0], ctx->stream));           // the offsets are in place (and the staging buffers are free)
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_coded[0], 0));
+        for (int c = 0; c < nchunks; c++) {
+            const int64_t r0 = cuts[c], r1 = cuts[c + 1], bytes = offs[r1] - offs[r0];
+            uint8_t* stage = ctx->d_ascii.as<uint8_t>() + (size_t)(c & 1) * (size_t)max_chunk;
+            if (c >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_coded[c & 1], 0));     // chunk c - 2 has left this buffer
+            if (bytes) CK(cudaMemcpyAsync(stage, ascii + offs[r0], (size_t)bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_copied[c & 1], ctx->copy_stream));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[c & 1], 0));
+            const int blocks = grid_for((r1 - r0) * 32, 256, ctx->num_sms * 16);
+            k_encode_reads<<<blocks, 256, 0, ctx->stream>>>(stage, ctx->d_offs_in.as<int64_t>(), offs[r0], ctx->d_roff.as<int64_t>(),
+                                                            ctx->d_codes.as<uint8_t>(), r0, r1);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev_coded[c & 1], ctx->stream));
+        }
     }
-    CK(cudaStreamSynchronize(ctx->stream));      // `rel` and the caller's buffers may go away
+    CK(cudaStreamSynchronize(ctx->stream));      // the caller's buffers may go away
     ctx->n_reads = n;                            // committed only now: every step above has succeeded
     return LSW_OK;
 }
@@ -884,6 +977,9 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     if (reuse && ctx->d_blockbest.ensure((size_t)std::max<int64_t>(1, ctx->bb_total) * ctx->nseq * 4) != cudaSuccess) {
         (void)cudaGetLastError();
         reuse = false;
+        cnt.reuse_dropped = 1;          // reported, not silent: lsw_counters.reuse_dropped (and a line on stderr)
+        fprintf(stderr, "[lsw] warning: no room for the round-0 block bests (%.1f GB): child rounds align whole slices\n",
+                (double)ctx->bb_total * ctx->nseq * 4 / 1e9);
     }
     int64_t n = n0;
     int round = 0;
@@ -942,7 +1038,8 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         }
         CK(cudaMemcpyAsync(h_seg.data(), ctx->d_seg[cur ^ 1].p, h_seg.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(&h_nhits, ctx->d_nhits.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        unsigned long long h_nc[NCLASS], h_nf[NCLASS];
+        unsigned long long h_nc[NCLASS], h_nf[NCLASS], h_comp0 = 0;
+        if (round == 0) CK(cudaMemcpyAsync(&h_comp0, ctx->d_counters.as<unsigned long long>() + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_nc, ctx->d_ncand.p, NCLASS * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_nf, ctx->d_nfallback.p, NCLASS * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -951,7 +1048,8 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
             float ms[3] = {0.f, 0.f, 0.f};
             for (size_t k = dbg_from; k < ctx->timed.size(); k++) {
                 float m = 0.f;
-                if (ctx->timed[k].kind < 3 && cudaEventElapsedTime(&m, ctx->timed[k].e0, ctx->timed[k].e1) == cudaSuccess) ms[ctx->timed[k].kind] += m;
+                const int kd = ctx->timed[k].kind == 4 ? 0 : ctx->timed[k].kind;
+                if (kd < 3 && cudaEventElapsedTime(&m, ctx->timed[k].e0, ctx->timed[k].e1) == cudaSuccess) ms[kd] += m;
             }
             dbg_from = ctx->timed.size();
             unsigned long long c4[4] = {0, 0, 0, 0};
@@ -960,7 +1058,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
                             "cumulative lane-steps %llu, computed cells %llu, reference cells %llu\n",
                     round, (long long)n, total_next, h_nhits, ms[0], ms[1], ms[2], c4[2], c4[3], c4[1]);
         }
-        if (round == 0) { cnt.top_tasks = n; }
+        if (round == 0) { cnt.top_tasks = n; cnt.computed_cells_round0 = (int64_t)h_comp0; }
         cur ^= 1;
         n = total_next;
         round++;
@@ -1027,6 +1125,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     if (tt.e1) { cudaEventRecord(tt.e1, ctx->stream); ctx->timed.push_back(tt); }
     CK(cudaStreamSynchronize(ctx->stream));
     collect_times(ctx, &cnt);
+    cnt.device_bytes = device_bytes(ctx);
     ctx->n_hits = nh;
     if (n_hits) *n_hits = nh;
     if (counters) *counters = cnt;
@@ -1044,6 +1143,36 @@ int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out) {
     CK(cudaStreamSynchronize(ctx->stream));
     return LSW_OK;
 }
+
+int lsw_fetch_hits_compact(lsw_ctx* ctx, lsw_hit16* out, int64_t cap, int64_t* n_out) {
+    if (!ctx) return LSW_E_ARG;
+    if (n_out) *n_out = ctx->n_hits;
+    if (ctx->n_hits > cap) return fail(ctx, LSW_E_OVERFLOW, "lsw_fetch_hits_compact: caller buffer too small");
+    if (ctx->n_hits == 0) return LSW_OK;
+    if (!out) return fail(ctx, LSW_E_ARG, "lsw_fetch_hits_compact: out is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_hits16.ensure((size_t)ctx->n_hits * sizeof(lsw_hit16)));
+    k_pack_hits16<<<grid_for(ctx->n_hits, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+        ctx->d_hits_sorted.as<lsw_hit>(), ctx->n_hits, ctx->d_hits16.as<uint4>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_hits16.p, (size_t)ctx->n_hits * sizeof(lsw_hit16), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LSW_OK;
+}
+
+int lsw_host_alloc(int64_t bytes, void** out) {
+    if (!out || bytes < 0) return LSW_E_ARG;
+    *out = nullptr;
+    if (cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        g_create_error = "lsw_host_alloc: cudaHostAlloc failed";
+        *out = nullptr;
+        return LSW_E_CUDA;
+    }
+    return LSW_OK;
+}
+
+void lsw_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int lsw_align_tasks(lsw_ctx* ctx, int64_t n, const lsw_task* tasks, lsw_result* out,
                     uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used) {
@@ -1131,7 +1260,9 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n, const lsw_task* tasks, lsw_result* 
 int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per_s, float* ms_out) {
     if (!ctx || !lane_ops_per_s || iters <= 0) return LSW_E_ARG;
     CK(cudaSetDevice(ctx->device));
-    const int threads = 256, blocks = ctx->num_sms * 8;
+    int threads = 256, blocks = ctx->num_sms * 8;
+    if (mode == 9) { threads = SCORE_WARPS * 32; blocks = ctx->num_sms * ScoreOcc<24>::value; }
+    const size_t smem9 = sizeof(U2) * (size_t)NIDX * ScoreLane<24>::PROF_STRIDE;
     DevBuf out, in;
     CK(out.ensure((size_t)threads * blocks * 4));
     CK(in.ensure(64));
@@ -1145,6 +1276,7 @@ int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per
 #define LSW_IP(M) case M: k_intpeak<M><<<blocks, threads, 0, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters, 1u); break;
         switch (mode) {
             LSW_IP(0) LSW_IP(1) LSW_IP(2) LSW_IP(3) LSW_IP(4) LSW_IP(5) LSW_IP(6) LSW_IP(7) LSW_IP(8)
+            case 9: k_intpeak_k1row<<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
             default: cudaEventDestroy(e0); cudaEventDestroy(e1); out.release(); in.release();
                      return fail(ctx, LSW_E_ARG, "lsw_measure_int_peak: unknown mode");
         }
@@ -1158,7 +1290,8 @@ int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     out.release(); in.release();
-    const double ops = (double)threads * blocks * (double)iters * intpeak_ops_per_iter(mode);
+    // mode 9: one iteration = column2 = 24 rows x (5 DPX + 4 adds) lane-ops = 96 cells per lane
+    const double ops = (double)threads * blocks * (double)iters * (mode == 9 ? 24 * 9 : intpeak_ops_per_iter(mode));
     *lane_ops_per_s = ops / (best * 1e-3);
     if (ms_out) *ms_out = best;
     return LSW_OK;

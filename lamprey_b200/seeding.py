@@ -136,13 +136,58 @@ class SeedBatch(object):
         return self.alignments(i), float(self.coverage[i])
 
 
-def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None):
+_pools = {}
+
+
+def _scoring_of(aligner):
+    if aligner is None:
+        return (2, -1, -1, -1)                          # initAligners, lamprey.py:1860-1865
+    return (aligner.scoring_matrix.match, aligner.scoring_matrix.mismatch, aligner.gap_penalty, aligner.gap_extension_penalty)
+
+
+def get_pool(devices, contexts_per_device=1):
+    """One lazily created pool per (device list, contexts per device)."""
+    key = (tuple(int(d) for d in devices), int(contexts_per_device))
+    pool = _pools.get(key)
+    if pool is None:
+        pool = _pools[key] = _native.Pool(key[0], key[1])
+    return pool
+
+
+def _seed_on_pool(pool, concat, offs, hit_cap=None):
+    """One batch through a configured pool: submit, wait, enlarge the hit buffer once if it was too small."""
+    cap = int(hit_cap or (len(concat) // 8 + 4096))
+    while True:
+        out = np.zeros(cap, pool.hit_dtype)
+        try:
+            hits, counters, times = pool.wait(pool.submit(concat, offs, out))
+        except OverflowError as e:
+            cap = e.needed + 1024
+            continue
+        if pool.hit_format == _native.HITS_COMPACT:
+            hits = _native.expand_hits(hits, *pool.scoring)
+        counters["pool_times"] = times
+        return hits, counters
+
+
+def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None, devices=None,
+               compact=True):
     """findAllPrimerAlignments for every read of a batch in one device pass.  allowed_overlap (LAMPrey uses 4,
-    lamprey.py:1536) also runs removeOverlappingPrimerAlignments on the device: see SeedBatch.kept."""
+    lamprey.py:1536) also runs removeOverlappingPrimerAlignments on the device: see SeedBatch.kept.
+
+    devices=[0, 1, ...]: the batch is split over those GPUs in contiguous read ranges balanced by bases, one host thread
+    and context per GPU, and the hits are gathered on the host in global read order -- what the reference does with
+    worker processes (lamprey.py:2182-2207).  The result is identical to the single-device one."""
     from . import swalign as _sw
     concat, offs = _read_arrays(reads)
     pairs = primer_set.sequences()
     names = [n for n, _ in pairs]
+    if devices is not None:
+        pool = get_pool(devices)
+        sc = _scoring_of(aligner)
+        pool.configure([s for _, s in pairs], threshold, *sc, allowed_overlap=allowed_overlap, compact=compact)
+        hits, counters = _seed_on_pool(pool, concat, offs)
+        return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, counters)
     eng = engine or _sw.get_engine(device)
     if aligner is not None:
         eng.set_scoring(aligner.scoring_matrix.match, aligner.scoring_matrix.mismatch, aligner.gap_penalty,
@@ -157,6 +202,38 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
     finally:
         eng.set_overlap(None)            # the engine is shared (swalign.get_engine): never leave the pruning switched on
     return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters)
+
+
+def seed_stream(batches, primer_set, threshold, aligner=None, devices=(0,), allowed_overlap=None, compact=True, depth=2):
+    """Seed a stream of read batches (e.g. the FASTQ files an online run delivers one by one, lamprey.py:451-507), yielding
+    one SeedBatch per input batch, in order.  The library double-buffers: while one batch is being seeded, the next one is
+    uploaded and the previous one's hits are downloaded (`depth` contexts per device take alternate batches)."""
+    pairs = primer_set.sequences()
+    names = [n for n, _ in pairs]
+    pool = get_pool(devices, depth)
+    pool.configure([s for _, s in pairs], threshold, *_scoring_of(aligner), allowed_overlap=allowed_overlap, compact=compact)
+    inflight = []
+
+    def finish(item):
+        ticket, concat, offs, out = item
+        try:
+            hits, counters, times = pool.wait(ticket)
+        except OverflowError as e:                       # rare: the default hit buffer was too small for this batch
+            hits, counters = _seed_on_pool(pool, concat, offs, hit_cap=e.needed + 1024)
+            return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, counters)
+        if pool.hit_format == _native.HITS_COMPACT:
+            hits = _native.expand_hits(hits, *pool.scoring)
+        counters["pool_times"] = times
+        return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, counters)
+
+    for reads in batches:
+        concat, offs = _read_arrays(reads)
+        out = np.zeros(len(concat) // 8 + 4096, pool.hit_dtype)
+        inflight.append((pool.submit(concat, offs, out), concat, offs, out))
+        if len(inflight) >= depth:
+            yield finish(inflight.pop(0))
+    while inflight:
+        yield finish(inflight.pop(0))
 
 
 def seed_fastq(path, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None, with_names=False):

@@ -1,0 +1,104 @@
+"""GPU tests of the library-level pool (include/lsw.h "Pool"): one batch split over several contexts / GPUs with the
+host-side gather, double-buffered streaming, and the 16-byte hit records.  Everything is compared byte for byte with the
+single-context result, which test_gpu_parity.py pins to the oracle and the goldens."""
+import numpy as np
+import pytest
+
+from conftest import load_reads, schema_path, load_seed_golden, hits_matrix
+from lamprey_b200 import _native, seeding, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _seqs(schema):
+    return [s for _, s in seeding.PrimerSet(schema_path(schema)).sequences()]
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_compact_hits_equal_wide_hits(engine):
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries(_seqs("H33"))
+    engine.upload_read_list(load_reads("1k"))
+    engine.set_overlap(4)
+    try:
+        wide = engine.find_all(0.70)
+        compact = engine.fetch_hits_compact(len(wide))
+    finally:
+        engine.set_overlap(None)
+    assert compact.dtype.itemsize == 16 and len(compact) == len(wide) > 10000
+    back = _native.expand_hits(compact, 2, -1, -1)
+    assert back.tobytes() == wide.tobytes()              # every field, score and survivor flag included
+    c = engine.last_counters
+    assert c["device_bytes"] > 0 and c["reuse_dropped"] == 0 and 0 < c["ms_score_round0"] <= c["ms_score"]
+    assert 0 < c["computed_cells_round0"] <= c["computed_cells"]
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_pool_split_over_contexts_equals_one_context(compact):
+    # ONE batch dealt over several contexts (every visible GPU; on a single-GPU box two contexts of GPU 0 stand in for two
+    # devices) with the host-side gather == the same batch on one context, byte for byte
+    devices = list(range(_n_gpus())) if _n_gpus() > 1 else [0, 0]
+    concat, offs = synth.generate(600, seed=21, mean_len=1500)
+    seqs = _seqs("H33")
+    one = _native.Engine(0)
+    one.set_scoring(2, -1, -1, -1); one.set_queries(seqs); one.upload_reads(concat, offs)
+    one.set_overlap(4)
+    want = one.find_all(0.7)
+    want_cnt = one.last_counters
+    one.close()
+    pool = _native.Pool(devices)
+    pool.configure(seqs, 0.7, allowed_overlap=4, compact=compact)
+    out = np.zeros(len(want) + 10, pool.hit_dtype)
+    hits, cnt, times = pool.wait(pool.submit(concat, offs, out))
+    if compact:
+        hits = _native.expand_hits(hits)
+    assert hits.tobytes() == want.tobytes()
+    assert (cnt["tasks"], cnt["cells"], cnt["hits"]) == (want_cnt["tasks"], want_cnt["cells"], want_cnt["hits"])
+    assert sum(times["reads"]) == 600 and sum(times["hits"]) == len(want) and min(times["reads"][:len(devices)]) > 0
+    # a buffer that is too small: reported with the needed count, nothing written past it
+    small = np.zeros(100, pool.hit_dtype)
+    with pytest.raises(OverflowError) as e:
+        pool.wait(pool.submit(concat, offs, small))
+    assert e.value.needed == len(want)
+    pool.close()
+
+
+def test_seed_reads_devices_equals_golden():
+    devices = list(range(_n_gpus())) if _n_gpus() > 1 else [0, 0]
+    reads = load_reads("1k")
+    ps = seeding.PrimerSet(schema_path("H33"))
+    gold = load_seed_golden("1k", "H33", 0.75)
+    batch = seeding.seed_reads(reads, ps, 0.75, devices=devices)
+    assert np.array_equal(hits_matrix(batch.hits), gold["hits"])
+    assert np.array_equal(batch.coverage, gold["coverage"])
+    assert (batch.counters["tasks"], batch.counters["cells"]) == (int(gold["calls"]), int(gold["cells"]))
+
+
+def test_seed_stream_double_buffered_equals_per_batch_seeding(engine):
+    ps = seeding.PrimerSet(schema_path("H33"))
+    batches = [synth.generate(n, seed=40 + k, mean_len=900) for k, n in enumerate((64, 1, 200, 0, 33))]
+    got = list(seeding.seed_stream(batches, ps, 0.7, devices=[0], depth=2))
+    assert len(got) == len(batches)
+    for (concat, offs), b in zip(batches, got):
+        want = seeding.seed_reads((concat, offs), ps, 0.7)
+        assert b.hits.tobytes() == want.hits.tobytes() and len(b) == len(offs) - 1
+
+
+def test_pool_errors():
+    pool = _native.Pool([0])
+    with pytest.raises(ValueError):                       # not configured yet
+        pool.submit(np.zeros(4, np.uint8), np.array([0, 4]), np.zeros(8, _native.HIT_DT))
+    with pytest.raises(ValueError):
+        pool.configure(["ACGN"], 0.7)
+    with pytest.raises(NotImplementedError):
+        pool.configure(["ACGT"], 0.7, gap=-2, gap_ext=-1)
+    pool.configure(["ACGTACGTAC"], 0.7)
+    hits, cnt, _ = pool.wait(pool.submit(np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(8, _native.HIT_DT)))
+    assert len(hits) == 0 and cnt["tasks"] == 0          # an empty batch
+    pool.close()
+    with pytest.raises(RuntimeError):
+        _native.Pool([99])
