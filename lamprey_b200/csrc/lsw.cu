@@ -349,6 +349,7 @@ __global__ void k_merge_segments(ReuseParams R) {
 // lsw_measure_int_peak mode 9: K1's inner loop and nothing else -- ScoreLane<24>::column2 (per row and column pair: 2 VIADDMNMX,
 // 3 VIMNMX3, 4 adds, one LDS.64 of the profile) on a profile in shared memory, with K1's block size, register budget and
 // occupancy.  What K1 would reach if task switches, chunk loads, masks and the arg-max folds were free.
+template <int KEYV>
 __global__ void __launch_bounds__(SCORE_WARPS * 32, ScoreOcc<24>::value)
 k_intpeak_k1row(uint32_t* out, const uint32_t* in, int iters) {
     using Lane = ScoreLane<24>;
@@ -362,7 +363,7 @@ k_intpeak_k1row(uint32_t* out, const uint32_t* in, int iters) {
     const uint32_t G2 = 0x01000100u;
     uint32_t tvec = 0, ia = (threadIdx.x + in[1]) & 15u, ib = (threadIdx.x * 3 + in[2]) & 15u;
     for (int it = 0; it < iters; it++) {
-        L.column2(prof + ia * Lane::PROF_STRIDE, prof + ib * Lane::PROF_STRIDE, tvec, tvec + 0x00010001u, G2, G2);
+        L.template column2<KEYV>(prof + ia * Lane::PROF_STRIDE, prof + ib * Lane::PROF_STRIDE, tvec, tvec + 0x00010001u, G2, G2, in[5]);
         tvec = (tvec + 0x00020002u) & 0x003F003Fu;
         ia = (ia + 5u) & 15u; ib = (ib + 3u) & 15u;
     }
@@ -1261,12 +1262,12 @@ int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per
     if (!ctx || !lane_ops_per_s || iters <= 0) return LSW_E_ARG;
     CK(cudaSetDevice(ctx->device));
     int threads = 256, blocks = ctx->num_sms * 8;
-    if (mode == 9) { threads = SCORE_WARPS * 32; blocks = ctx->num_sms * ScoreOcc<24>::value; }
+    if (mode >= 9) { threads = SCORE_WARPS * 32; blocks = ctx->num_sms * ScoreOcc<24>::value; }
     const size_t smem9 = sizeof(U2) * (size_t)NIDX * ScoreLane<24>::PROF_STRIDE;
     DevBuf out, in;
     CK(out.ensure((size_t)threads * blocks * 4));
     CK(in.ensure(64));
-    const uint32_t h_in[8] = {0x00030002u, 0x00010001u, 0x01000100u, 0x00100020u, 0x00000000u, 0, 0, 0};
+    const uint32_t h_in[8] = {0x00030002u, 0x00010001u, 0x01000100u, 0x00100020u, 0x00000000u, 1u, 0, 0};
     CK(cudaMemcpyAsync(in.p, h_in, sizeof h_in, cudaMemcpyHostToDevice, ctx->stream));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -1276,7 +1277,10 @@ int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per
 #define LSW_IP(M) case M: k_intpeak<M><<<blocks, threads, 0, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters, 1u); break;
         switch (mode) {
             LSW_IP(0) LSW_IP(1) LSW_IP(2) LSW_IP(3) LSW_IP(4) LSW_IP(5) LSW_IP(6) LSW_IP(7) LSW_IP(8)
-            case 9: k_intpeak_k1row<<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
+            case 9: k_intpeak_k1row<LSW_K1_KEYV><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;   // what K1 is built with
+            case 10: k_intpeak_k1row<0><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
+            case 11: k_intpeak_k1row<1><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
+            case 12: k_intpeak_k1row<2><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
             default: cudaEventDestroy(e0); cudaEventDestroy(e1); out.release(); in.release();
                      return fail(ctx, LSW_E_ARG, "lsw_measure_int_peak: unknown mode");
         }
@@ -1291,7 +1295,7 @@ int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     out.release(); in.release();
     // mode 9: one iteration = column2 = 24 rows x (5 DPX + 4 adds) lane-ops = 96 cells per lane
-    const double ops = (double)threads * blocks * (double)iters * (mode == 9 ? 24 * 9 : intpeak_ops_per_iter(mode));
+    const double ops = (double)threads * blocks * (double)iters * (mode >= 9 ? 24 * 9 : intpeak_ops_per_iter(mode));
     *lane_ops_per_s = ops / (best * 1e-3);
     if (ms_out) *ms_out = best;
     return LSW_OK;

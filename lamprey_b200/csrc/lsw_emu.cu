@@ -112,7 +112,7 @@ void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& c
             }
         }
         if (!(L.tid[0] >= 0 || L.tid[1] >= 0)) break;
-        L.run_block(P, prof.data(), keep_ge, keep_lt, Q);
+        L.run_block(P, prof.data(), keep_ge, keep_lt, Q, q);
     }
     E.counters[0] += L.n_tasks; E.counters[1] += L.n_cells; E.counters[2] += L.n_steps; E.comp_cells += L.n_comp;
 }

@@ -26,6 +26,21 @@
 
 namespace lsw {
 
+#ifndef LSW_K1_KEYV
+#define LSW_K1_KEYV 0        // how K1 folds the arg-max keys: see ScoreLane::column2
+#endif
+
+// a * one + b as a real multiply-add (FMA pipe); `one` is a run-time 1, so that the assembler cannot turn it back into an add
+LSW_HD uint32_t mad_one(uint32_t a, uint32_t one, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t o;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(o) : "r"(a), "r"(one), "r"(b));
+    return o;
+#else
+    return a * one + b;
+#endif
+}
+
 struct U4 { uint32_t x, y, z, w; };
 struct U2 { uint32_t x, y; };
 
@@ -45,6 +60,7 @@ struct ScoreLane {
     int32_t  bestc[2];     // its DP column
     int32_t  len[2];       // slice length
     int32_t  skipb[2];     // leading blocks of the current task that are warm-up only (not folded)
+    uint32_t bbo[2];       // round 0: first block-best slot of the task's read (lsw_reuse.cuh), fetched when the task starts
     U4       nx[2];        // read codes of the next 16 steps, fetched one chunk ahead
     unsigned long long n_tasks, n_cells, n_steps, n_comp;
 
@@ -56,7 +72,7 @@ struct ScoreLane {
         tid[0] = tid[1] = -1;
         rem[0] = rem[1] = 0; begin[0] = begin[1] = 0;
         pos[0] = pos[1] = 0; cbase[0] = cbase[1] = 0;
-        best[0] = best[1] = 0; bestc[0] = bestc[1] = 0; len[0] = len[1] = 0; skipb[0] = skipb[1] = 0;
+        best[0] = best[1] = 0; bestc[0] = bestc[1] = 0; len[0] = len[1] = 0; skipb[0] = skipb[1] = 0; bbo[0] = bbo[1] = 0;
         nx[0].x = nx[0].y = nx[0].z = nx[0].w = 0;
         nx[1] = nx[0];
     }
@@ -100,6 +116,9 @@ struct ScoreLane {
         for (int r = 0; r < NR; r++) M[r] &= keep;     // zero boundary column for this half
         nx[h] = *reinterpret_cast<const U4*>(P.codes + pos[h]);
         skipb[h] = k.skip;
+        // the row of block bests this task writes: looked up HERE, a block before the first store needs it (the address used to be
+        // chased through task -> read -> offset at every store: 12 % of round 0 sat on those dependent loads)
+        if (P.blockbest) bbo[h] = (uint32_t)P.bb_off[P.t.read[t]];
         if (P.count_ref) {
             n_tasks += 1;
             n_cells += (unsigned long long)k.len * (unsigned long long)Q;
@@ -132,9 +151,14 @@ struct ScoreLane {
     }
 
     // TWO DP columns (c, c+1) for both halves, row by row.  prowA / prowB: profile rows of the two columns'
-    // (code_lo, code_hi) pairs.  Doing two columns per sweep lets one VIMNMX3 fold both arg-max keys into K[r]
-    // (the key adds are plain adds), i.e. 5 DPX ops and 4 adds per four cells.
-    LSW_HD void column2(const U2* prowA, const U2* prowB, uint32_t tvA, uint32_t tvB, uint32_t G2, uint32_t FLOOR2) {
+    // (code_lo, code_hi) pairs.  Per row and column pair (four cells): 2 VIADDMNMX + 2 VIMNMX3 for the values, two subtractions,
+    // and the arg-max keys of both columns folded into K[r].  KEYV selects how the keys are folded (all variants compute the
+    // same K; they differ in which pipe the instructions land on -- measured by lsw_measure_int_peak modes 9..12):
+    //   0  K = max3(K, h1 + tagA, h2 + tagB)            2 adds + 1 VIMNMX3   (the compiler issues the adds as VIADD: ALU pipe)
+    //   1  K = max(h2 + tagB, max(h1 + tagA, K))        2 VIADDMNMX          (one ALU instruction less, none on the FMA pipe)
+    //   2  as 0 with the adds forced onto the FMA pipe  (IMAD with a run-time multiplier of one)
+    template <int KEYV = LSW_K1_KEYV>
+    LSW_HD void column2(const U2* prowA, const U2* prowB, uint32_t tvA, uint32_t tvB, uint32_t G2, uint32_t FLOOR2, uint32_t one = 1u) {
         uint32_t dOld = 0, uA = 0, uB = 0;
 #pragma unroll
         for (int r2 = 0; r2 < NR / 2; r2++) {
@@ -148,8 +172,10 @@ struct ScoreLane {
                 const uint32_t T2 = addmax2(uA, SB, m1);         \
                 const uint32_t h2 = max3_2(T2, uB, FLOOR2);      \
                 const uint32_t m2 = h2 - G2;                     \
-                K[(R) >> 1] = max3_2(K[(R) >> 1], h1 + (tvA + ((R) & 1) * 0x00400040u), \
-                                     h2 + (tvB + ((R) & 1) * 0x00400040u)); \
+                const uint32_t tA = tvA + ((R) & 1) * 0x00400040u, tB = tvB + ((R) & 1) * 0x00400040u; \
+                if (KEYV == 1) K[(R) >> 1] = addmax2(h2, tB, addmax2(h1, tA, K[(R) >> 1])); \
+                else if (KEYV == 2) K[(R) >> 1] = max3_2(K[(R) >> 1], mad_one(h1, one, tA), mad_one(h2, one, tB)); \
+                else K[(R) >> 1] = max3_2(K[(R) >> 1], h1 + tA, h2 + tB); \
                 M[R] = m2;                                       \
                 dOld = mold; uA = m1; uB = m2;                   \
             }
@@ -161,7 +187,7 @@ struct ScoreLane {
 
     // P.block_steps (64, or 32 for the short segment tasks of lsw_reuse.cuh) columns for both halves, then fold the block's arg-max into the task state.
     // keep_ge[n]: bytes j >= n of a 16-byte chunk are live; keep_lt[n]: bytes j < n are live.
-    LSW_HD void run_block(const ScoreParams& P, const U2* prof, const U4* keep_ge, const U4* keep_lt, int Q) {
+    LSW_HD void run_block(const ScoreParams& P, const U2* prof, const U4* keep_ge, const U4* keep_lt, int Q, int q) {
         const uint32_t G2 = (uint32_t)(P.g * SC) * 0x00010001u;
         const uint32_t FLOOR2 = G2;
         int end[2];
@@ -235,9 +261,8 @@ struct ScoreLane {
                 if (tid[h] >= 0 && P.blockbest) {
                     // first column of this half block, 0-based on the read; a half block that starts past the read's end is not stored
                     const int col0 = cbase[h] - 1 + part * BB_BLOCK;
-                    const int t = tid[h];
-                    if (col0 < len[h])
-                        P.blockbest[(size_t)P.t.seq[t] * P.bb_total + P.bb_off[P.t.read[t]] + (col0 / BB_BLOCK)] = bb;
+                    if (col0 < len[h])          // (every lane of the warp serves sequence q)
+                        P.blockbest[(size_t)q * P.bb_total + bbo[h] + (uint32_t)(col0 / BB_BLOCK)] = bb;
                 }
                 if (tid[h] >= 0 && skipb[h] == 0 && (bb >> 6) >= (best[h] >> 6)) {   // >= : a later block wins ties on (H, row); bits 6.. hold (H, row)
                     best[h] = bb;                                                    // (warm-up blocks of a tail segment are not counted)
@@ -398,7 +423,7 @@ k_score(const ScoreParams P) {
             }
             const bool active = (L.tid[0] >= 0) || (L.tid[1] >= 0);
             if (!__any_sync(0xFFFFFFFFu, active)) break;
-            L.run_block(P, prof, keep_ge, keep_lt, Q);
+            L.run_block(P, prof, keep_ge, keep_lt, Q, q);
         }
     }
     // per-lane work counters -> global (one atomic per lane per launch)
