@@ -132,6 +132,16 @@ int lsw_set_stream(lsw_ctx* ctx, void* cuda_stream);
  * pair in force does not fit. */
 int lsw_set_scoring(lsw_ctx* ctx, int match, int mismatch, int gap, int gap_ext);
 
+/* Switches the context to LAMPrey's DEFAULT seeding path (no --swalign): scikit-bio's StripedSmithWaterman(primer)(read slice)
+ * (/root/reference/lamprey.py:572-593, 609-610).  skbio's defaults are match 2, mismatch -3, gap_open 5, gap_extend 2 (penalties
+ * positive, as skbio takes them); a non-ACGT read base scores 0 against everything.  In this mode
+ *   lsw_align_tasks  returns ssw_align's fields: score, r_pos / r_end = target_begin / target_end_optimal + 1, q_pos / q_end =
+ *                    query_begin / query_end + 1 (r_pos = -1 if nothing aligned), matches = aligned columns with equal bases
+ *                    (lamprey.py:579-583), mismatches = the other CIGAR columns, CIGAR as banded_sw produces it;
+ *   lsw_find_all     applies identity = matches / len(primer) >= thr and (end - start) >= len(primer) * thr, and recurses.
+ * lsw_set_scoring() switches back to the swalign path. */
+int lsw_set_ssw(lsw_ctx* ctx, int match, int mismatch, int gap_open, int gap_extend);
+
 /* The schema sequences (already in search order; reverse complements supplied by the caller).
  * ASCII, upper-cased by the library; must be ACGT only and 1..LSW_MAX_QUERY_LEN long. */
 int lsw_set_queries(lsw_ctx* ctx, int n, const uint8_t* concat, const int32_t* offs /* n+1 */);

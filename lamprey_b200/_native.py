@@ -37,7 +37,7 @@ assert HIT16_DT.itemsize == 16
 # every symbol include/lsw.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",
            "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_overlap", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
-           "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_host_alloc", "lsw_host_free",
+           "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_set_ssw", "lsw_host_alloc", "lsw_host_free",
            "lsw_pool_create", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_pool_configure", "lsw_pool_submit", "lsw_pool_wait")
 HITS_WIDE, HITS_COMPACT = 0, 1
 POOL_TIMES_DT = np.dtype([("upload_s", "<f8"), ("find_s", "<f8"), ("fetch_s", "<f8"), ("gather_wait_s", "<f8"), ("total_s", "<f8"),
@@ -73,6 +73,7 @@ def load():
     lib.lsw_fetch_hits.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_measure_int_peak.argtypes = [vp, i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_float)]
     lib.lsw_fetch_hits_compact.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
+    lib.lsw_set_ssw.argtypes = [vp, i32, i32, i32, i32]
     lib.lsw_host_alloc.argtypes = [i64, ctypes.POINTER(vp)]
     lib.lsw_host_free.argtypes = [vp]
     lib.lsw_host_free.restype = None
@@ -274,6 +275,15 @@ class Engine(object):
             return
         self._scoring = None
         self._check(self._lib.lsw_set_scoring(self._h, *key), "lsw_set_scoring")
+        self._scoring = key
+
+    def set_ssw(self, match=2, mismatch=-3, gap_open=5, gap_extend=2):
+        """The default seeding path: skbio StripedSmithWaterman semantics (include/lsw.h lsw_set_ssw)."""
+        key = ("ssw", int(match), int(mismatch), int(gap_open), int(gap_extend))
+        if key == self._scoring:
+            return
+        self._scoring = None
+        self._check(self._lib.lsw_set_ssw(self._h, *key[1:]), "lsw_set_ssw")
         self._scoring = key
 
     def set_queries(self, seqs):

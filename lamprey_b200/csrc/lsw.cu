@@ -27,6 +27,7 @@
 #include "lsw_trace.cuh"
 #include "lsw_band.cuh"
 #include "lsw_reuse.cuh"
+#include "lsw_ssw.cuh"
 #include "intpeak.cuh"
 #include "lsw_host.hpp"
 
@@ -89,6 +90,9 @@ struct lsw_ctx {
     int num_sms = 0;
 
     int match = 2, mismatch = -1, g = 1;
+    // the default (skbio / SSW) seeding path (lsw_ssw.cuh): on after lsw_set_ssw(), off after lsw_set_scoring()
+    bool ssw = false;
+    int ssw_match = 2, ssw_mismatch = -3, ssw_open = 5, ssw_extend = 2;
     int nseq = 0;
     std::vector<int32_t> qlen;
     std::vector<uint8_t> qcodes;
@@ -660,6 +664,67 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
     return LSW_OK;
 }
 
+template <int NR>
+int launch_ssw(lsw_ctx* ctx, SswParams P, int64_t n_class_tasks) {
+    // tier 1: one thread per task, band <= SSW_BW1 in local memory
+    const int blocks = grid_for(n_class_tasks, SSW_THREADS, ctx->num_sms * 16);
+    k_ssw_round<NR, SSW_BW1><<<blocks, SSW_THREADS, 0, ctx->stream>>>(P, nullptr);
+    CK(cudaGetLastError());
+    // tier 2: the tasks whose band outgrew it, direction bytes in a global scratch
+    const int blocks2 = 32;
+    CK(ctx->d_scratch.ensure((size_t)blocks2 * SSW_THREADS * SswBand<SSW_BW2>::DIR_BYTES));
+    SswParams P2 = P;
+    P2.fb_in = P.fallback; P2.fb_in_cnt = P.nfallback;
+    P2.fallback = nullptr; P2.nfallback = ctx->d_fb2cnt.as<unsigned long long>();     // (a tier-2 overflow is an error, not a list)
+    k_ssw_round<NR, SSW_BW2><<<blocks2, SSW_THREADS, 0, ctx->stream>>>(P2, ctx->d_scratch.as<uint8_t>());
+    CK(cudaGetLastError());
+    return LSW_OK;
+}
+
+int launch_ssw_class(lsw_ctx* ctx, int c, const SswParams& P, int64_t n) {
+    switch (CLASS_NR[c]) {
+        case 16: return launch_ssw<16>(ctx, P, n);
+        case 20: return launch_ssw<20>(ctx, P, n);
+        case 24: return launch_ssw<24>(ctx, P, n);
+        case 28: return launch_ssw<28>(ctx, P, n);
+        case 32: return launch_ssw<32>(ctx, P, n);
+        case 40: return launch_ssw<40>(ctx, P, n);
+        case 48: return launch_ssw<48>(ctx, P, n);
+        case 56: return launch_ssw<56>(ctx, P, n);
+        default: return launch_ssw<64>(ctx, P, n);
+    }
+}
+
+// One recursion round of the default (skbio / SSW) seeding path: per register-row class one fused launch (forward scan,
+// reverse scan, banded traceback, hit test, children) and its second band tier.
+int run_round_ssw(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int64_t>& h_seg, SswParams P, lsw_counters* cnt) {
+    CK(ctx->d_nfallback.ensure(NCLASS * 8));
+    CK(cudaMemsetAsync(ctx->d_nfallback.p, 0, NCLASS * 8, ctx->stream));
+    CK(ctx->d_fb2cnt.ensure((size_t)std::max(ctx->nseq, 1) * 8));
+    CK(cudaMemsetAsync(ctx->d_fb2cnt.p, 0, 8, ctx->stream));
+    P.codes = ctx->d_codes.as<uint8_t>(); P.roff = ctx->d_roff.as<int64_t>();
+    P.t = cur.view();
+    P.qcodes = ctx->d_qcodes.as<uint8_t>(); P.qlen = ctx->d_qlen.as<int32_t>();
+    P.seg = ctx->d_seg[segi].as<int64_t>();
+    P.match = ctx->ssw_match; P.mismatch = ctx->ssw_mismatch; P.gap_open = ctx->ssw_open; P.gap_extend = ctx->ssw_extend;
+    P.counters = ctx->d_counters.as<unsigned long long>();
+    P.errflag = ctx->d_err.as<int32_t>();
+    Span sp(ctx, (P.mode == 0 && P.round == 0) ? 4 : 0);
+    for (int c = 0; c < NCLASS; c++) {
+        int64_t ncls = 0;
+        for (int s : ctx->class_seqs[c]) ncls += h_seg[s + 1] - h_seg[s];
+        if (!ncls) continue;
+        CK(ctx->d_fallback[c].ensure((size_t)ncls * 4));
+        P.class_seqs = ctx->d_class_seqs[c].as<int32_t>();
+        P.n_class_seqs = (int)ctx->class_seqs[c].size();
+        P.fallback = ctx->d_fallback[c].as<uint32_t>();
+        P.nfallback = ctx->d_nfallback.as<unsigned long long>() + c;
+        if (int rc = launch_ssw_class(ctx, c, P, ncls)) return rc;
+        if (cnt) cnt->score_launches += 2;
+    }
+    return LSW_OK;
+}
+
 void collect_times(lsw_ctx* ctx, lsw_counters* cnt) {
     for (const Timed& t : ctx->timed) {
         float ms = 0.f;
@@ -766,11 +831,23 @@ int lsw_set_scoring(lsw_ctx* ctx, int match, int mismatch, int gap, int gap_ext)
     if (mismatch - gap < -128)
         return fail(ctx, LSW_E_UNSUPPORTED, "mismatch + |gap| must be >= -128 for the packed 8.8 fixed-point cells");
     ctx->match = match; ctx->mismatch = mismatch; ctx->g = -gap;
+    ctx->ssw = false;
     return LSW_OK;          // scoring and queries may be set in either order: the pair is checked when work is submitted
+}
+
+int lsw_set_ssw(lsw_ctx* ctx, int match, int mismatch, int gap_open, int gap_extend) {
+    if (!ctx) return LSW_E_ARG;
+    if (match <= 0 || match > 100 || mismatch > 0 || mismatch < -100 || gap_open <= 0 || gap_open > 100 || gap_extend <= 0 ||
+        gap_extend > gap_open)
+        return fail(ctx, LSW_E_UNSUPPORTED, "SSW scoring: need 0 < match <= 100, -100 <= mismatch <= 0, 0 < gap_extend <= gap_open <= 100");
+    ctx->ssw_match = match; ctx->ssw_mismatch = mismatch; ctx->ssw_open = gap_open; ctx->ssw_extend = gap_extend;
+    ctx->ssw = true;
+    return LSW_OK;
 }
 
 // Scores are kept as 8.8 fixed point in 16-bit halves, biased by g: the largest value a cell can hold must stay <= 127.
 static int check_scoring_fits(lsw_ctx* ctx) {
+    if (ctx->ssw) return LSW_OK;          // scalar int32 cells: lsw_set_ssw's bounds are enough
     for (int s = 0; s < ctx->nseq; s++)
         if (ctx->match * ctx->qlen[s] + ctx->g > 127)
             return fail(ctx, LSW_E_UNSUPPORTED, "match * len(query) + |gap| must be <= 127 for the packed cells");
@@ -972,7 +1049,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     }
 
     // block bests of round 0 for the child tasks: 4 B per BB_BLOCK columns per (read, sequence)
-    bool reuse = ctx->reuse && !getenv("LSW_NO_REUSE");
+    bool reuse = ctx->reuse && !getenv("LSW_NO_REUSE") && !ctx->ssw;    // (SSW's "first maximum wins" end rule has no block-best merge yet)
     // the block bests are an optimisation (4 B per 32 columns per sequence): without room for them every round simply
     // aligns whole slices -- same results, more cells
     if (reuse && ctx->d_blockbest.ensure((size_t)std::max<int64_t>(1, ctx->bb_total) * ctx->nseq * 4) != cudaSuccess) {
@@ -1003,7 +1080,16 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         T.hits = ctx->d_hits.p; T.hits_cap = hit_cap; T.nhits = ctx->d_nhits.as<unsigned long long>();
         T.child_flag = ctx->d_child_flag.as<uint8_t>();
         T.child = ctx->child.view();
-        rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse ? (round == 0 ? 1 : 2) : 0);
+        if (ctx->ssw) {
+            SswParams S;
+            memset(&S, 0, sizeof S);
+            S.mode = 0; S.thr = thr; S.round = round;
+            S.hits = T.hits; S.hits_cap = T.hits_cap; S.nhits = T.nhits;
+            S.child_flag = T.child_flag; S.child = T.child;
+            rc = run_round_ssw(ctx, ctx->tb[cur], cur, h_seg, S, &cnt);
+        } else {
+            rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse ? (round == 0 ? 1 : 2) : 0);
+        }
         if (rc) break;
         if (reuse && round == 0 && ctx->use_bb1 && ctx->bb1_total > 0) {
             Span sp(ctx, 2);
@@ -1039,6 +1125,8 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         }
         CK(cudaMemcpyAsync(h_seg.data(), ctx->d_seg[cur ^ 1].p, h_seg.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(&h_nhits, ctx->d_nhits.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx->d_ncand.ensure(NCLASS * 8)); CK(ctx->d_nfallback.ensure(NCLASS * 8));
+        if (ctx->ssw) CK(cudaMemsetAsync(ctx->d_ncand.p, 0, NCLASS * 8, ctx->stream));
         unsigned long long h_nc[NCLASS], h_nf[NCLASS], h_comp0 = 0;
         if (round == 0) CK(cudaMemcpyAsync(&h_comp0, ctx->d_counters.as<unsigned long long>() + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_nc, ctx->d_ncand.p, NCLASS * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1236,7 +1324,15 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n, const lsw_task* tasks, lsw_result* 
     T.cigar = want_cigar ? ctx->d_cigar.as<uint32_t>() : nullptr;
     T.cigar_cap = want_cigar ? cigar_cap : 0;
     T.ncigar = ctx->d_ncigar.as<unsigned long long>();
-    int rc = run_round(ctx, cur, 0, h_seg, n, T, nullptr);
+    int rc;
+    if (ctx->ssw) {
+        SswParams S;
+        memset(&S, 0, sizeof S);
+        S.mode = 1; S.results = T.results; S.cigar = T.cigar; S.cigar_cap = T.cigar_cap; S.ncigar = T.ncigar;
+        rc = run_round_ssw(ctx, cur, 0, h_seg, S, nullptr);
+    } else {
+        rc = run_round(ctx, cur, 0, h_seg, n, T, nullptr);
+    }
     if (rc) return rc;
 
     unsigned long long h_ncig = 0;
@@ -1281,6 +1377,8 @@ int lsw_measure_int_peak(lsw_ctx* ctx, int mode, int iters, double* lane_ops_per
             case 10: k_intpeak_k1row<0><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
             case 11: k_intpeak_k1row<1><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
             case 12: k_intpeak_k1row<2><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
+            case 13: k_intpeak_k1row<3><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
+            case 14: k_intpeak_k1row<4><<<blocks, threads, smem9, ctx->stream>>>(out.as<uint32_t>(), in.as<uint32_t>(), iters); break;
             default: cudaEventDestroy(e0); cudaEventDestroy(e1); out.release(); in.release();
                      return fail(ctx, LSW_E_ARG, "lsw_measure_int_peak: unknown mode");
         }

@@ -18,6 +18,7 @@
 #include "lsw_trace.cuh"
 #include "lsw_band.cuh"
 #include "lsw_reuse.cuh"
+#include "lsw_ssw.cuh"
 #include "lsw_host.hpp"
 
 using namespace lsw;
@@ -422,6 +423,119 @@ int lsw_emu_align_tasks(int64_t n_reads, const uint8_t* ascii, const int64_t* of
     if (n) emu_round(E, T);
     if (fallbacks) *fallbacks = (int64_t)E.fallbacks;
     if (errflag) return LSW_E_INTERNAL;
+    if (cigar_used) *cigar_used = (int64_t)ncig;
+    if (cigar_buf && (int64_t)ncig > cigar_cap) return LSW_E_OVERFLOW;
+    return LSW_OK;
+}
+
+
+}  // extern "C"
+
+// ---- the default (skbio / SSW) seeding path: lsw_ssw.cuh driven one task at a time --------------------------------------
+namespace {
+template <int NR>
+int emu_ssw_one(const SswParams& P, int t, std::vector<uint8_t>& dir, unsigned long long* tier2) {
+    dir.assign(SswBand<SSW_BW2>::DIR_BYTES, 0);
+    int rc = ssw_task<NR, SSW_BW1>(P, t, dir.data());
+    if (rc == 0) { if (tier2) (*tier2)++; rc = ssw_task<NR, SSW_BW2>(P, t, dir.data()); }
+    return rc;
+}
+int emu_ssw_task(const SswParams& P, int t, int Q, std::vector<uint8_t>& dir, unsigned long long* tier2) {
+    int c = 0;
+    while (CLASS_NR[c] < Q) c++;
+    switch (CLASS_NR[c]) {
+        case 16: return emu_ssw_one<16>(P, t, dir, tier2);
+        case 20: return emu_ssw_one<20>(P, t, dir, tier2);
+        case 24: return emu_ssw_one<24>(P, t, dir, tier2);
+        case 28: return emu_ssw_one<28>(P, t, dir, tier2);
+        case 32: return emu_ssw_one<32>(P, t, dir, tier2);
+        case 40: return emu_ssw_one<40>(P, t, dir, tier2);
+        case 48: return emu_ssw_one<48>(P, t, dir, tier2);
+        case 56: return emu_ssw_one<56>(P, t, dir, tier2);
+        default: return emu_ssw_one<64>(P, t, dir, tier2);
+    }
+}
+void ssw_base_params(Emu& E, SswParams& P, int match, int mismatch, int gap_open, int gap_extend) {
+    memset(&P, 0, sizeof P);
+    P.codes = E.codes.data(); P.roff = E.roff.data();
+    P.qcodes = E.qcodes.data(); P.qlen = E.qlen.data();
+    P.match = match; P.mismatch = mismatch; P.gap_open = gap_open; P.gap_extend = gap_extend;
+}
+}  // namespace
+
+extern "C" {
+
+int lsw_emu_ssw_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
+                         const int32_t* qoffs, int match, int mismatch, int gap_open, int gap_extend, double thr, lsw_hit* out,
+                         int64_t cap, int64_t* n_out, int64_t* counters /* tasks, cells, rounds, tier-2 tasks */) {
+    Emu E;
+    if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, 2, -1, -1)) return LSW_E_UNSUPPORTED;
+    const int64_t n0 = n_reads * nseq;
+    E.t_read.resize(n0); E.t_a.resize(n0); E.t_b.resize(n0); E.t_seq.resize(n0);
+    for (int64_t i = 0; i < n0; i++) {
+        const int s = (int)(i / n_reads); const int64_t r = i - (int64_t)s * n_reads;
+        E.t_read[i] = (int32_t)r; E.t_a[i] = 0; E.t_b[i] = E.rlen[r]; E.t_seq[i] = (int16_t)s;
+    }
+    unsigned long long nhits = 0, tasks = 0, cells = 0, tier2 = 0;
+    int32_t errflag = 0;
+    int round = 0;
+    std::vector<uint8_t> dir;
+    while (!E.t_read.empty()) {
+        const int64_t n = (int64_t)E.t_read.size(), n2 = 2 * n;
+        std::vector<int32_t> c_read(n2), c_a(n2), c_b(n2);
+        std::vector<int16_t> c_seq(n2);
+        std::vector<uint8_t> flag(n2 + 1, 0);
+        SswParams P;
+        ssw_base_params(E, P, match, mismatch, gap_open, gap_extend);
+        P.t.read = E.t_read.data(); P.t.a = E.t_a.data(); P.t.b = E.t_b.data(); P.t.seq = E.t_seq.data();
+        P.mode = 0; P.thr = thr; P.round = round;
+        P.hits = out; P.hits_cap = cap; P.nhits = &nhits;
+        P.child_flag = flag.data();
+        P.child.read = c_read.data(); P.child.a = c_a.data(); P.child.b = c_b.data(); P.child.seq = c_seq.data();
+        for (int64_t t = 0; t < n; t++) {
+            tasks++; cells += (unsigned long long)(E.t_b[t] - E.t_a[t]) * E.qlen[E.t_seq[t]];
+            if (emu_ssw_task(P, (int)t, E.qlen[E.t_seq[t]], dir, &tier2) != 1) errflag = 1;
+        }
+        std::vector<int32_t> nr, na, nb; std::vector<int16_t> ns;
+        for (int64_t j = 0; j < n2; j++)
+            if (flag[j]) { nr.push_back(c_read[j]); na.push_back(c_a[j]); nb.push_back(c_b[j]); ns.push_back(c_seq[j]); }
+        E.t_read.swap(nr); E.t_a.swap(na); E.t_b.swap(nb); E.t_seq.swap(ns);
+        round++;
+    }
+    if (errflag) return LSW_E_INTERNAL;
+    if (n_out) *n_out = (int64_t)nhits;
+    if (counters) { counters[0] = (int64_t)tasks; counters[1] = (int64_t)cells; counters[2] = round; counters[3] = (int64_t)tier2; }
+    if ((int64_t)nhits > cap) return LSW_E_OVERFLOW;
+    std::sort(out, out + nhits, [](const lsw_hit& x, const lsw_hit& y) {
+        if (x.read != y.read) return x.read < y.read;
+        if (x.start != y.start) return x.start < y.start;
+        return x.query < y.query;
+    });
+    return LSW_OK;
+}
+
+int lsw_emu_ssw_align_tasks(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
+                            const int32_t* qoffs, int match, int mismatch, int gap_open, int gap_extend, int64_t n,
+                            const lsw_task* tasks, lsw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used) {
+    Emu E;
+    if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, 2, -1, -1)) return LSW_E_UNSUPPORTED;
+    E.t_read.resize(n); E.t_a.resize(n); E.t_b.resize(n); E.t_seq.resize(n); E.t_orig.resize(n);
+    for (int64_t i = 0; i < n; i++) {
+        const lsw_task& t = tasks[i];
+        if (t.query < 0 || t.query >= nseq || t.read < 0 || t.read >= n_reads || t.start < 0 || t.end < t.start ||
+            t.end > E.rlen[t.read]) return LSW_E_ARG;
+        E.t_read[i] = t.read; E.t_a[i] = t.start; E.t_b[i] = t.end; E.t_seq[i] = (int16_t)t.query; E.t_orig[i] = (int32_t)i;
+    }
+    unsigned long long ncig = 0;
+    SswParams P;
+    ssw_base_params(E, P, match, mismatch, gap_open, gap_extend);
+    P.t.read = E.t_read.data(); P.t.a = E.t_a.data(); P.t.b = E.t_b.data(); P.t.seq = E.t_seq.data(); P.t.orig = E.t_orig.data();
+    P.mode = 1; P.results = out; P.cigar = cigar_buf; P.cigar_cap = cigar_buf ? cigar_cap : 0; P.ncigar = &ncig;
+    std::vector<uint8_t> dir;
+    int bad = 0;
+    for (int64_t t = 0; t < n; t++)
+        if (emu_ssw_task(P, (int)t, E.qlen[E.t_seq[t]], dir, nullptr) != 1) bad = 1;
+    if (bad) return LSW_E_INTERNAL;
     if (cigar_used) *cigar_used = (int64_t)ncig;
     if (cigar_buf && (int64_t)ncig > cigar_cap) return LSW_E_OVERFLOW;
     return LSW_OK;

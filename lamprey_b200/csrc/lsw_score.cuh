@@ -41,6 +41,19 @@ LSW_HD uint32_t mad_one(uint32_t a, uint32_t one, uint32_t b) {
 #endif
 }
 
+// a * 0x10001 + b as a multiply-add with an IMMEDIATE multiplier: the assembler cannot turn it into an add, so it is issued on
+// the FMA pipe (IMAD), next to the DPX instructions that saturate the ALU pipe.  a = a small count: a * 0x10001 puts it into
+// both s16 halves; a = -256 g: a * 0x10001 == -(0x01000100 g) (mod 2^32), the packed subtraction of the gap penalty.
+LSW_HD uint32_t mad_x2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t o;
+    asm("mad.lo.u32 %0, %1, 0x10001, %2;" : "=r"(o) : "r"(a), "r"(b));
+    return o;
+#else
+    return a * 0x10001u + b;
+#endif
+}
+
 struct U4 { uint32_t x, y, z, w; };
 struct U2 { uint32_t x, y; };
 
@@ -157,9 +170,12 @@ struct ScoreLane {
     //   0  K = max3(K, h1 + tagA, h2 + tagB)            2 adds + 1 VIMNMX3   (the compiler issues the adds as VIADD: ALU pipe)
     //   1  K = max(h2 + tagB, max(h1 + tagA, K))        2 VIADDMNMX          (one ALU instruction less, none on the FMA pipe)
     //   2  as 0 with the adds forced onto the FMA pipe  (IMAD with a run-time multiplier of one)
+    //   3  as 0 with the key adds as IMAD with the immediate multiplier 0x10001 (mad_x2): FMA pipe
+    //   4  as 3, and the two subtractions of the gap penalty the same way
     template <int KEYV = LSW_K1_KEYV>
     LSW_HD void column2(const U2* prowA, const U2* prowB, uint32_t tvA, uint32_t tvB, uint32_t G2, uint32_t FLOOR2, uint32_t one = 1u) {
         uint32_t dOld = 0, uA = 0, uB = 0;
+        const uint32_t negG = 0u - (G2 & 0xFFFFu) * one;       // -256 g (times a run-time one: stays a register operand)
 #pragma unroll
         for (int r2 = 0; r2 < NR / 2; r2++) {
             const U2 sa = prowA[r2], sb = prowB[r2];
@@ -168,12 +184,13 @@ struct ScoreLane {
                 const uint32_t mold = M[R];                      \
                 const uint32_t T1 = addmax2(dOld, SA, mold);     \
                 const uint32_t h1 = max3_2(T1, uA, FLOOR2);      \
-                const uint32_t m1 = h1 - G2;                     \
+                const uint32_t m1 = KEYV == 4 ? mad_x2(negG, h1) : h1 - G2; \
                 const uint32_t T2 = addmax2(uA, SB, m1);         \
                 const uint32_t h2 = max3_2(T2, uB, FLOOR2);      \
-                const uint32_t m2 = h2 - G2;                     \
+                const uint32_t m2 = KEYV == 4 ? mad_x2(negG, h2) : h2 - G2; \
                 const uint32_t tA = tvA + ((R) & 1) * 0x00400040u, tB = tvB + ((R) & 1) * 0x00400040u; \
-                if (KEYV == 1) K[(R) >> 1] = addmax2(h2, tB, addmax2(h1, tA, K[(R) >> 1])); \
+                if (KEYV == 3 || KEYV == 4) K[(R) >> 1] = max3_2(K[(R) >> 1], mad_x2((tvA & 0xFFFFu) + ((R) & 1) * 64u, h1), mad_x2((tvB & 0xFFFFu) + ((R) & 1) * 64u, h2)); \
+                else if (KEYV == 1) K[(R) >> 1] = addmax2(h2, tB, addmax2(h1, tA, K[(R) >> 1])); \
                 else if (KEYV == 2) K[(R) >> 1] = max3_2(K[(R) >> 1], mad_one(h1, one, tA), mad_one(h2, one, tB)); \
                 else K[(R) >> 1] = max3_2(K[(R) >> 1], h1 + tA, h2 + tB); \
                 M[R] = m2;                                       \

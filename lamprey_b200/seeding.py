@@ -6,7 +6,8 @@ Mirrors, name for name and argument for argument (same ordering and error behavi
 * ``PrimerSet``                  /root/reference/lamprey.py:81-136
 * ``Alignment``                  /root/reference/lamprey.py:138-161
 * ``alignSequence_swalign``      /root/reference/lamprey.py:558-569
-* ``findPrimerAlignments``       /root/reference/lamprey.py:596-645   (--swalign branch)
+* ``alignSequence_skbio``        /root/reference/lamprey.py:572-593   (the default branch: scikit-bio's StripedSmithWaterman)
+* ``findPrimerAlignments``       /root/reference/lamprey.py:596-645   (both branches: ``args.swalign`` decides, as in the reference)
 * ``findAllPrimerAlignments``    /root/reference/lamprey.py:699-733
 
 and adds the batched form the reference lacks: ``seed_reads(reads, primer_set, threshold)`` seeds a
@@ -102,14 +103,17 @@ class SeedBatch(object):
     """Seeds of a read batch.  ``hits`` is a HIT_DT array ordered by (read, start, search order) --
     the order lamprey.py:722's stable sort produces; ``offsets[i]:offsets[i+1]`` are read i's hits."""
 
-    def __init__(self, hits, n_reads, read_lengths, names, counters):
+    def __init__(self, hits, n_reads, read_lengths, names, counters, qlen=None):
         self.hits = hits
         self.names = names
         self.counters = counters
         self.read_lengths = read_lengths
         self.offsets = np.searchsorted(hits["read"], np.arange(n_reads + 1)).astype(np.int64)
-        tot = (hits["matches"].astype(np.int64) + hits["mismatches"])
-        self.identity = hits["matches"] / np.maximum(tot, 1)        # tot > 0 for every hit
+        if qlen is not None:          # skbio path: float(matches)/float(len(primer)), lamprey.py:585
+            self.identity = hits["matches"] / qlen[hits["query"]].astype(np.float64)
+        else:
+            tot = (hits["matches"].astype(np.int64) + hits["mismatches"])
+            self.identity = hits["matches"] / np.maximum(tot, 1)        # tot > 0 for every hit
         covered = np.zeros(n_reads, np.int64)
         np.add.at(covered, hits["read"], (hits["end"] - hits["start"]).astype(np.int64))
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -145,6 +149,26 @@ def _scoring_of(aligner):
     return (aligner.scoring_matrix.match, aligner.scoring_matrix.mismatch, aligner.gap_penalty, aligner.gap_extension_penalty)
 
 
+SKBIO_DEFAULTS = (2, -3, 5, 2)       # StripedSmithWaterman: match_score, mismatch_score, gap_open_penalty, gap_extend_penalty
+
+
+def _use_skbio(args, method):
+    """Which branch of lamprey.py:607-610 to take: `args.swalign` decides, as in the reference (its default is False: skbio);
+    without an args object the `method` keyword does ("swalign" unless told otherwise)."""
+    if method is not None:
+        if method not in ("swalign", "skbio"):
+            raise ValueError("method must be 'swalign' or 'skbio'")
+        return method == "skbio"
+    return args is not None and hasattr(args, "swalign") and not args.swalign
+
+
+def _set_engine_scoring(eng, aligner, skbio):
+    if skbio:
+        eng.set_ssw(*SKBIO_DEFAULTS)
+    else:
+        eng.set_scoring(*_scoring_of(aligner))
+
+
 def get_pool(devices, contexts_per_device=1):
     """One lazily created pool per (device list, contexts per device)."""
     key = (tuple(int(d) for d in devices), int(contexts_per_device))
@@ -171,17 +195,35 @@ def _seed_on_pool(pool, concat, offs, hit_cap=None):
 
 
 def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None, devices=None,
-               compact=True):
+               compact=True, method=None, args=None):
     """findAllPrimerAlignments for every read of a batch in one device pass.  allowed_overlap (LAMPrey uses 4,
     lamprey.py:1536) also runs removeOverlappingPrimerAlignments on the device: see SeedBatch.kept.
 
     devices=[0, 1, ...]: the batch is split over those GPUs in contiguous read ranges balanced by bases, one host thread
     and context per GPU, and the hits are gathered on the host in global read order -- what the reference does with
-    worker processes (lamprey.py:2182-2207).  The result is identical to the single-device one."""
+    worker processes (lamprey.py:2182-2207).  The result is identical to the single-device one.
+
+    method="skbio" (or an `args` whose .swalign is False, the reference's default) seeds with scikit-bio's
+    StripedSmithWaterman semantics instead of swalign's (lamprey.py:572-593): hits then carry identity = matches / len(primer)."""
     from . import swalign as _sw
     concat, offs = _read_arrays(reads)
     pairs = primer_set.sequences()
     names = [n for n, _ in pairs]
+    skbio = _use_skbio(args, method)
+    if skbio:
+        if devices is not None:
+            raise NotImplementedError("the skbio seeding path runs on one context (devices= is for the swalign path)")
+        eng = engine or _sw.get_engine(device)
+        eng.set_ssw(*SKBIO_DEFAULTS)
+        eng.set_queries([s for _, s in pairs])
+        eng.upload_reads(concat, offs)
+        eng.set_overlap(allowed_overlap)
+        try:
+            hits = eng.find_all(threshold)
+        finally:
+            eng.set_overlap(None)
+        return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters,
+                         qlen=np.array([len(s) for _, s in pairs], np.int64))
     if devices is not None:
         pool = get_pool(devices)
         sc = _scoring_of(aligner)
@@ -254,6 +296,20 @@ def alignSequence_swalign(aligner, seq, primer, primer_name):
     return Alignment(alignment_tmp.r_pos, alignment_tmp.r_end, alignment_tmp.identity, primer_name)
 
 
+def alignSequence_skbio(seq, primer, primer_name):
+    """Aligns two sequences with scikit-bio's StripedSmithWaterman semantics -- drop-in for
+    /root/reference/lamprey.py:572-593 (the default seeding branch)."""
+    from . import skbio_ssw
+    alignment = skbio_ssw.StripedSmithWaterman(primer)(str(seq))
+    aq, at = alignment.aligned_query_sequence, alignment.aligned_target_sequence
+    matches = 0
+    for i in range(0, len(aq)):
+        if aq[i] == at[i]:
+            matches = matches + 1
+    identity = float(matches) / float(len(primer))
+    return Alignment(alignment.target_begin, alignment.target_end_optimal + 1, identity, primer_name)
+
+
 def _preorder(hits, identity, name):
     """Rebuild findPrimerAlignments' pre-order list from one sequence's hits sorted by start.
     Hits of one sequence never overlap and each knows its recursion depth, so the recursion tree
@@ -277,11 +333,13 @@ def findPrimerAlignments(aligner, seq, primer, primer_name, identity_threshold, 
     (the reference only reads ``args.swalign`` from it)."""
     from . import swalign as _sw
     eng = _sw.get_engine(getattr(aligner, "device", 0))
-    eng.set_scoring(aligner.scoring_matrix.match, aligner.scoring_matrix.mismatch, aligner.gap_penalty,
-                    aligner.gap_extension_penalty)
+    skbio = _use_skbio(args, None)
+    _set_engine_scoring(eng, aligner, skbio)
     eng.set_queries([primer])
     eng.upload_read_list([str(seq)])
     hits = eng.find_all(identity_threshold)
+    if skbio:
+        return _preorder(hits, hits["matches"] / float(len(primer)), primer_name)
     tot = hits["matches"].astype(np.int64) + hits["mismatches"]
     return _preorder(hits, hits["matches"] / np.maximum(tot, 1), primer_name)
 
@@ -289,7 +347,7 @@ def findPrimerAlignments(aligner, seq, primer, primer_name, identity_threshold, 
 def findAllPrimerAlignments(aligner, seq, primers, identity_threshold, args=None):
     """(stable-sorted hit list, coverage) for one read -- drop-in for lamprey.py:699-733."""
     batch = seed_reads([str(seq)], primers, identity_threshold, aligner=aligner,
-                       device=getattr(aligner, "device", 0))
+                       device=getattr(aligner, "device", 0), args=args)
     return batch[0]
 
 

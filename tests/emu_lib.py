@@ -57,3 +57,39 @@ def align_tasks(reads, seqs, tasks, match=2, mismatch=-1, gap=-1, force_full=Fal
     if stats is not None:
         stats["fallbacks"] = fb.value
     return out, cig[:used.value]
+
+
+def ssw_find_all(reads, seqs, thr, match=2, mismatch=-3, gap_open=5, gap_extend=2):
+    """The default (skbio / SSW) seeding path through the host emulation of lsw_ssw.cuh."""
+    rc_, ro = concat_sequences(reads)
+    qc, qo = concat_sequences(seqs)
+    qo = qo.astype(np.int32)
+    cap = max(1024, int(ro[-1]) // 4)
+    out = np.zeros(cap, HIT_DT)
+    n = ctypes.c_int64(0)
+    cnt = np.zeros(4, np.int64)
+    lib().lsw_emu_ssw_find_all.restype = ctypes.c_int
+    rc = lib().lsw_emu_ssw_find_all(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc), _ptr(qo),
+                                    ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap_open), ctypes.c_int(gap_extend),
+                                    ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt))
+    if rc:
+        raise RuntimeError("lsw_emu_ssw_find_all rc=%d" % rc)
+    return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), rounds=int(cnt[2]), tier2=int(cnt[3]))
+
+
+def ssw_align_tasks(reads, seqs, tasks, match=2, mismatch=-3, gap_open=5, gap_extend=2):
+    rc_, ro = concat_sequences(reads)
+    qc, qo = concat_sequences(seqs)
+    qo = qo.astype(np.int32)
+    tasks = np.ascontiguousarray(tasks, dtype=TASK_DT)
+    out = np.zeros(len(tasks), RESULT_DT)
+    cap = max(64, 8 * len(tasks) + int(sum(t["end"] - t["start"] for t in tasks)))
+    cig = np.zeros(cap, np.uint32)
+    used = ctypes.c_int64(0)
+    lib().lsw_emu_ssw_align_tasks.restype = ctypes.c_int
+    rc = lib().lsw_emu_ssw_align_tasks(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc), _ptr(qo),
+                                       ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap_open), ctypes.c_int(gap_extend),
+                                       ctypes.c_int64(len(tasks)), _ptr(tasks), _ptr(out), _ptr(cig), ctypes.c_int64(cap), ctypes.byref(used))
+    if rc:
+        raise RuntimeError("lsw_emu_ssw_align_tasks rc=%d" % rc)
+    return out, cig[:used.value]

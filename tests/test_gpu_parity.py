@@ -464,6 +464,26 @@ def test_find_all_1024_synthetic_reads_vs_oracle(engine):
     assert len(rows) > 100000
 
 
+@pytest.mark.parametrize("wl", ["synth_5kb_12pct", "synth_20_50kb_12pct"])
+def test_find_all_1000_reads_of_the_large_configs_vs_committed_digest(engine, wl):
+    # BASELINE.json configs[3] and [4] (5 kb / 12 %; 20-50 kb with the 40-sequence schema): 1000-read slices, oracle results
+    # committed as counts + SHA-256 of the int32 hit matrix (tests/golden/make_golden_more.py)
+    import hashlib
+    gold = json.load(open(os.path.join(GOLD, "synth_digests.json")))[wl]
+    concat, offs = synth.generate(gold["reads"], **synth.CONFIGS[wl])
+    assert int(offs[-1]) == gold["bases"]
+    ps = seeding.PrimerSet(schema_path("H33"))
+    engine.set_scoring(2, -1, -1, -1)
+    engine.set_queries([s for _, s in synth.schema_sequences(ps, wl)])
+    engine.upload_reads(concat, offs)
+    hits = engine.find_all(gold["threshold"])
+    mat = hits_matrix(hits)
+    assert mat[:8].tolist() == gold["first_rows"]
+    assert (len(mat), engine.last_counters["tasks"], engine.last_counters["cells"]) == (gold["hits"], gold["calls"], gold["cells"])
+    assert hashlib.sha256(np.ascontiguousarray(mat, dtype="<i4").tobytes()).hexdigest() == gold["sha256"]
+    assert engine.last_counters["fallbacks"] == 0
+
+
 def test_seed_fastq_one_file_one_batch(engine, tmp_path):
     # FASTQ file -> seeds in one call (the online mode's one file = one batch), against the golden seeding result
     reads = load_reads("50")

@@ -6,8 +6,9 @@ from lamprey_b200 import _native
 e = _native.Engine(0)
 NAMES = {0: "VIADDMNMX.S16x2", 1: "VIMNMX3.S16x2", 2: "IADD", 3: "IMAD", 4: "row mix (old model)", 5: "row mix, IMAD sub", 6: "LOP3",
          7: "VIADDMNMX.S16x2.RELU", 8: "VIMNMX.S16x2 (2 operands)", 9: "K1 inner loop as built", 10: "K1 inner loop, keys: 2 add + VIMNMX3",
-         11: "K1 inner loop, keys: 2 VIADDMNMX", 12: "K1 inner loop, keys: 2 IMAD + VIMNMX3"}
-for m in range(13):
+         11: "K1 inner loop, keys: 2 VIADDMNMX", 12: "K1 inner loop, keys: 2 IMAD + VIMNMX3",
+         13: "K1 inner loop, keys: 2 IMAD-imm + VIMNMX3", 14: "K1 inner loop, keys and subs as IMAD-imm"}
+for m in range(15):
     ops, ms = e.measure_int_peak(m, 20000 if m < 9 else 4000)
     if m >= 9:
         print("%2d %-42s %9.1f GCUPS  (%.3f ms)" % (m, NAMES[m], ops * 4 / 9 / 1e9, ms))
