@@ -37,6 +37,7 @@ extern "C" {
 #define LSW_E_STATE      -5   /* call order (e.g. align before set_queries)             */
 #define LSW_E_INTERNAL   -6   /* an internal invariant failed (reported, never silent)  */
 
+#define LSW_MAX_ORDER 16       /* names in a fwd_primer_order / rev_primer_order line (lsw_chain_subreads) */
 #define LSW_MAX_QUERY_LEN 63  /* rows a query may have (kernels keep all rows in registers) */
 
 typedef struct lsw_ctx lsw_ctx;
@@ -89,6 +90,16 @@ typedef struct {
     uint8_t  mismatches;
     uint8_t  q_pos, q_end;
 } lsw_hit16;                       /* 16 bytes */
+
+/* One candidate sub-read of stage 1 of processLamplicon (lamprey.py:1566-1589): the amplicon extractAmpliconAroundTarget
+ * grows around a surviving target hit ('T' or 'Tc'), in read coordinates as the reference slices them (seq[start:end]). */
+typedef struct {
+    int32_t read;
+    int32_t start, end;            /* end: amplicon_end, or len(read) - 1 where the reference got -1 */
+    int32_t target_idx;            /* n-th target of the read: the subread id is "<lamp_idx>_<target_idx>" */
+    int32_t direction;             /* 0 'fwd' (target 'T'), 1 'rev' (target 'Tc') */
+    int32_t hit;                   /* the target hit: index within the read's hits */
+} lsw_subread;
 
 typedef struct {
     int64_t tasks;        /* align() invocations the reference would have made            */
@@ -164,6 +175,12 @@ int lsw_set_read_base(lsw_ctx* ctx, int64_t base);     /* added to lsw_hit.read:
  * allowed_overlap >= 0 every hit lsw_find_all returns has reserved = 1 if it survives the pruning of its read's
  * sorted hit list, 0 otherwise.  Negative (default) = off. */
 int lsw_set_overlap(lsw_ctx* ctx, int allowed_overlap);
+/* Stage 1 of processLamplicon for every read of the last lsw_find_all (which must have run with lsw_set_overlap >= 0; LAMPrey
+ * uses 4): extractAmpliconAroundTarget around every surviving target hit.  fwd_order / rev_order: the query index of every name
+ * of the schema's fwd_primer_order / rev_primer_order lines (-1 for a name that is not a schema sequence); t_query / tc_query:
+ * the query indices of 'T' and 'Tc'.  Sub-reads come back ordered by (read, target_idx). */
+int lsw_chain_subreads(lsw_ctx* ctx, int n_fwd, const int32_t* fwd_order, int n_rev, const int32_t* rev_order, int t_query,
+                       int tc_query, lsw_subread* out, int64_t cap, int64_t* n_out);
 int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap);   /* 0 = default (total bases / 8 + 4096) */
 int lsw_find_all(lsw_ctx* ctx, double identity_threshold, int64_t* n_hits, lsw_counters* counters);
 int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out);

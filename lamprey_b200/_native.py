@@ -37,8 +37,9 @@ assert HIT16_DT.itemsize == 16
 # every symbol include/lsw.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",
            "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_overlap", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
-           "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_set_ssw", "lsw_host_alloc", "lsw_host_free",
+           "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_set_ssw", "lsw_chain_subreads", "lsw_host_alloc", "lsw_host_free",
            "lsw_pool_create", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_pool_configure", "lsw_pool_submit", "lsw_pool_wait")
+SUBREAD_DT = np.dtype([("read", "<i4"), ("start", "<i4"), ("end", "<i4"), ("target_idx", "<i4"), ("direction", "<i4"), ("hit", "<i4")])
 HITS_WIDE, HITS_COMPACT = 0, 1
 POOL_TIMES_DT = np.dtype([("upload_s", "<f8"), ("find_s", "<f8"), ("fetch_s", "<f8"), ("gather_wait_s", "<f8"), ("total_s", "<f8"),
                           ("reads", "<i8", (8,)), ("hits", "<i8", (8,))])
@@ -74,6 +75,7 @@ def load():
     lib.lsw_measure_int_peak.argtypes = [vp, i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_float)]
     lib.lsw_fetch_hits_compact.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_set_ssw.argtypes = [vp, i32, i32, i32, i32]
+    lib.lsw_chain_subreads.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_host_alloc.argtypes = [i64, ctypes.POINTER(vp)]
     lib.lsw_host_free.argtypes = [vp]
     lib.lsw_host_free.restype = None
@@ -360,6 +362,22 @@ class Engine(object):
         got = ctypes.c_int64(0)
         self._check(self._lib.lsw_fetch_hits(self._h, _ptr(out), len(out), ctypes.byref(got)), "lsw_fetch_hits")
         return out[:got.value]
+
+    def chain_subreads(self, fwd_order, rev_order, t_query, tc_query):
+        """Stage 1 of processLamplicon for the last find_all (which must have run with set_overlap): SUBREAD_DT records."""
+        fo = np.ascontiguousarray(fwd_order, dtype=np.int32)
+        ro = np.ascontiguousarray(rev_order, dtype=np.int32)
+        cap = 1024
+        while True:
+            out = np.zeros(cap, SUBREAD_DT)
+            n = ctypes.c_int64(0)
+            rc = self._lib.lsw_chain_subreads(self._h, len(fo), _ptr(fo), len(ro), _ptr(ro), int(t_query), int(tc_query), _ptr(out), cap,
+                                              ctypes.byref(n))
+            if rc == LSW_E_OVERFLOW and n.value > cap:
+                cap = n.value
+                continue
+            self._check(rc, "lsw_chain_subreads")
+            return out[:n.value]
 
     def fetch_hits_compact(self, n=None, out=None):
         """The hits of the last find_all as 16-byte records (HIT16_DT); expand_hits() turns them into HIT_DT."""

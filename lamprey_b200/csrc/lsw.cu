@@ -120,6 +120,7 @@ struct lsw_ctx {
     DevBuf d_blockbest, d_bb_off, d_bb1, d_bb1_off, d_nseg, d_segpos, d_res_s, d_seg_s, d_class_of, d_kt;
     int32_t allowed_overlap = -1;
     int64_t n_hits = 0;
+    bool hits_pruned = false;        // the sorted hits carry the survivor flag of lsw_set_overlap (lsw_chain_subreads needs it)
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -282,14 +283,34 @@ __global__ void k_pack_hits16(const lsw_hit* __restrict__ hits, int64_t n, uint4
 }
 
 // one thread per read: find the read's segment in the sorted hits and prune overlaps (lsw_set_overlap)
-__global__ void k_prune_overlaps(lsw_hit* __restrict__ hits, int64_t n_hits, int64_t n_reads, int32_t read_base, int allowed) {
+__device__ __forceinline__ void hit_range_of_read(const lsw_hit* __restrict__ hits, int64_t n_hits, int32_t rid, long long& lo, long long& e) {
+    lo = 0;
+    long long hi = n_hits;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (hits[mid].read < rid) lo = mid + 1; else hi = mid; }
+    e = lo;
+    long long eh = n_hits;
+    while (e < eh) { const long long mid = (e + eh) >> 1; if (hits[mid].read <= rid) e = mid + 1; else eh = mid; }
+}
+
+__global__ void k_prune_overlaps(lsw_hit* __restrict__ hits, int64_t n_hits, int64_t n_reads, int32_t read_base, int allowed,
+                                 const int32_t* __restrict__ qlen /* skbio path: identity = matches / len(primer); else null */) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t rid = (int32_t)i + read_base;
-        long long lo = 0, hi = n_hits;
-        while (lo < hi) { const long long mid = (lo + hi) >> 1; if (hits[mid].read < rid) lo = mid + 1; else hi = mid; }
-        long long e = lo, eh = n_hits;
-        while (e < eh) { const long long mid = (e + eh) >> 1; if (hits[mid].read <= rid) e = mid + 1; else eh = mid; }
-        prune_overlaps_read(hits, lo, e, allowed);
+        long long lo, e;
+        hit_range_of_read(hits, n_hits, (int32_t)i + read_base, lo, e);
+        prune_overlaps_read(hits, lo, e, allowed, qlen);
+    }
+}
+
+// stage 1 of processLamplicon (lsw_chain.cuh), one thread per read: pass 1 counts the targets of every read, pass 2 (after a
+// scan) writes the sub-reads
+__global__ void k_chain_subreads(const lsw_hit* __restrict__ hits, int64_t n_hits, int64_t n_reads, int32_t read_base,
+                                 const int32_t* __restrict__ rlen, ChainOrders C, int32_t* __restrict__ count,
+                                 const int32_t* __restrict__ pos, lsw_subread* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (int64_t)gridDim.x * blockDim.x) {
+        long long lo, e;
+        hit_range_of_read(hits, n_hits, (int32_t)i + read_base, lo, e);
+        if (!out) count[i] = chain_subreads_read(hits, lo, e, rlen[i], C, nullptr);
+        else chain_subreads_read(hits, lo, e, rlen[i], C, out + pos[i]);
     }
 }
 
@@ -898,7 +919,7 @@ int lsw_upload_reads(lsw_ctx* ctx, int64_t n, const uint8_t* ascii, const int64_
     if (n >= (1ll << 26)) return fail(ctx, LSW_E_ARG, "at most 2^26 - 1 reads per batch");
     CK(cudaSetDevice(ctx->device));
     // a failed upload leaves the context EMPTY (n_reads = 0), never describing the previous batch with the new lengths
-    ctx->n_reads = 0; ctx->total_bases = 0; ctx->n_hits = 0;
+    ctx->n_reads = 0; ctx->total_bases = 0; ctx->n_hits = 0; ctx->hits_pruned = false;
     // one pass over the offsets: lengths, padded size, and the block-best rows of lsw_reuse.cuh (BB_BLOCK columns per block,
     // BB_GROUP blocks per second-level entry)
     ctx->h_rlen.resize((size_t)n);
@@ -1206,7 +1227,8 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         cnt.other_launches += 3;
         if (ctx->allowed_overlap >= 0) {
             k_prune_overlaps<<<grid_for(ctx->n_reads, 128, ctx->num_sms * 8), 128, 0, ctx->stream>>>(
-                ctx->d_hits_sorted.as<lsw_hit>(), nh, ctx->n_reads, ctx->read_base, ctx->allowed_overlap);
+                ctx->d_hits_sorted.as<lsw_hit>(), nh, ctx->n_reads, ctx->read_base, ctx->allowed_overlap,
+                ctx->ssw ? ctx->d_qlen.as<int32_t>() : nullptr);
             CK(cudaGetLastError());
             cnt.other_launches += 1;
         }
@@ -1216,8 +1238,51 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     collect_times(ctx, &cnt);
     cnt.device_bytes = device_bytes(ctx);
     ctx->n_hits = nh;
+    ctx->hits_pruned = nh > 0 && ctx->allowed_overlap >= 0;
     if (n_hits) *n_hits = nh;
     if (counters) *counters = cnt;
+    return LSW_OK;
+}
+
+int lsw_chain_subreads(lsw_ctx* ctx, int n_fwd, const int32_t* fwd_order, int n_rev, const int32_t* rev_order, int t_query,
+                       int tc_query, lsw_subread* out, int64_t cap, int64_t* n_out) {
+    if (!ctx) return LSW_E_ARG;
+    if (n_out) *n_out = 0;
+    if (n_fwd < 1 || n_fwd > LSW_MAX_ORDER || n_rev < 1 || n_rev > LSW_MAX_ORDER || !fwd_order || !rev_order || cap < 0 || (cap > 0 && !out))
+        return fail(ctx, LSW_E_ARG, "lsw_chain_subreads: bad argument (1..16 names per primer order)");
+    ChainOrders C;
+    memset(&C, 0, sizeof C);
+    C.n_fwd = n_fwd; C.n_rev = n_rev; C.t_query = t_query; C.tc_query = tc_query; C.fwd_t = -1; C.rev_tc = -1;
+    for (int i = 0; i < n_fwd; i++) { C.fwd[i] = fwd_order[i]; if (fwd_order[i] == t_query && C.fwd_t < 0) C.fwd_t = i; }
+    for (int i = 0; i < n_rev; i++) { C.rev[i] = rev_order[i]; if (rev_order[i] == tc_query && C.rev_tc < 0) C.rev_tc = i; }
+    if (t_query < 0 || tc_query < 0 || C.fwd_t < 0 || C.rev_tc < 0)
+        return fail(ctx, LSW_E_ARG, "lsw_chain_subreads: 'T' must be in fwd_primer_order and 'Tc' in rev_primer_order (the reference raises ValueError)");
+    if (ctx->n_hits == 0 || ctx->n_reads == 0) return LSW_OK;
+    if (!ctx->hits_pruned) return fail(ctx, LSW_E_STATE, "lsw_chain_subreads needs the hits of an lsw_find_all that ran with lsw_set_overlap >= 0");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n_reads;
+    CK(ctx->d_nseg.ensure((size_t)(n + 1) * 4)); CK(ctx->d_segpos.ensure((size_t)(n + 1) * 4));
+    CK(cudaMemsetAsync(ctx->d_nseg.p, 0, (size_t)(n + 1) * 4, ctx->stream));
+    const int grid = grid_for(n, 128, ctx->num_sms * 8);
+    k_chain_subreads<<<grid, 128, 0, ctx->stream>>>(ctx->d_hits_sorted.as<lsw_hit>(), ctx->n_hits, n, ctx->read_base, ctx->d_rlen.as<int32_t>(), C,
+                                                    ctx->d_nseg.as<int32_t>(), nullptr, nullptr);
+    CK(cudaGetLastError());
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_nseg.as<int32_t>(), ctx->d_segpos.as<int32_t>(), (int)(n + 1), ctx->stream));
+    CK(ctx->d_cubtemp.ensure(tmp));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->d_cubtemp.p, tmp, ctx->d_nseg.as<int32_t>(), ctx->d_segpos.as<int32_t>(), (int)(n + 1), ctx->stream));
+    int32_t total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->d_segpos.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_out) *n_out = total;
+    if (total > cap) return fail(ctx, LSW_E_OVERFLOW, "lsw_chain_subreads: caller buffer too small; *n_out records are needed");
+    if (total == 0) return LSW_OK;
+    CK(ctx->d_res_s.ensure((size_t)total * sizeof(lsw_subread)));
+    k_chain_subreads<<<grid, 128, 0, ctx->stream>>>(ctx->d_hits_sorted.as<lsw_hit>(), ctx->n_hits, n, ctx->read_base, ctx->d_rlen.as<int32_t>(), C,
+                                                    nullptr, ctx->d_segpos.as<int32_t>(), reinterpret_cast<lsw_subread*>(ctx->d_res_s.p));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_res_s.p, (size_t)total * sizeof(lsw_subread), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return LSW_OK;
 }
 

@@ -541,4 +541,28 @@ int lsw_emu_ssw_align_tasks(int64_t n_reads, const uint8_t* ascii, const int64_t
     return LSW_OK;
 }
 
+
+// lsw_chain.cuh on the host: the sub-reads of stage 1 for hits that already carry the survivor flag
+int lsw_emu_chain_subreads(const lsw_hit* hits, int64_t n_hits, int64_t n_reads, const int32_t* rlen, int n_fwd, const int32_t* fwd_order,
+                           int n_rev, const int32_t* rev_order, int t_query, int tc_query, lsw_subread* out, int64_t cap, int64_t* n_out) {
+    ChainOrders C;
+    memset(&C, 0, sizeof C);
+    C.n_fwd = n_fwd; C.n_rev = n_rev; C.t_query = t_query; C.tc_query = tc_query; C.fwd_t = -1; C.rev_tc = -1;
+    for (int i = 0; i < n_fwd; i++) { C.fwd[i] = fwd_order[i]; if (fwd_order[i] == t_query && C.fwd_t < 0) C.fwd_t = i; }
+    for (int i = 0; i < n_rev; i++) { C.rev[i] = rev_order[i]; if (rev_order[i] == tc_query && C.rev_tc < 0) C.rev_tc = i; }
+    if (C.fwd_t < 0 || C.rev_tc < 0) return LSW_E_ARG;
+    int64_t total = 0, lo = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        while (lo < n_hits && hits[lo].read < r) lo++;
+        int64_t hi = lo;
+        while (hi < n_hits && hits[hi].read == r) hi++;
+        const int k = chain_subreads_read(hits, lo, hi, rlen[r], C, nullptr);
+        if (total + k <= cap) chain_subreads_read(hits, lo, hi, rlen[r], C, out + total);
+        total += k;
+        lo = hi;
+    }
+    if (n_out) *n_out = total;
+    return total > cap ? LSW_E_OVERFLOW : LSW_OK;
+}
+
 }  // extern "C"

@@ -37,6 +37,7 @@
 #include "lsw_common.cuh"
 #include "lsw_score.cuh"
 #include "../../include/lsw.h"
+#include "lsw_chain.cuh"
 
 namespace lsw {
 
@@ -604,26 +605,6 @@ struct TraceLane {
         }
     }
 };
-
-// removeOverlappingPrimerAlignments (/root/reference/lamprey.py:859-899) over one read's hits [lo, hi) in the
-// final (start, search order) order: a hit that starts more than `allowed` bases before the end of the current
-// survivor competes with it and the strictly higher identity (Python doubles: m / (m + x)) wins.  Survivors
-// get reserved = 1.
-LSW_HD void prune_overlaps_read(lsw_hit* hits, long long lo, long long hi, int allowed) {
-    if (lo >= hi) return;
-    long long cur = lo;
-    for (long long j = lo + 1; j < hi; j++) {
-        if (hits[j].start < hits[cur].end - allowed) {
-            const double ij = (double)hits[j].matches / (double)(hits[j].matches + hits[j].mismatches);
-            const double ic = (double)hits[cur].matches / (double)(hits[cur].matches + hits[cur].mismatches);
-            if (ij > ic) cur = j;
-        } else {
-            hits[cur].reserved = 1;
-            cur = j;
-        }
-    }
-    hits[cur].reserved = 1;
-}
 
 #if defined(__CUDACC__)
 

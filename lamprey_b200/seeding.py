@@ -122,6 +122,23 @@ class SeedBatch(object):
     def __len__(self):
         return len(self.offsets) - 1
 
+    subreads = None          # SUBREAD_DT array ordered by (read, target_idx), when seed_reads(..., subreads=True) asked for it
+    subread_offsets = None
+
+    def _set_subreads(self, sub):
+        self.subreads = sub
+        self.subread_offsets = np.searchsorted(sub["read"], np.arange(len(self) + 1)).astype(np.int64)
+
+    def target_subreads(self, i, lamp_idx=None):
+        """Stage 1 of processLamplicon for read i (lamprey.py:1566-1589): [(seq_start, seq_end, subread_id, direction)], computed
+        on the device (lsw_chain_subreads) -- what lamprey_b200.chain.target_subreads returns for the pruned hit list."""
+        if self.subreads is None:
+            raise ValueError("seed the batch with seed_reads(..., allowed_overlap=4, subreads=True)")
+        lo, hi = self.subread_offsets[i], self.subread_offsets[i + 1]
+        k = i if lamp_idx is None else lamp_idx
+        return [(int(x["start"]), int(x["end"]), "{}_{}".format(k, int(x["target_idx"])), 'fwd' if x["direction"] == 0 else 'rev')
+                for x in self.subreads[lo:hi]]
+
     @property
     def kept(self):
         """Mask of the hits that survive removeOverlappingPrimerAlignments (needs seed_reads(allowed_overlap=...))."""
@@ -141,6 +158,13 @@ class SeedBatch(object):
 
 
 _pools = {}
+
+
+def _device_subreads(eng, primer_set, names):
+    """extractAmpliconAroundTarget for every surviving target hit of the batch the engine just seeded (lsw_chain_subreads)."""
+    index = {n: k for k, n in enumerate(names)}
+    return eng.chain_subreads([index.get(n, -1) for n in primer_set.fwd_primer_order],
+                              [index.get(n, -1) for n in primer_set.rev_primer_order], index["T"], index["Tc"])
 
 
 def _scoring_of(aligner):
@@ -195,7 +219,7 @@ def _seed_on_pool(pool, concat, offs, hit_cap=None):
 
 
 def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None, devices=None,
-               compact=True, method=None, args=None):
+               compact=True, method=None, args=None, subreads=False):
     """findAllPrimerAlignments for every read of a batch in one device pass.  allowed_overlap (LAMPrey uses 4,
     lamprey.py:1536) also runs removeOverlappingPrimerAlignments on the device: see SeedBatch.kept.
 
@@ -220,10 +244,16 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
         eng.set_overlap(allowed_overlap)
         try:
             hits = eng.find_all(threshold)
+            sub = _device_subreads(eng, primer_set, names) if subreads else None
         finally:
             eng.set_overlap(None)
-        return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters,
-                         qlen=np.array([len(s) for _, s in pairs], np.int64))
+        batch = SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters,
+                          qlen=np.array([len(s) for _, s in pairs], np.int64))
+        if sub is not None:
+            batch._set_subreads(sub)
+        return batch
+    if subreads and (allowed_overlap is None or devices is not None):
+        raise ValueError("subreads=True needs allowed_overlap (LAMPrey uses 4) and a single device")
     if devices is not None:
         pool = get_pool(devices)
         sc = _scoring_of(aligner)
@@ -241,9 +271,13 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
     eng.set_overlap(allowed_overlap)
     try:
         hits = eng.find_all(threshold)
+        sub = _device_subreads(eng, primer_set, names) if subreads else None
     finally:
         eng.set_overlap(None)            # the engine is shared (swalign.get_engine): never leave the pruning switched on
-    return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters)
+    batch = SeedBatch(hits, len(offs) - 1, np.diff(offs), names, eng.last_counters)
+    if sub is not None:
+        batch._set_subreads(sub)
+    return batch
 
 
 def seed_stream(batches, primer_set, threshold, aligner=None, devices=(0,), allowed_overlap=None, compact=True, depth=2):

@@ -102,3 +102,31 @@ def test_pool_errors():
     pool.close()
     with pytest.raises(RuntimeError):
         _native.Pool([99])
+
+
+def test_device_subreads_and_processLamplicon_seed_stage():
+    # stage 1 of processLamplicon behind the batched call: device sub-reads == the host mirror of extractAmpliconAroundTarget
+    from lamprey_b200 import chain, pipeline
+    reads = load_reads("1k")
+    ps = seeding.PrimerSet(schema_path("H33"))
+    for kw in (dict(), dict(args=__import__("types").SimpleNamespace(swalign=False))):
+        seeds = pipeline.seed_batch(reads, ps, 0.70, **kw)
+        n_sub = 0
+        for i in range(len(reads)):
+            al = seeds.alignments(i, pruned=True)
+            want = chain.target_subreads(ps, al, len(reads[i]), i) if al else []
+            assert seeds.target_subreads(i) == want
+            n_sub += len(want)
+        assert n_sub == len(seeds.subreads) and n_sub > (500 if not kw else 50)
+        k = next(i for i in range(len(reads)) if len(seeds.target_subreads(i)) >= 2)
+        st = pipeline.processLamplicon_seed_stage(seeds, k, 7, reads[k], ps, 0.70)
+        assert st.target_depth == sum(1 for a in st.alignments if a.primer_name in ("T", "Tc")) == len(st.subread_slices)
+        sid, direction, sub = st.subread_slices[1]
+        s, e, d = st.alignment_interval_dict[sid]
+        assert sid == "7_1" and sub == reads[k][s:e] and d == direction
+    eng = _native.Engine(0)
+    eng.set_scoring(2, -1, -1, -1); eng.set_queries(_seqs("H33")); eng.upload_read_list(reads[:20])
+    eng.find_all(0.7)
+    with pytest.raises(ValueError):                       # the hits carry no survivor flags
+        eng.chain_subreads([0, 1], [1, 0], 0, 1)
+    eng.close()

@@ -84,3 +84,44 @@ def test_emu_overlap_pruning_matches_reference_function():
         want = chain.removeOverlappingPrimerAlignments(False, al, 4)
         got = [a for a, x in zip(al, h) if x["reserved"] == 1]
         assert [(a.start, a.end, a.primer_name) for a in got] == [(a.start, a.end, a.primer_name) for a in want]
+
+
+def test_emu_device_subreads_match_reference_functions():
+    # lsw_chain.cuh (the device's extractAmpliconAroundTarget / stage-1 loop) on the host against the host mirror and the oracle
+    import ctypes
+    import emu_lib
+    from lamprey_b200 import _native
+    reads = load_reads("50")
+    ps = seeding.PrimerSet(schema_path("H33"))
+    ps_r = seeding_ref.PrimerSet(schema_path("H33"))
+    names = [n for n, _ in ps.sequences()]
+    index = {n: k for k, n in enumerate(names)}
+    hits, _ = emu_lib.find_all(reads, [s for _, s in ps.sequences()], 0.70, allowed_overlap=4)
+    hits = np.ascontiguousarray(hits)
+    fo = np.array([index.get(n, -1) for n in ps.fwd_primer_order], np.int32)
+    ro = np.array([index.get(n, -1) for n in ps.rev_primer_order], np.int32)
+    rlen = np.array([len(r) for r in reads], np.int32)
+    out = np.zeros(4096, _native.SUBREAD_DT)
+    n = ctypes.c_int64(0)
+    lib = emu_lib.lib()
+    lib.lsw_emu_chain_subreads.restype = ctypes.c_int
+    rc = lib.lsw_emu_chain_subreads(emu_lib._ptr(hits), ctypes.c_int64(len(hits)), ctypes.c_int64(len(reads)), emu_lib._ptr(rlen),
+                                    ctypes.c_int(len(fo)), emu_lib._ptr(fo), ctypes.c_int(len(ro)), emu_lib._ptr(ro),
+                                    ctypes.c_int(index["T"]), ctypes.c_int(index["Tc"]), emu_lib._ptr(out), ctypes.c_int64(len(out)),
+                                    ctypes.byref(n))
+    assert rc == 0 and n.value > 20
+    got = out[:n.value]
+    k = 0
+    for i in range(len(reads)):
+        h = hits[(hits["read"] == i) & (hits["reserved"] == 1)]
+        al = [seeding.Alignment(int(x["start"]), int(x["end"]), x["matches"] / (x["matches"] + x["mismatches"]), names[x["query"]]) for x in h]
+        want = chain.target_subreads(ps, al, len(reads[i]), i)
+        al_r = [seeding_ref.Alignment(a.start, a.end, a.identity, a.primer_name) for a in al]
+        for a, w in zip([a for a in al_r if a.primer_name in ("T", "Tc")], want):
+            s, e = chain_ref.extract_amplicon_around_target(ps_r, al_r, a)
+            assert (s, len(reads[i]) - 1 if e == -1 else e) == w[:2]
+        mine = [(int(x["start"]), int(x["end"]), "%d_%d" % (i, x["target_idx"]), "fwd" if x["direction"] == 0 else "rev")
+                for x in got[k:k + len(want)]]
+        assert mine == want and all(x["read"] == i for x in got[k:k + len(want)])
+        k += len(want)
+    assert k == n.value
