@@ -101,6 +101,14 @@ typedef struct {
     int32_t hit;                   /* the target hit: index within the read's hits */
 } lsw_subread;
 
+/* One stage-2 alignment (lamprey.py:1637-1658): the QUERY is read[start:end) of the uploaded batch -- a candidate sub-read --
+ * reverse-complemented first if revcomp != 0 ('rev' targets, lamprey.py:1642-1643). */
+typedef struct {
+    int32_t read;
+    int32_t start, end;
+    int32_t revcomp;
+} lsw_pair;
+
 typedef struct {
     int64_t tasks;        /* align() invocations the reference would have made            */
     int64_t cells;        /* sum over those of len(slice) * len(query)  (the CUPS unit)   */
@@ -181,6 +189,13 @@ int lsw_set_overlap(lsw_ctx* ctx, int allowed_overlap);
  * the query indices of 'T' and 'Tc'.  Sub-reads come back ordered by (read, target_idx). */
 int lsw_chain_subreads(lsw_ctx* ctx, int n_fwd, const int32_t* fwd_order, int n_rev, const int32_t* rev_order, int t_query,
                        int tc_query, lsw_subread* out, int64_t cap, int64_t* n_out);
+/* Stage 2 of processLamplicon: StripedSmithWaterman(sub-read)(target_ref_str) for n sub-reads of the uploaded batch against ONE
+ * target reference (ASCII, target_len bases), with the scoring of lsw_set_ssw (skbio defaults if it was never called).  The
+ * query may be of any length.  Results as lsw_align_tasks returns them in SSW mode: r_pos / r_end on the TARGET (target_begin,
+ * target_end_optimal + 1; r_pos = -1: nothing aligned), q_pos / q_end on the sub-read (after the reverse complement), CIGAR
+ * runs with 'I' consuming the sub-read and 'D' the reference, as skbio prints them. */
+int lsw_ssw_subreads(lsw_ctx* ctx, int64_t n, const lsw_pair* pairs, const uint8_t* target, int32_t target_len, lsw_result* out,
+                     uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used);
 int lsw_set_hit_capacity(lsw_ctx* ctx, int64_t cap);   /* 0 = default (total bases / 8 + 4096) */
 int lsw_find_all(lsw_ctx* ctx, double identity_threshold, int64_t* n_hits, lsw_counters* counters);
 int lsw_fetch_hits(lsw_ctx* ctx, lsw_hit* out, int64_t cap, int64_t* n_out);

@@ -37,8 +37,9 @@ assert HIT16_DT.itemsize == 16
 # every symbol include/lsw.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",
            "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_overlap", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
-           "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_set_ssw", "lsw_chain_subreads", "lsw_host_alloc", "lsw_host_free",
+           "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_set_ssw", "lsw_chain_subreads", "lsw_ssw_subreads", "lsw_host_alloc", "lsw_host_free",
            "lsw_pool_create", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_pool_configure", "lsw_pool_submit", "lsw_pool_wait")
+PAIR_DT = np.dtype([("read", "<i4"), ("start", "<i4"), ("end", "<i4"), ("revcomp", "<i4")])
 SUBREAD_DT = np.dtype([("read", "<i4"), ("start", "<i4"), ("end", "<i4"), ("target_idx", "<i4"), ("direction", "<i4"), ("hit", "<i4")])
 HITS_WIDE, HITS_COMPACT = 0, 1
 POOL_TIMES_DT = np.dtype([("upload_s", "<f8"), ("find_s", "<f8"), ("fetch_s", "<f8"), ("gather_wait_s", "<f8"), ("total_s", "<f8"),
@@ -75,6 +76,7 @@ def load():
     lib.lsw_measure_int_peak.argtypes = [vp, i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_float)]
     lib.lsw_fetch_hits_compact.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_set_ssw.argtypes = [vp, i32, i32, i32, i32]
+    lib.lsw_ssw_subreads.argtypes = [vp, i64, vp, vp, i32, vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_chain_subreads.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_host_alloc.argtypes = [i64, ctypes.POINTER(vp)]
     lib.lsw_host_free.argtypes = [vp]
@@ -362,6 +364,24 @@ class Engine(object):
         got = ctypes.c_int64(0)
         self._check(self._lib.lsw_fetch_hits(self._h, _ptr(out), len(out), ctypes.byref(got)), "lsw_fetch_hits")
         return out[:got.value]
+
+    def ssw_subreads(self, pairs, target):
+        """Stage 2 of processLamplicon: StripedSmithWaterman(sub-read)(target) for PAIR_DT sub-reads of the uploaded batch.
+        -> (results RESULT_DT, cigar uint32[])."""
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DT)
+        t = np.frombuffer(target.encode("ascii") if isinstance(target, str) else bytes(target), dtype=np.uint8)
+        n = len(pairs)
+        out = np.zeros(n, RESULT_DT)
+        used = ctypes.c_int64(0)
+        cap = max(64, 16 * n)
+        while True:
+            cig = np.zeros(cap, np.uint32)
+            rc = self._lib.lsw_ssw_subreads(self._h, n, _ptr(pairs), _ptr(t), len(t), _ptr(out), _ptr(cig), cap, ctypes.byref(used))
+            if rc == LSW_E_OVERFLOW and used.value > cap:
+                cap = used.value
+                continue
+            self._check(rc, "lsw_ssw_subreads")
+            return out, cig[:used.value]
 
     def chain_subreads(self, fwd_order, rev_order, t_query, tc_query):
         """Stage 1 of processLamplicon for the last find_all (which must have run with set_overlap): SUBREAD_DT records."""

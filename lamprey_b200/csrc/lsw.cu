@@ -1244,6 +1244,84 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     return LSW_OK;
 }
 
+int lsw_ssw_subreads(lsw_ctx* ctx, int64_t n, const lsw_pair* pairs, const uint8_t* target, int32_t target_len, lsw_result* out,
+                     uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used) {
+    if (!ctx) return LSW_E_ARG;
+    if (cigar_used) *cigar_used = 0;
+    if (n < 0 || (n > 0 && (!pairs || !out)) || target_len < 0 || (target_len > 0 && !target))
+        return fail(ctx, LSW_E_ARG, "lsw_ssw_subreads: bad argument");
+    if (n == 0) return LSW_OK;
+    if (target_len > 30000) return fail(ctx, LSW_E_UNSUPPORTED, "lsw_ssw_subreads: target reference longer than 30000 bases");
+    int maxq = 1;
+    for (int64_t i = 0; i < n; i++) {
+        const lsw_pair& p = pairs[i];
+        if (p.read < 0 || p.read >= ctx->n_reads || p.start < 0 || p.end < p.start || p.end > ctx->h_rlen[p.read])
+            return fail(ctx, LSW_E_ARG, "lsw_ssw_subreads: sub-read out of range");
+        maxq = std::max(maxq, p.end - p.start);
+    }
+    CK(cudaSetDevice(ctx->device));
+    const int nslots = (int)std::min<int64_t>(((n + 127) / 128) * 128, 4096);
+    // banded_sw's direction bytes: (2 band + 1) x query span per sub-read; 256 KB holds a band of 64 over 2000 aligned bases
+    const long long dir_cap = 256 << 10;
+    DevBuf d_pairs, d_target, d_he, d_qbuf, d_dir;
+    auto release = [&]() { d_pairs.release(); d_target.release(); d_he.release(); d_qbuf.release(); d_dir.release(); };
+    std::vector<uint8_t> tcodes((size_t)std::max(target_len, 1));
+    for (int i = 0; i < target_len; i++) tcodes[i] = encode_base(target[i]);
+    cudaError_t e = cudaSuccess;
+    if ((e = d_pairs.ensure((size_t)n * sizeof(lsw_pair))) != cudaSuccess || (e = d_target.ensure(tcodes.size())) != cudaSuccess ||
+        (e = d_he.ensure((size_t)maxq * nslots * 4)) != cudaSuccess || (e = d_qbuf.ensure((size_t)maxq * nslots)) != cudaSuccess ||
+        (e = d_dir.ensure((size_t)dir_cap * nslots)) != cudaSuccess) {
+        release();
+        ctx->err = std::string("lsw_ssw_subreads: ") + cudaGetErrorString(e);
+        return LSW_E_CUDA;
+    }
+    int rc = LSW_OK;
+    unsigned long long h_ncig = 0;
+    int32_t h_err = 0;
+    do {
+#define CKB(call) if ((e = (call)) != cudaSuccess) { ctx->err = std::string("lsw_ssw_subreads: ") + cudaGetErrorString(e); rc = LSW_E_CUDA; break; }
+        CKB(ctx->d_results.ensure((size_t)n * sizeof(lsw_result)));
+        CKB(ctx->d_err.ensure(4)); CKB(ctx->d_ncigar.ensure(8));
+        const bool want_cigar = cigar_buf != nullptr && cigar_cap > 0;
+        if (want_cigar) CKB(ctx->d_cigar.ensure((size_t)cigar_cap * 4));
+        CKB(cudaMemsetAsync(ctx->d_err.p, 0, 4, ctx->stream));
+        CKB(cudaMemsetAsync(ctx->d_ncigar.p, 0, 8, ctx->stream));
+        CKB(cudaMemcpyAsync(d_pairs.p, pairs, (size_t)n * sizeof(lsw_pair), cudaMemcpyHostToDevice, ctx->stream));
+        CKB(cudaMemcpyAsync(d_target.p, tcodes.data(), tcodes.size(), cudaMemcpyHostToDevice, ctx->stream));
+        SswGenParams G;
+        memset(&G, 0, sizeof G);
+        G.codes = ctx->d_codes.as<uint8_t>(); G.roff = ctx->d_roff.as<int64_t>();
+        G.pairs = d_pairs.as<lsw_pair>(); G.n = n;
+        G.tcodes = d_target.as<uint8_t>(); G.tlen = target_len;
+        G.match = ctx->ssw_match; G.mismatch = ctx->ssw_mismatch; G.gap_open = ctx->ssw_open; G.gap_extend = ctx->ssw_extend;
+        G.he = d_he.as<uint32_t>(); G.qbuf = d_qbuf.as<uint8_t>(); G.qcap = maxq;
+        G.dir = d_dir.as<uint8_t>(); G.dir_cap = dir_cap;
+        G.results = ctx->d_results.as<lsw_result>();
+        G.cigar = want_cigar ? ctx->d_cigar.as<uint32_t>() : nullptr; G.cigar_cap = want_cigar ? cigar_cap : 0;
+        G.ncigar = ctx->d_ncigar.as<unsigned long long>();
+        G.errflag = ctx->d_err.as<int32_t>();
+        k_ssw_generic<<<nslots / 128, 128, 0, ctx->stream>>>(G, nslots);
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpyAsync(out, ctx->d_results.p, (size_t)n * sizeof(lsw_result), cudaMemcpyDeviceToHost, ctx->stream));
+        CKB(cudaMemcpyAsync(&h_ncig, ctx->d_ncigar.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CKB(cudaMemcpyAsync(&h_err, ctx->d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CKB(cudaStreamSynchronize(ctx->stream));
+        if (h_err) { rc = fail(ctx, LSW_E_UNSUPPORTED, "lsw_ssw_subreads: an alignment exceeded the band / path limits of the stage-2 kernel"); break; }
+        if (cigar_used) *cigar_used = (int64_t)h_ncig;
+        if (want_cigar) {
+            if ((int64_t)h_ncig > cigar_cap) { rc = fail(ctx, LSW_E_OVERFLOW, "cigar buffer too small; *cigar_used runs are needed"); break; }
+            if (h_ncig) {
+                CKB(cudaMemcpyAsync(cigar_buf, ctx->d_cigar.p, (size_t)h_ncig * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CKB(cudaStreamSynchronize(ctx->stream));
+            }
+        }
+#undef CKB
+    } while (0);
+    cudaStreamSynchronize(ctx->stream);
+    release();
+    return rc;
+}
+
 int lsw_chain_subreads(lsw_ctx* ctx, int n_fwd, const int32_t* fwd_order, int n_rev, const int32_t* rev_order, int t_query,
                        int tc_query, lsw_subread* out, int64_t cap, int64_t* n_out) {
     if (!ctx) return LSW_E_ARG;

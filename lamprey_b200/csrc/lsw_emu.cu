@@ -565,4 +565,40 @@ int lsw_emu_chain_subreads(const lsw_hit* hits, int64_t n_hits, int64_t n_reads,
     return total > cap ? LSW_E_OVERFLOW : LSW_OK;
 }
 
+
+// stage 2 (lsw_ssw.cuh ssw_generic_task) on the host, one sub-read at a time
+int lsw_emu_ssw_subreads(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int match, int mismatch, int gap_open,
+                         int gap_extend, int64_t n, const lsw_pair* pairs, const uint8_t* target, int32_t target_len,
+                         lsw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used) {
+    Emu E;
+    const uint8_t q1[1] = {'A'};
+    const int32_t qo[2] = {0, 1};
+    if (!setup(E, n_reads, ascii, offs, 1, q1, qo, 2, -1, -1)) return LSW_E_UNSUPPORTED;
+    int maxq = 1;
+    for (int64_t i = 0; i < n; i++) {
+        if (pairs[i].read < 0 || pairs[i].read >= n_reads || pairs[i].start < 0 || pairs[i].end < pairs[i].start ||
+            pairs[i].end > E.rlen[pairs[i].read]) return LSW_E_ARG;
+        maxq = std::max(maxq, pairs[i].end - pairs[i].start);
+    }
+    std::vector<uint8_t> tcodes((size_t)std::max(target_len, 1));
+    for (int i = 0; i < target_len; i++) tcodes[i] = encode_base(target[i]);
+    const long long dir_cap = 256 << 10;
+    std::vector<uint32_t> he((size_t)maxq);
+    std::vector<uint8_t> qbuf((size_t)maxq), dir((size_t)dir_cap);
+    unsigned long long ncig = 0;
+    int32_t errflag = 0;
+    SswGenParams G;
+    memset(&G, 0, sizeof G);
+    G.codes = E.codes.data(); G.roff = E.roff.data(); G.pairs = pairs; G.n = n; G.tcodes = tcodes.data(); G.tlen = target_len;
+    G.match = match; G.mismatch = mismatch; G.gap_open = gap_open; G.gap_extend = gap_extend;
+    G.he = he.data(); G.qbuf = qbuf.data(); G.qcap = maxq; G.dir = dir.data(); G.dir_cap = dir_cap;
+    G.results = out; G.cigar = cigar_buf; G.cigar_cap = cigar_buf ? cigar_cap : 0; G.ncigar = &ncig; G.errflag = &errflag;
+    for (int64_t k = 0; k < n; k++)
+        if (ssw_generic_task(G, k, 0, 1) != 1) errflag = 1;
+    if (errflag) return LSW_E_UNSUPPORTED;
+    if (cigar_used) *cigar_used = (int64_t)ncig;
+    if (cigar_buf && (int64_t)ncig > cigar_cap) return LSW_E_OVERFLOW;
+    return LSW_OK;
+}
+
 }  // extern "C"

@@ -48,11 +48,27 @@ struct SswParams {
     int32_t* errflag;
 };
 
-struct SswOut {
+template <int PW>
+struct PathBuf {                                             // 2 bits per op, in walk order (alignment end first)
+    int nops;
+    uint32_t ops[PW];
+    LSW_HD void clear() { nops = 0; for (int i = 0; i < PW; i++) ops[i] = 0; }
+    LSW_HD bool push(int op) {
+        if (nops >= PW * 16) return false;
+        ops[nops >> 4] |= (uint32_t)op << (2 * (nops & 15));
+        nops++;
+        return true;
+    }
+    LSW_HD int get(int i) const { return (int)((ops[i >> 4] >> (2 * (i & 15))) & 3u); }
+};
+
+template <int PW>
+struct SswOutT {
     int score, ref_begin, ref_end, read_begin, read_end;     // 0-based, inclusive (-1: nothing aligned)
     int matches, others, nrun;
-    PathOut po;                                              // ops in walk order (alignment end first)
+    PathBuf<PW> po;
 };
+using SswOut = SswOutT<MAX_PATH_WORDS>;                      // primer rows: a path has < 63 + 190 ops
 
 template <int NR>
 struct SswLane {
@@ -129,7 +145,8 @@ struct SswBand {
 
     LSW_HD static int xoff(int i, int w) { const int x = i - w; return x > 0 ? x : 0; }
 
-    LSW_HD static int run(const SswParams& P, const uint8_t* ref, const uint8_t* qc, SswOut& o, uint8_t* dir) {
+    template <class OUT>
+    LSW_HD static int run(const SswParams& P, const uint8_t* ref, const uint8_t* qc, OUT& o, uint8_t* dir, long long dir_cap = DIR_BYTES) {
         const int refLen = o.ref_end - o.ref_begin + 1, readLen = o.read_end - o.read_begin + 1;
         const uint8_t* rf = ref + o.ref_begin;
         const uint8_t* rd = qc + o.read_begin;
@@ -138,7 +155,7 @@ struct SswBand {
         int16_t h_b[WMAX], e_b[WMAX], h_c[WMAX];
         int width_d = 0, mx = 0;
         for (;;) {
-            if (band > BWMAX) return 0;
+            if (band > BWMAX || (long long)(band * 2 + 1) * readLen > dir_cap) return 0;
             const int width = band * 2 + 3;
             width_d = band * 2 + 1;
             for (int j = 0; j < width; j++) { h_b[j] = 0; e_b[j] = 0; h_c[j] = 0; }
@@ -149,7 +166,7 @@ struct SswBand {
                 const int edge = end + 1 < width - 1 ? end + 1 : width - 2;
                 int f = 0;
                 h_b[0] = 0; e_b[0] = 0; h_b[edge] = 0; e_b[edge] = 0; h_c[0] = 0;
-                uint8_t* line = dir + width_d * i;
+                uint8_t* line = dir + (long long)width_d * i;
                 const int x0 = xoff(i, band), x1 = xoff(i - 1, band);
                 const int qb = rd[i];
                 for (j = beg; j <= end; j++) {
@@ -187,7 +204,7 @@ struct SswBand {
         while (i > 0) {
             const int x = j - xoff(i, band);
             if (j < 0 || x < 0 || x >= width_d) return -1;
-            const int cell = dir[width_d * i + x];
+            const int cell = dir[(long long)width_d * i + x];
             const int code = state == 2 ? (cell >> 2) : state == 0 ? ((cell & 1) ? 3 : 2) : ((cell & 2) ? 5 : 4);
             int op;
             if (code == 1) { --i; --j; state = 2; op = OPC_M; }
@@ -292,10 +309,112 @@ LSW_HD int ssw_task(const SswParams& P, int t, uint8_t* dir) {
     return 1;
 }
 
+// ---- stage 2 of processLamplicon: StripedSmithWaterman(sub-read)(target reference) ---------------------------------------
+//   /root/reference/lamprey.py:1637-1658: every candidate sub-read (reverse-complemented for 'rev' targets) is the QUERY, the
+//   target reference string (279 / 627 bp for the shipped targets) the target.  A query of any length does not fit the register
+//   rows above: this path keeps (H, E) of every query row in a global scratch, laid out [row][thread] so that the threads of a
+//   warp, which walk the rows in step, touch consecutive words; the columns are the reference.  Same three steps, same rules.
+constexpr int SSWG_BW = 510;             // band limit (3 x 1024 int16 band rows in local memory)
+constexpr int SSWG_PATH_WORDS = 512;     // up to 8192 CIGAR columns
+
+struct SswGenParams {
+    const uint8_t* codes; const int64_t* roff;
+    const lsw_pair* pairs; int64_t n;
+    const uint8_t* tcodes; int32_t tlen;
+    int32_t match, mismatch, gap_open, gap_extend;
+    uint32_t* he;            // [row][slot]: H | E << 16 of the current column
+    uint8_t* qbuf;           // [slot][qcap]: the query's codes (reverse-complemented if asked)
+    int32_t qcap;
+    uint8_t* dir; long long dir_cap;     // [slot][dir_cap]
+    lsw_result* results; uint32_t* cigar; int64_t cigar_cap; unsigned long long* ncigar;
+    int32_t* errflag;
+};
+
+// One sub-read.  Returns 1 done, -1 band / path / scratch limits exceeded or an internal inconsistency (flagged, never guessed).
+LSW_HD int ssw_generic_task(const SswGenParams& G, int64_t k, int slot, int nslots) {
+    const lsw_pair pr = G.pairs[k];
+    const int Lq = pr.end - pr.start;
+    const uint8_t* src = G.codes + G.roff[pr.read] + pr.start;
+    uint8_t* qb = G.qbuf + (size_t)slot * G.qcap;
+    for (int q = 0; q < Lq; q++) {
+        const int c = pr.revcomp ? src[Lq - 1 - q] : src[q];
+        qb[q] = (uint8_t)((pr.revcomp && c < CODE_OTHER) ? 3 - c : c);      // A<->T, C<->G; anything else stays "N"
+    }
+    lsw_result* out = G.results + k;
+    out->score = 0; out->q_pos = 0; out->q_end = 0; out->r_pos = -1; out->r_end = 0; out->matches = 0; out->mismatches = 0;
+    out->n_cigar = 0; out->cigar_off = 0;
+    const int go = G.gap_open, ge = G.gap_extend;
+    uint32_t* he = G.he + slot;
+    auto scan = [&](int c0, int c1, int step, int r0 /* first row */, int rstep, int nrows, int stop, int& best, int& bref, int& bread) {
+        for (int q = 0; q < nrows; q++) he[(size_t)(r0 + q * rstep) * nslots] = 0u;
+        best = 0; bref = -1; bread = r0;
+        for (int c = c0; c != c1; c += step) {
+            const int tc = G.tcodes[c];
+            int diag = 0, F = 0, colmax = 0, colrow = r0;
+            for (int q = 0; q < nrows; q++) {
+                const int r = r0 + q * rstep;
+                const uint32_t v = he[(size_t)r * nslots];
+                const int hp = (int)(int16_t)(v & 0xFFFFu), E = (int)(int16_t)(v >> 16);
+                int h = diag + SswLane<16>::sub(qb[r], tc, G.match, G.mismatch);
+                h = h > 0 ? h : 0;
+                h = h > E ? h : E;
+                h = h > F ? h : F;
+                diag = hp;
+                if (h > colmax) { colmax = h; colrow = r; }
+                int hg = h - go; hg = hg > 0 ? hg : 0;
+                const int e = E - ge, f = F - ge;
+                const int en = e > hg ? e : hg;
+                F = f > hg ? f : hg;
+                he[(size_t)r * nslots] = ((uint32_t)h & 0xFFFFu) | ((uint32_t)en << 16);
+            }
+            if (colmax > best) { best = colmax; bref = c; bread = colrow; }
+            if (colmax == stop) break;
+        }
+    };
+    if (Lq <= 0 || G.tlen <= 0) return 1;
+    SswOutT<SSWG_PATH_WORDS> o;
+    o.matches = 0; o.others = 0; o.nrun = 0;
+    scan(0, G.tlen, 1, 0, 1, Lq, -1, o.score, o.ref_end, o.read_end);
+    out->score = o.score;
+    if (o.score <= 0 || o.score > 32000) return o.score > 32000 ? -1 : 1;
+    int best2;
+    scan(o.ref_end, -1, -1, o.read_end, -1, o.read_end + 1, o.score, best2, o.ref_begin, o.read_begin);
+    if (o.ref_begin < 0) return -1;
+    SswParams P;
+    P.match = G.match; P.mismatch = G.mismatch; P.gap_open = go; P.gap_extend = ge;
+    const int rc = SswBand<SSWG_BW>::run(P, G.tcodes, qb, o, G.dir + (size_t)slot * (size_t)G.dir_cap, G.dir_cap);
+    if (rc != 1) return -1;
+    out->q_pos = o.read_begin; out->q_end = o.read_end + 1;
+    out->r_pos = o.ref_begin; out->r_end = o.ref_end + 1;
+    out->matches = o.matches; out->mismatches = o.others; out->n_cigar = o.nrun;
+    if (G.cigar && o.nrun > 0) {
+        const long long off = (long long)atomic_add_ull(G.ncigar, (unsigned long long)o.nrun);
+        out->cigar_off = off;
+        if (off + o.nrun <= G.cigar_cap) {
+            int kk = 0, last = 0, cnt = 0;
+            for (int i = o.po.nops - 1; i >= 0; i--) {
+                const int op = o.po.get(i);
+                if (op != last) { if (last) G.cigar[off + kk++] = ((uint32_t)cnt << 2) | (uint32_t)last; last = op; cnt = 0; }
+                cnt++;
+            }
+            if (last) G.cigar[off + kk++] = ((uint32_t)cnt << 2) | (uint32_t)last;
+        }
+    }
+    return 1;
+}
+
 constexpr int SSW_THREADS = 128;
 constexpr int SSW_BW1 = 8, SSW_BW2 = 128;     // band limits of the two tiers (banded_sw doubles its band until the score is reproduced)
 
 #if defined(__CUDACC__)
+__global__ void __launch_bounds__(128)
+k_ssw_generic(const SswGenParams G, int nslots) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    for (int64_t k = slot; k < G.n; k += nslots)
+        if (ssw_generic_task(G, k, slot, nslots) != 1) *G.errflag = 1;
+}
+
 
 // Tier 1: one thread per task of the class, band up to SSW_BW1 (direction bytes in local memory).
 // Tier 2: the few tasks whose band grew further, band up to SSW_BW2 (direction bytes in a global scratch).

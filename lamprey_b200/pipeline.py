@@ -7,7 +7,7 @@ The reference's ``processLamplicon`` (/root/reference/lamprey.py:1521-1605) star
 prefix with the alignments coming from ``seeding.seed_reads(batch, ..., allowed_overlap=4, subreads=True)``: one device
 pass per FASTQ instead of ~65 align() calls per read.  Everything after it in the reference (minimap2, pysam, pileups,
 voting) is host / external-tool code and out of scope."""
-from . import seeding
+from . import seeding, skbio_ssw
 
 
 class SeedStage(object):
@@ -47,3 +47,24 @@ def processLamplicon_seed_stage(seeds, k, lamp_idx, lamplicon_seq, primers, thre
             interval_dict[subread_id] = (seq_start, seq_end, direction)
             slices.append((subread_id, direction, lamplicon_seq[seq_start:seq_end]))
     return SeedStage(alignments, alignment_coverage, target_depth, num_ont_seqs, intervals, interval_dict, slices)
+
+
+cigarOpMap = {'M': 0, 'I': 1, 'D': 2}          # the pysam codes LAMPrey's cigarStringToTuples produces (lamprey.py:527-545)
+
+
+def stage2_align_batch(reads, seeds, target_ref_str, device=0):
+    """Stage 2 of processLamplicon for a whole seeded batch (lamprey.py:1637-1669): every candidate sub-read of every read --
+    seeds.subreads, from seed_batch() -- against the target reference, in one device pass.  -> one dict per sub-read, in
+    seeds.subreads order, with what the reference puts into its pysam.AlignedSegment: query_name parts, reference_start
+    (target_begin), cigar string and pysam tuples, and query_sequence (aligned_query_sequence without '-')."""
+    sub = seeds.subreads
+    pairs = [(int(x["read"]), int(x["start"]), int(x["end"]), int(x["direction"])) for x in sub]
+    als = skbio_ssw.align_subreads(reads, pairs, target_ref_str, device=device)
+    out = []
+    for x, a in zip(sub, als):
+        out.append({"read": int(x["read"]), "target_idx": int(x["target_idx"]), "direction": 'fwd' if x["direction"] == 0 else 'rev',
+                    "reference_start": a.target_begin, "cigar": a.cigar,
+                    "cigartuples": [(cigarOpMap[op], n) for n, op in a._runs],
+                    "query_sequence": a.aligned_query_sequence.replace('-', '') if a.target_begin >= 0 else "",
+                    "score": a.optimal_alignment_score})
+    return out

@@ -7,9 +7,10 @@ aligned_target_sequence`` (zero-based, inclusive ends: skbio's defaults).  Only 
 (gap_open 5, gap_extend 2, match 2, mismatch -3, nucleotides); other keyword values raise NotImplementedError rather than
 silently differ.  The arithmetic runs in liblsw.so (lsw_set_ssw + lsw_align_tasks); nothing here aligns on the CPU.
 
-The engine keeps all rows of the QUERY in registers, so a query may be at most 63 bases: the seeding call (query = primer)
-fits; LAMPrey's stage-2 call (query = a whole sub-read, lamprey.py:1643-1647) does not and raises ValueError.
-``align_many`` is the batched form."""
+Two device paths sit behind the one class: a query of at most 63 bases (the seeding call: query = primer) runs on the
+register-row kernel; a longer query (LAMPrey's stage-2 call: query = a whole sub-read against the target reference,
+lamprey.py:1643-1647) runs on the stage-2 kernel (``lsw_ssw_subreads``).  ``align_many`` and ``align_subreads`` are the
+batched forms."""
 import numpy as np
 
 from . import _native
@@ -93,4 +94,35 @@ class StripedSmithWaterman(object):
         self.device = device
 
     def __call__(self, target_sequence):
+        if len(self.query_sequence) > _native.MAX_QUERY_LEN:
+            n = len(self.query_sequence)
+            return align_subreads([self.query_sequence], [(0, 0, n, 0)], str(target_sequence), device=self.device)[0]
         return align_many([self.query_sequence], [str(target_sequence)], device=self.device)[0]
+
+
+_COMP = {'A': 'T', 'C': 'G', 'G': 'C', 'T': 'A'}
+
+
+def align_subreads(reads, pairs, target, device=0, engine=None):
+    """Batched stage 2 of processLamplicon (lamprey.py:1637-1658): for every (read, start, end, revcomp) row, the sub-read
+    read[start:end] -- reverse-complemented if revcomp -- is the QUERY of StripedSmithWaterman, `target` (the target reference
+    string) the target.  reads: list of str, or None to use the batch already uploaded to `engine` (then the AlignmentStructure
+    objects carry no sequences).  -> list of AlignmentStructure."""
+    from . import swalign as _sw
+    eng = engine or _sw.get_engine(device)
+    if reads is not None:
+        reads = [str(r) for r in reads]
+        eng.upload_read_list(reads)
+    p = np.zeros(len(pairs), _native.PAIR_DT)
+    for k, row in enumerate(pairs):
+        p[k] = tuple(int(v) for v in row)
+    res, cig = eng.ssw_subreads(p, target)
+    out = []
+    for r, row in zip(res, p):
+        q = ""
+        if reads is not None:
+            q = reads[row["read"]][row["start"]:row["end"]]
+            if row["revcomp"]:
+                q = ''.join(_COMP.get(b, b) for b in reversed(q))
+        out.append(AlignmentStructure(r, cig[r["cigar_off"]:r["cigar_off"] + r["n_cigar"]], q, str(target)))
+    return out

@@ -93,3 +93,22 @@ def ssw_align_tasks(reads, seqs, tasks, match=2, mismatch=-3, gap_open=5, gap_ex
     if rc:
         raise RuntimeError("lsw_emu_ssw_align_tasks rc=%d" % rc)
     return out, cig[:used.value]
+
+
+def ssw_subreads(reads, pairs, target, match=2, mismatch=-3, gap_open=5, gap_extend=2):
+    """Stage 2 (query = sub-read of any length, target = reference) through the host emulation of ssw_generic_task."""
+    from lamprey_b200._native import PAIR_DT
+    rc_, ro = concat_sequences(reads)
+    pairs = np.ascontiguousarray(pairs, dtype=PAIR_DT)
+    t = np.frombuffer(target.encode(), np.uint8)
+    out = np.zeros(len(pairs), RESULT_DT)
+    cap = max(64, 16 * len(pairs) + 4 * int(sum(p["end"] - p["start"] for p in pairs)))
+    cig = np.zeros(cap, np.uint32)
+    used = ctypes.c_int64(0)
+    lib().lsw_emu_ssw_subreads.restype = ctypes.c_int
+    rc = lib().lsw_emu_ssw_subreads(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(match), ctypes.c_int(mismatch),
+                                    ctypes.c_int(gap_open), ctypes.c_int(gap_extend), ctypes.c_int64(len(pairs)), _ptr(pairs), _ptr(t),
+                                    ctypes.c_int(len(t)), _ptr(out), _ptr(cig), ctypes.c_int64(cap), ctypes.byref(used))
+    if rc:
+        raise RuntimeError("lsw_emu_ssw_subreads rc=%d" % rc)
+    return out, cig[:used.value]

@@ -158,3 +158,32 @@ def test_ssw_synthetic_concatemers_vs_oracle(engine):
     assert np.array_equal(ssw_matrix(batch.hits), np.array(rows, np.int32).reshape(-1, 9)) and len(rows) > 2000
     k = len(rows) // 2
     assert batch.identity[k] == rows[k][4] / len(seqs[rows[k][1]])
+
+
+def test_stage2_subreads_against_the_target_reference(engine):
+    # lamprey.py:1637-1669 behind one batched call: seeds -> device sub-reads -> every sub-read (rc for 'rev') against the target
+    # reference, compared with the oracle alignment of the same strings
+    from lamprey_b200 import pipeline
+    reads = load_reads("1k")[:300]
+    ps = seeding.PrimerSet(schema_path("H33"))
+    ref = open(os.path.join(GOLD, "H3F3A.fa")).read().split("\n", 1)[1].replace("\n", "").upper()
+    seeds = pipeline.seed_batch(reads, ps, 0.70)
+    recs = pipeline.stage2_align_batch(reads, seeds, ref)
+    assert len(recs) == len(seeds.subreads) > 150
+    for x, rec in zip(seeds.subreads, recs):
+        q = reads[x["read"]][x["start"]:x["end"]]
+        if x["direction"] == 1:
+            q = seeding.rc(q)
+        a = ssw_oracle.StripedSmithWaterman(q)(ref)
+        if a.optimal_alignment_score == 0:
+            assert rec["score"] == 0 and rec["reference_start"] == -1
+            continue
+        assert (rec["score"], rec["reference_start"], rec["cigar"]) == (a.optimal_alignment_score, a.target_begin, a.cigar)
+        assert rec["query_sequence"] == a.aligned_query_sequence.replace('-', '')
+    # the drop-in class takes the same path for a long query
+    q = reads[5][:700]
+    a = skbio_ssw.StripedSmithWaterman(q)(ref)
+    b = ssw_oracle.StripedSmithWaterman(q)(ref)
+    assert (a.optimal_alignment_score, a.target_begin, a.target_end_optimal, a.query_begin, a.query_end, a.cigar) == \
+           (b.optimal_alignment_score, b.target_begin, b.target_end_optimal, b.query_begin, b.query_end, b.cigar)
+    assert a.aligned_query_sequence == b.aligned_query_sequence and a.aligned_target_sequence == b.aligned_target_sequence

@@ -149,3 +149,38 @@ def test_restated_alignSequence_skbio_and_recursion_agree():
             rec(r, 0, 0)
         h, _ = ssw_oracle.find_all(r, [s for _, s in ps.sequences()], 0.75)
         assert [(int(x["seq"]), int(x["start"]), int(x["end"])) for x in h] == py
+
+
+def test_emu_stage2_subreads_vs_oracle():
+    # stage 2 (lamprey.py:1637-1658): the sub-read, any length, reverse-complemented for 'rev' targets, is the QUERY and the target
+    # reference the target
+    from lamprey_b200._native import PAIR_DT
+    from lamprey_b200 import seeding
+    rng = random.Random(9)
+    refs = {}
+    for fn in ("H3F3A.fa", "HIST1H3B.fa"):
+        refs[fn] = open(os.path.join(GOLD, fn)).read().split("\n", 1)[1].replace("\n", "").upper()
+    reads = load_reads("50")[:16] + ["ACGT" * 30, "A" * 50, "", "NNNNACGTTGCANNN"]
+    pairs = []
+    for i, r in enumerate(reads):
+        pairs.append((i, 0, len(r), 0))
+        for _ in range(2):
+            a = rng.randrange(0, max(1, len(r) - 40))
+            pairs.append((i, a, min(len(r), a + rng.randrange(20, 1200)), rng.randrange(2)))
+    pairs = np.array(pairs, dtype=PAIR_DT)
+    for fn, ref in refs.items():
+        res, cig = emu_lib.ssw_subreads(reads, pairs, ref)
+        n_aligned = 0
+        for p, r in zip(pairs, res):
+            q = reads[p["read"]][p["start"]:p["end"]]
+            if p["revcomp"]:
+                q = seeding.rc(q)
+            d = ssw_oracle.align(ref, q)
+            if d["score"] == 0:
+                assert r["score"] == 0 and r["r_pos"] == -1
+                continue
+            n_aligned += 1
+            got = (r["score"], r["r_pos"], r["r_end"] - 1, r["q_pos"], r["q_end"] - 1, r["matches"],
+                   [(int(c >> 2), _OPS[int(c & 3)]) for c in cig[r["cigar_off"]:r["cigar_off"] + r["n_cigar"]]])
+            assert got == (d["score"], d["ref_begin"], d["ref_end"], d["read_begin"], d["read_end"], d["matches"], d["cigar"])
+        assert n_aligned > 40
