@@ -174,6 +174,13 @@ class ClockSampler(threading.Thread):
 
 
 _JSON_FD = None
+_T0 = time.time()
+
+
+def log(msg):
+    """Progress on stderr (stdout carries the JSON line only)."""
+    sys.stderr.write("[bench %6.1fs rank %s] %s\n" % (time.time() - _T0, os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
 
 
 def emit(line):
@@ -318,6 +325,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-batch strong-scaling leg")
     ap.add_argument("--extra-reads-5kb", type=int, default=400000)
     ap.add_argument("--extra-reads-long", type=int, default=100000)
+    ap.add_argument("--skbio-reads", type=int, default=100000, help="reads of the headline batch seeded on the skbio path (extra config)")
     ap.add_argument("--e2e-depth", type=int, default=2, help="contexts per device of the pool (batches in flight)")
     args = ap.parse_args()
     # stdout carries the one JSON line and nothing else: libraries that print to fd 1 (NCCL's version
@@ -368,13 +376,18 @@ def main():
             cpu_ref = {"n": sample, "py_hits": None, "calls": None, "cells": None}
         cpu_ref["c_rows"] = c_oracle_rows(reads, seqs, args.thr, workers if world > 1 else cores)
 
+    log("inputs generated, CPU legs done")
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a second, CPU-side group: ranks that wait while rank 0 drives all GPUs (strong-scaling leg) must not spin a NCCL kernel on
+        # the very GPUs being measured
+        cpu_group = dist.new_group(backend="gloo")
     from lamprey_b200 import _native
 
     eng = _native.Engine(local_rank)
@@ -412,6 +425,7 @@ def main():
     t_value, reads_total, cells_total, hits_total = gather_max_and_sum(
         t_value, [args.reads * args.steps, cnt["cells"] * args.steps, n_hits * args.steps])
 
+    log("value leg done: %.1f ms/step" % (1e3 * t_value / args.steps))
     # parity against the CPU sample (same reads, same threshold): every hit, field by field
     parity = None
     if cpu_ref is not None:
@@ -457,9 +471,26 @@ def main():
                           "roofline": {"bound": "int_alu", "achieved": k1["all"], "peak": pk, "unit": "GCUPS",
                                        "frac": k1["all"] / pk if (pk and k1["all"]) else None, "k1_gcups": k1},
                           "device_bytes": c_x["device_bytes"], "reuse_dropped": c_x["reuse_dropped"], "clocks": clk_x})
+    # the DEFAULT seeding path (scikit-bio StripedSmithWaterman semantics, lamprey.py:572-593) on a slice of the headline batch
+    if not args.no_extra:
+        n_sk = min(args.reads, args.skbio_reads)
+        eng.set_queries(seqs)
+        eng.set_ssw(2, -3, 5, 2)
+        eng.upload_reads(ascii_np[:offs_np[n_sk]], offs_np[:n_sk + 1])
+        xs = max(2, min(args.steps, 3))
+        t_x, c_x, a_x, clk_x, h_x = timed_find_all(eng, torch, stream, args.thr, xs, 3, barrier, local_rank if rank == 0 else None)
+        t_x, r_x, cells_x = gather_max_and_sum(t_x, [n_sk * xs, c_x["cells"] * xs])
+        if rank == 0:
+            extra.append({"workload": args.workload, "path": "skbio (StripedSmithWaterman semantics: lsw_set_ssw, lsw_ssw.cuh)",
+                          "reads_per_gpu": n_sk, "n_gpus": world, "steps": xs, "warmup": 3, "value": r_x / t_x, "unit": "reads/s",
+                          "ms_per_step": 1e3 * t_x / xs, "gcups": cells_x / t_x / 1e9, "tasks_per_step": c_x["tasks"],
+                          "hits_per_step": h_x, "rounds": c_x["rounds"], "clocks": clk_x,
+                          "note": "first CUDA version of this row: one thread per task, scalar int32 cells, no reuse of round 0"})
+        eng.set_scoring(2, -1, -1, -1)
     del extra_reads
     eng.set_queries(seqs)
     eng.close()
+    log("extra configs done")
 
     # ---- e2e: host buffers in, hits on the host out, every step, through the library's pool --------------------
     # lsw_pool_submit / lsw_pool_wait (include/lsw.h): the pool's worker threads run lsw_upload_reads -> lsw_find_all ->
@@ -521,9 +552,16 @@ def main():
     # ---- strong scaling: ONE fixed batch (rank 0's) over all N GPUs, host-side gather included --------------------
     # The product path for several GPUs is one process with one thread + context per GPU (seeding.seed_reads(devices=...),
     # lsw_pool_*): rank 0 drives all N GPUs while the other ranks, whose engines are closed, wait at the barrier.
+    log("e2e leg done")
+
+    def cpu_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier(group=cpu_group)
+
     strong = None
     if not args.no_strong:
-        barrier()
+        cpu_barrier()
         if rank == 0:
             ndev = min(world, torch.cuda.device_count())
             pool = _native.Pool(list(range(ndev)), 2)
@@ -559,7 +597,8 @@ def main():
             pool.close()
             for o in outs:
                 o.close()
-        barrier()
+        cpu_barrier()
+    log("strong-scaling leg done")
 
     if rank == 0:
         gcups = cells_total / t_value / 1e9
