@@ -1260,9 +1260,15 @@ int lsw_ssw_subreads(lsw_ctx* ctx, int64_t n, const lsw_pair* pairs, const uint8
         maxq = std::max(maxq, p.end - p.start);
     }
     CK(cudaSetDevice(ctx->device));
-    const int nslots = (int)std::min<int64_t>(((n + 127) / 128) * 128, 4096);
-    // banded_sw's direction bytes: (2 band + 1) x query span per sub-read; 256 KB holds a band of 64 over 2000 aligned bases
-    const long long dir_cap = 256 << 10;
+    // banded_sw's direction bytes: (2 band + 1) x query span per sub-read.  An aligned query span cannot exceed the target by
+    // more than the insertions its score pays for, so 4 x target rows at a band of 64 covers what real data produces; beyond that
+    // the call reports LSW_E_UNSUPPORTED, never a guess.  One thread per sub-read in flight: as many as ~2 GB of scratch allow.
+    const long long rows_cap = std::min<long long>(maxq, 4ll * target_len + 64);
+    const long long dir_cap = std::min<long long>(std::max<long long>(129 * rows_cap, 16 << 10), 1 << 20);
+    const long long per_slot = dir_cap + 5ll * maxq;
+    long long slots = std::min<long long>(32768, (2ll << 30) / per_slot);
+    slots = std::max<long long>(128, std::min<long long>(slots, ((n + 127) / 128) * 128));
+    const int nslots = (int)((slots / 128) * 128);
     DevBuf d_pairs, d_target, d_he, d_qbuf, d_dir;
     auto release = [&]() { d_pairs.release(); d_target.release(); d_he.release(); d_qbuf.release(); d_dir.release(); };
     std::vector<uint8_t> tcodes((size_t)std::max(target_len, 1));

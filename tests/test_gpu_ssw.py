@@ -49,8 +49,11 @@ def test_skbio_documentation_example_through_the_dropin_class():
     assert a.aligned_query_sequence == "ACTAAGGCTCTCTACCCCTC-TCAGAGA" and a.aligned_target_sequence == "ACTAAGGCTCTCTACCCCTCTTCAGAGA"
     with pytest.raises(NotImplementedError):
         skbio_ssw.StripedSmithWaterman("ACGT", gap_open_penalty=3)
-    with pytest.raises(ValueError):
-        skbio_ssw.StripedSmithWaterman("ACGT" * 20)("ACGT" * 30)       # a query longer than the register rows
+    long_q = "ACGTTGCA" * 12                                            # longer than the register rows: the stage-2 kernel takes it
+    b = skbio_ssw.StripedSmithWaterman(long_q)("TT" + long_q[:50] + "G" + long_q[50:] + "AA")
+    w = ssw_oracle.StripedSmithWaterman(long_q)("TT" + long_q[:50] + "G" + long_q[50:] + "AA")
+    assert (b.optimal_alignment_score, b.target_begin, b.target_end_optimal, b.cigar) == \
+           (w.optimal_alignment_score, w.target_begin, w.target_end_optimal, w.cigar)
     # the module boundary of lamprey.py:14-17: ./lib first on sys.path, then `from skbio.alignment import StripedSmithWaterman`
     sys.path.insert(0, os.path.join(ROOT, "lib"))
     try:
