@@ -28,6 +28,7 @@
 #include "lsw_band.cuh"
 #include "lsw_reuse.cuh"
 #include "lsw_ssw.cuh"
+#include "lsw_affine.cuh"
 #include "intpeak.cuh"
 #include "lsw_host.hpp"
 
@@ -686,8 +687,20 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
 }
 
 template <int NR>
-int launch_ssw(lsw_ctx* ctx, SswParams P, int64_t n_class_tasks) {
-    // tier 1: one thread per task, band <= SSW_BW1 in local memory
+int launch_ssw(lsw_ctx* ctx, SswParams P, int64_t n_class_tasks, const ScoreParams* K1) {
+    if (K1) {
+        // K1: the forward scan of every task of the class with packed DPX instructions (lsw_affine.cuh); it queues the tasks
+        // that need the rest (reverse scan, banded traceback) as candidates
+        const size_t smem = score_smem_bytes<NR>();
+        CK(cudaFuncSetAttribute(k_score_affine<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_affine<NR>, SCORE_WARPS * 32, smem));
+        if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "affine score kernel does not fit on an SM");
+        const int blocks1 = grid_for((n_class_tasks + 1) / 2, SCORE_WARPS * 32, ctx->num_sms * occ);
+        k_score_affine<NR><<<blocks1, SCORE_WARPS * 32, smem, ctx->stream>>>(*K1);
+        CK(cudaGetLastError());
+    }
+    // tier 1: one thread per task (or per candidate of K1), band <= SSW_BW1 in local memory
     const int blocks = grid_for(n_class_tasks, SSW_THREADS, ctx->num_sms * 16);
     k_ssw_round<NR, SSW_BW1><<<blocks, SSW_THREADS, 0, ctx->stream>>>(P, nullptr);
     CK(cudaGetLastError());
@@ -702,23 +715,24 @@ int launch_ssw(lsw_ctx* ctx, SswParams P, int64_t n_class_tasks) {
     return LSW_OK;
 }
 
-int launch_ssw_class(lsw_ctx* ctx, int c, const SswParams& P, int64_t n) {
+int launch_ssw_class(lsw_ctx* ctx, int c, const SswParams& P, int64_t n, const ScoreParams* K1) {
     switch (CLASS_NR[c]) {
-        case 16: return launch_ssw<16>(ctx, P, n);
-        case 20: return launch_ssw<20>(ctx, P, n);
-        case 24: return launch_ssw<24>(ctx, P, n);
-        case 28: return launch_ssw<28>(ctx, P, n);
-        case 32: return launch_ssw<32>(ctx, P, n);
-        case 40: return launch_ssw<40>(ctx, P, n);
-        case 48: return launch_ssw<48>(ctx, P, n);
-        case 56: return launch_ssw<56>(ctx, P, n);
-        default: return launch_ssw<64>(ctx, P, n);
+        case 16: return launch_ssw<16>(ctx, P, n, K1);
+        case 20: return launch_ssw<20>(ctx, P, n, K1);
+        case 24: return launch_ssw<24>(ctx, P, n, K1);
+        case 28: return launch_ssw<28>(ctx, P, n, K1);
+        case 32: return launch_ssw<32>(ctx, P, n, K1);
+        case 40: return launch_ssw<40>(ctx, P, n, K1);
+        case 48: return launch_ssw<48>(ctx, P, n, K1);
+        case 56: return launch_ssw<56>(ctx, P, n, K1);
+        default: return launch_ssw<64>(ctx, P, n, K1);
     }
 }
 
-// One recursion round of the default (skbio / SSW) seeding path: per register-row class one fused launch (forward scan,
-// reverse scan, banded traceback, hit test, children) and its second band tier.
-int run_round_ssw(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int64_t>& h_seg, SswParams P, lsw_counters* cnt) {
+// One recursion round of the default (skbio / SSW) seeding path.  Per register-row class: K1 (packed forward scan, when the
+// scores fit its 8.8 cells: match * len(primer) <= 127) and the per-task kernel that finishes the alignment (reverse scan,
+// banded traceback, hit test, children) in two band tiers; without K1 the per-task kernel does the forward scan itself.
+int run_round_ssw(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int64_t>& h_seg, int64_t n, SswParams P, lsw_counters* cnt) {
     CK(ctx->d_nfallback.ensure(NCLASS * 8));
     CK(cudaMemsetAsync(ctx->d_nfallback.p, 0, NCLASS * 8, ctx->stream));
     CK(ctx->d_fb2cnt.ensure((size_t)std::max(ctx->nseq, 1) * 8));
@@ -730,6 +744,26 @@ int run_round_ssw(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<
     P.match = ctx->ssw_match; P.mismatch = ctx->ssw_mismatch; P.gap_open = ctx->ssw_open; P.gap_extend = ctx->ssw_extend;
     P.counters = ctx->d_counters.as<unsigned long long>();
     P.errflag = ctx->d_err.as<int32_t>();
+    bool packed = !getenv("LSW_SSW_SCALAR");
+    for (int s = 0; s < ctx->nseq; s++) if (ctx->ssw_match * ctx->qlen[s] > 127) packed = false;
+    ScoreParams K1;
+    if (packed) {
+        CK(ctx->d_res.ensure((size_t)n * sizeof(int2)));
+        CK(ctx->d_head.ensure((size_t)ctx->nseq * 8));
+        CK(ctx->d_ncand.ensure(NCLASS * 8));
+        CK(cudaMemsetAsync(ctx->d_head.p, 0, (size_t)ctx->nseq * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_ncand.p, 0, NCLASS * 8, ctx->stream));
+        CK(ctx->d_kt.ensure((size_t)n * sizeof(KTask)));
+        k_make_ktasks<<<grid_for(n, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(cur.view(), ctx->d_roff.as<int64_t>(), ctx->d_kt.as<KTask>(), n);
+        CK(cudaGetLastError());
+        if (cnt) cnt->other_launches++;
+        fill_score_params(ctx, K1, cur, segi);
+        K1.kt = ctx->d_kt.as<KTask>();
+        K1.s_match = SC * ctx->ssw_match; K1.s_mis = SC * ctx->ssw_mismatch;
+        K1.aff_open = ctx->ssw_open; K1.aff_extend = ctx->ssw_extend;
+        K1.push_cands = 1; K1.count_ref = 1; K1.block_steps = BLOCK_STEPS;
+        P.res = ctx->d_res.as<int2>();
+    }
     Span sp(ctx, (P.mode == 0 && P.round == 0) ? 4 : 0);
     for (int c = 0; c < NCLASS; c++) {
         int64_t ncls = 0;
@@ -740,8 +774,17 @@ int run_round_ssw(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<
         P.n_class_seqs = (int)ctx->class_seqs[c].size();
         P.fallback = ctx->d_fallback[c].as<uint32_t>();
         P.nfallback = ctx->d_nfallback.as<unsigned long long>() + c;
-        if (int rc = launch_ssw_class(ctx, c, P, ncls)) return rc;
-        if (cnt) cnt->score_launches += 2;
+        if (packed) {
+            CK(ctx->d_cand[c].ensure((size_t)ncls * 4)); CK(ctx->d_cand_key[c].ensure((size_t)ncls * 2));
+            CK(ctx->d_cand_rec[c].ensure((size_t)ncls * sizeof(CandRec)));
+            K1.class_seqs = P.class_seqs; K1.n_class_seqs = P.n_class_seqs;
+            K1.cand = ctx->d_cand[c].as<uint32_t>(); K1.cand_key = ctx->d_cand_key[c].as<uint16_t>();
+            K1.cand_rec = ctx->d_cand_rec[c].as<CandRec>();
+            K1.ncand = ctx->d_ncand.as<unsigned long long>() + c;
+            P.cand_rec = K1.cand_rec; P.ncand = K1.ncand;
+        }
+        if (int rc = launch_ssw_class(ctx, c, P, ncls, packed ? &K1 : nullptr)) return rc;
+        if (cnt) { cnt->score_launches += packed ? 1 : 0; cnt->trace_launches += 2; }
     }
     return LSW_OK;
 }
@@ -1039,6 +1082,10 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     if (n0 == 0) { if (counters) *counters = cnt; return LSW_OK; }
 
     std::vector<uint8_t> tab;
+    if (ctx->ssw) {      // K1 of the skbio path queues every task with a positive score (the per-task kernel applies the hit test)
+        tab.assign((size_t)ctx->nseq * 128, 1);
+        for (int s = 0; s < ctx->nseq; s++) tab[(size_t)s * 128] = 0;
+    } else
     build_cand_ok(ctx->nseq, ctx->qlen.data(), ctx->match, ctx->mismatch, ctx->g, thr, false, tab);
     CK(ctx->d_cand_ok.ensure(tab.size()));
     CK(cudaMemcpyAsync(ctx->d_cand_ok.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1107,7 +1154,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
             S.mode = 0; S.thr = thr; S.round = round;
             S.hits = T.hits; S.hits_cap = T.hits_cap; S.nhits = T.nhits;
             S.child_flag = T.child_flag; S.child = T.child;
-            rc = run_round_ssw(ctx, ctx->tb[cur], cur, h_seg, S, &cnt);
+            rc = run_round_ssw(ctx, ctx->tb[cur], cur, h_seg, n, S, &cnt);
         } else {
             rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse ? (round == 0 ? 1 : 2) : 0);
         }
@@ -1455,6 +1502,8 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n, const lsw_task* tasks, lsw_result* 
     CK(cudaMemcpyAsync(ctx->d_seg[0].p, h_seg.data(), h_seg.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
 
     std::vector<uint8_t> tab;
+    if (ctx->ssw) tab.assign((size_t)ctx->nseq * 128, 1);
+    else
     build_cand_ok(ctx->nseq, ctx->qlen.data(), ctx->match, ctx->mismatch, ctx->g, 0.0, true, tab);          // every task gets a traceback
     CK(ctx->d_cand_ok.ensure(tab.size()));
     CK(cudaMemcpyAsync(ctx->d_cand_ok.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1478,7 +1527,7 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n, const lsw_task* tasks, lsw_result* 
         SswParams S;
         memset(&S, 0, sizeof S);
         S.mode = 1; S.results = T.results; S.cigar = T.cigar; S.cigar_cap = T.cigar_cap; S.ncigar = T.ncigar;
-        rc = run_round_ssw(ctx, cur, 0, h_seg, S, nullptr);
+        rc = run_round_ssw(ctx, cur, 0, h_seg, n, S, nullptr);
     } else {
         rc = run_round(ctx, cur, 0, h_seg, n, T, nullptr);
     }

@@ -156,6 +156,7 @@ struct ScoreParams {
     int32_t push_cands;       // 1: finish() queues traceback candidates; 0: the merge kernel does (segment mode)
     int32_t count_ref;        // 1: the tasks are reference align() calls (count them); 0: segments
     int32_t block_steps;      // columns between two task-switch points: BLOCK_STEPS, or 32 for segment lists
+    int32_t aff_open, aff_extend;   // lsw_affine.cuh (skbio path): gap open / gap extension penalties, positive; s_match / s_mis are 256 * score there
 };
 
 struct TraceParams {

@@ -19,6 +19,7 @@
 #include "lsw_band.cuh"
 #include "lsw_reuse.cuh"
 #include "lsw_ssw.cuh"
+#include "lsw_affine.cuh"
 #include "lsw_host.hpp"
 
 using namespace lsw;
@@ -90,9 +91,8 @@ bool setup(Emu& E, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, i
     return true;
 }
 
-template <int NR>
+template <int NR, class Lane = ScoreLane<NR>>
 void emu_score_seq(Emu& E, const ScoreParams& P, int q, std::vector<uint32_t>& cand) {
-    using Lane = ScoreLane<NR>;
     static U4 keep_ge[17], keep_lt[17];
     for (int n = 0; n <= 16; n++) make_keep_masks(keep_ge, keep_lt, n);
     std::vector<U2> prof((size_t)NIDX * Lane::PROF_STRIDE);
@@ -436,10 +436,51 @@ namespace {
 template <int NR>
 int emu_ssw_one(const SswParams& P, int t, std::vector<uint8_t>& dir, unsigned long long* tier2) {
     dir.assign(SswBand<SSW_BW2>::DIR_BYTES, 0);
-    int rc = ssw_task<NR, SSW_BW1>(P, t, dir.data());
-    if (rc == 0) { if (tier2) (*tier2)++; rc = ssw_task<NR, SSW_BW2>(P, t, dir.data()); }
+    bool have = false;
+    int sc = 0, re = 0, rr = 0;
+    if (P.res) { const int2 rs = P.res[t]; have = true; sc = rs.x & 0xFFFF; rr = (rs.x >> 16) - 1; re = rs.y - 1; }
+    int rc = ssw_task<NR, SSW_BW1>(P, t, dir.data(), have, sc, re, rr);
+    if (rc == 0) { if (tier2) (*tier2)++; rc = ssw_task<NR, SSW_BW2>(P, t, dir.data(), have, sc, re, rr); }
     return rc;
 }
+// the packed K1 of lsw_affine.cuh for every task of sequence q (tasks [seg[q], seg[q+1]) of the emulation's task list)
+void emu_affine_seq(Emu& E, const ScoreParams& P, int q) {
+    std::vector<uint32_t> cand;
+    int c = 0;
+    while (CLASS_NR[c] < E.qlen[q]) c++;
+    switch (CLASS_NR[c]) {
+        case 16: emu_score_seq<16, AffineLane<16>>(E, P, q, cand); break;
+        case 20: emu_score_seq<20, AffineLane<20>>(E, P, q, cand); break;
+        case 24: emu_score_seq<24, AffineLane<24>>(E, P, q, cand); break;
+        case 28: emu_score_seq<28, AffineLane<28>>(E, P, q, cand); break;
+        case 32: emu_score_seq<32, AffineLane<32>>(E, P, q, cand); break;
+        case 40: emu_score_seq<40, AffineLane<40>>(E, P, q, cand); break;
+        case 48: emu_score_seq<48, AffineLane<48>>(E, P, q, cand); break;
+        case 56: emu_score_seq<56, AffineLane<56>>(E, P, q, cand); break;
+        default: emu_score_seq<64, AffineLane<64>>(E, P, q, cand); break;
+    }
+}
+
+// K1 (packed) over a task list grouped by sequence (E.seg): fills E.res
+void emu_affine_round(Emu& E, int match, int mismatch, int gap_open, int gap_extend, std::vector<KTask>& kt, std::vector<uint8_t>& ok) {
+    const int64_t n = (int64_t)E.t_read.size();
+    E.res.assign((size_t)n, make_int2(0, 0));
+    kt.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) { kt[i].p0 = E.roff[E.t_read[i]] + E.t_a[i]; kt[i].len = E.t_b[i] - E.t_a[i]; kt[i].skip = 0; }
+    ok.assign((size_t)E.nseq * 128, 0);
+    ScoreParams P;
+    memset(&P, 0, sizeof P);
+    P.codes = E.codes.data(); P.roff = E.roff.data();
+    P.t.read = E.t_read.data(); P.t.a = E.t_a.data(); P.t.b = E.t_b.data(); P.t.seq = E.t_seq.data();
+    P.kt = kt.data(); P.seg = E.seg.data(); P.res = E.res.data();
+    P.qcodes = E.qcodes.data(); P.qlen = E.qlen.data(); P.cand_ok = ok.data();
+    P.s_match = SC * match; P.s_mis = SC * mismatch; P.aff_open = gap_open; P.aff_extend = gap_extend;
+    P.push_cands = 0; P.count_ref = 1; P.block_steps = BLOCK_STEPS;
+    P.counters = E.counters;
+    for (int s = 0; s < E.nseq; s++)
+        if (E.seg[s + 1] > E.seg[s]) emu_affine_seq(E, P, s);
+}
+
 int emu_ssw_task(const SswParams& P, int t, int Q, std::vector<uint8_t>& dir, unsigned long long* tier2) {
     int c = 0;
     while (CLASS_NR[c] < Q) c++;
@@ -467,11 +508,17 @@ extern "C" {
 
 int lsw_emu_ssw_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
                          const int32_t* qoffs, int match, int mismatch, int gap_open, int gap_extend, double thr, lsw_hit* out,
-                         int64_t cap, int64_t* n_out, int64_t* counters /* tasks, cells, rounds, tier-2 tasks */) {
+                         int64_t cap, int64_t* n_out, int64_t* counters /* tasks, cells, rounds, tier-2 tasks */,
+                         int packed /* 1: forward scan by the packed K1 of lsw_affine.cuh (what the library runs); 0: scalar scan */) {
     Emu E;
     if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, 2, -1, -1)) return LSW_E_UNSUPPORTED;
     const int64_t n0 = n_reads * nseq;
     E.t_read.resize(n0); E.t_a.resize(n0); E.t_b.resize(n0); E.t_seq.resize(n0);
+    E.seg.resize(nseq + 1);
+    for (int s = 0; s <= nseq; s++) E.seg[s] = (int64_t)s * n_reads;
+    std::vector<KTask> kt;
+    std::vector<uint8_t> okt;
+    for (int s = 0; s < nseq; s++) if (match * E.qlen[s] > 127) packed = 0;      // outside the 8.8 cells: the scalar scan (as the library does)
     for (int64_t i = 0; i < n0; i++) {
         const int s = (int)(i / n_reads); const int64_t r = i - (int64_t)s * n_reads;
         E.t_read[i] = (int32_t)r; E.t_a[i] = 0; E.t_b[i] = E.rlen[r]; E.t_seq[i] = (int16_t)s;
@@ -492,14 +539,19 @@ int lsw_emu_ssw_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* o
         P.hits = out; P.hits_cap = cap; P.nhits = &nhits;
         P.child_flag = flag.data();
         P.child.read = c_read.data(); P.child.a = c_a.data(); P.child.b = c_b.data(); P.child.seq = c_seq.data();
+        if (packed) { emu_affine_round(E, match, mismatch, gap_open, gap_extend, kt, okt); P.res = E.res.data(); }
         for (int64_t t = 0; t < n; t++) {
             tasks++; cells += (unsigned long long)(E.t_b[t] - E.t_a[t]) * E.qlen[E.t_seq[t]];
             if (emu_ssw_task(P, (int)t, E.qlen[E.t_seq[t]], dir, &tier2) != 1) errflag = 1;
         }
         std::vector<int32_t> nr, na, nb; std::vector<int16_t> ns;
+        std::vector<int64_t> nseg(nseq + 1, 0);
+        std::vector<int64_t> pos(n2 + 1, 0);
+        for (int64_t j = 0; j < n2; j++) pos[j + 1] = pos[j] + flag[j];
+        for (int s = 0; s <= nseq; s++) nseg[s] = pos[std::min<int64_t>(2 * E.seg[s], n2)];
         for (int64_t j = 0; j < n2; j++)
             if (flag[j]) { nr.push_back(c_read[j]); na.push_back(c_a[j]); nb.push_back(c_b[j]); ns.push_back(c_seq[j]); }
-        E.t_read.swap(nr); E.t_a.swap(na); E.t_b.swap(nb); E.t_seq.swap(ns);
+        E.t_read.swap(nr); E.t_a.swap(na); E.t_b.swap(nb); E.t_seq.swap(ns); E.seg.swap(nseg);
         round++;
     }
     if (errflag) return LSW_E_INTERNAL;
@@ -516,21 +568,36 @@ int lsw_emu_ssw_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* o
 
 int lsw_emu_ssw_align_tasks(int64_t n_reads, const uint8_t* ascii, const int64_t* offs, int nseq, const uint8_t* qconcat,
                             const int32_t* qoffs, int match, int mismatch, int gap_open, int gap_extend, int64_t n,
-                            const lsw_task* tasks, lsw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used) {
+                            const lsw_task* tasks, lsw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used,
+                            int packed) {
     Emu E;
     if (!setup(E, n_reads, ascii, offs, nseq, qconcat, qoffs, 2, -1, -1)) return LSW_E_UNSUPPORTED;
     E.t_read.resize(n); E.t_a.resize(n); E.t_b.resize(n); E.t_seq.resize(n); E.t_orig.resize(n);
+    E.seg.assign(nseq + 1, 0);
     for (int64_t i = 0; i < n; i++) {
         const lsw_task& t = tasks[i];
         if (t.query < 0 || t.query >= nseq || t.read < 0 || t.read >= n_reads || t.start < 0 || t.end < t.start ||
             t.end > E.rlen[t.read]) return LSW_E_ARG;
-        E.t_read[i] = t.read; E.t_a[i] = t.start; E.t_b[i] = t.end; E.t_seq[i] = (int16_t)t.query; E.t_orig[i] = (int32_t)i;
+        E.seg[t.query + 1]++;
     }
+    for (int s = 0; s < nseq; s++) E.seg[s + 1] += E.seg[s];
+    {
+        std::vector<int64_t> fill(E.seg.begin(), E.seg.end() - 1);
+        for (int64_t i = 0; i < n; i++) {
+            const lsw_task& t = tasks[i];
+            const int64_t d = fill[t.query]++;
+            E.t_read[d] = t.read; E.t_a[d] = t.start; E.t_b[d] = t.end; E.t_seq[d] = (int16_t)t.query; E.t_orig[d] = (int32_t)i;
+        }
+    }
+    std::vector<KTask> kt;
+    std::vector<uint8_t> okt;
+    for (int s = 0; s < nseq; s++) if (match * E.qlen[s] > 127) packed = 0;
     unsigned long long ncig = 0;
     SswParams P;
     ssw_base_params(E, P, match, mismatch, gap_open, gap_extend);
     P.t.read = E.t_read.data(); P.t.a = E.t_a.data(); P.t.b = E.t_b.data(); P.t.seq = E.t_seq.data(); P.t.orig = E.t_orig.data();
     P.mode = 1; P.results = out; P.cigar = cigar_buf; P.cigar_cap = cigar_buf ? cigar_cap : 0; P.ncigar = &ncig;
+    if (packed && n) { emu_affine_round(E, match, mismatch, gap_open, gap_extend, kt, okt); P.res = E.res.data(); }
     std::vector<uint8_t> dir;
     int bad = 0;
     for (int64_t t = 0; t < n; t++)

@@ -333,10 +333,8 @@ template <int NR> struct ScoreOcc {
                                : LSW_OCC_BOOST == 3 ? (NR <= 20 ? 5 : NR <= 28 ? 4 : NR <= 40 ? 3 : 2) : 1;
 };
 
-template <int NR>
-__global__ void __launch_bounds__(SCORE_WARPS * 32, ScoreOcc<NR>::value)
-k_score(const ScoreParams P) {
-    using Lane = ScoreLane<NR>;
+template <int NR, class Lane>
+__device__ __forceinline__ void score_kernel_body(const ScoreParams& P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     U4* keep_ge = reinterpret_cast<U4*>(smem_raw);
     U4* keep_lt = keep_ge + 17;
@@ -450,6 +448,12 @@ k_score(const ScoreParams P) {
     }
     if (L.n_steps) atomicAdd(&P.counters[2], L.n_steps);
     if (L.n_comp) atomicAdd(&P.counters[3], L.n_comp);
+}
+
+template <int NR>
+__global__ void __launch_bounds__(SCORE_WARPS * 32, ScoreOcc<NR>::value)
+k_score(const ScoreParams P) {
+    score_kernel_body<NR, ScoreLane<NR>>(P);
 }
 
 template <int NR>

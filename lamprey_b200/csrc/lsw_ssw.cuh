@@ -46,6 +46,10 @@ struct SswParams {
     const unsigned long long* fb_in_cnt;
     unsigned long long* counters; // [0] += tasks, [1] += cells
     int32_t* errflag;
+    // with the packed K1 of lsw_affine.cuh in front: its per-task result and the candidates it queued (null: the scalar forward scan)
+    const int2* res;
+    const CandRec* cand_rec;
+    const unsigned long long* ncand;
 };
 
 template <int PW>
@@ -104,6 +108,15 @@ struct SswLane {
         o.score = best; o.ref_end = end_ref; o.read_end = end_read;
         o.ref_begin = -1; o.read_begin = -1;
         if (best <= 0) return false;
+        return begin_from_end(P, ref, qw, o);
+    }
+
+    // step 2 alone: o.score, o.ref_end, o.read_end are known (from the scan above, or from the packed K1 of lsw_affine.cuh)
+    LSW_HD static bool begin_from_end(const SswParams& P, const uint8_t* ref, const uint32_t* qw, SswOut& o) {
+        int H[NR], E[NR];
+        const int go = P.gap_open, ge = P.gap_extend, M = P.match, X = P.mismatch;
+        const int best = o.score, end_ref = o.ref_end, end_read = o.read_end;
+        o.ref_begin = -1; o.read_begin = -1;
         // reverse scan from the end cell: rows end_read .. 0, columns end_ref .. 0, until a column's maximum equals the score
 #pragma unroll
         for (int r = 0; r < NR; r++) { H[r] = 0; E[r] = 0; }
@@ -237,7 +250,8 @@ struct SswBand {
 
 // One task, all steps.  Returns 1 done, 0 next tier (band), -1 internal inconsistency.
 template <int NR, int BWMAX>
-LSW_HD int ssw_task(const SswParams& P, int t, uint8_t* dir) {
+LSW_HD int ssw_task(const SswParams& P, int t, uint8_t* dir, bool have_end = false, int k_score = 0, int k_ref_end = 0,
+                    int k_read_end = 0) {
     const int rd = P.t.read[t], a = P.t.a[t], b = P.t.b[t], q = P.t.seq[t];
     const int Q = P.qlen[q];
     const uint8_t* ref = P.codes + P.roff[rd] + a;
@@ -247,7 +261,14 @@ LSW_HD int ssw_task(const SswParams& P, int t, uint8_t* dir) {
     for (int i = 0; i < NR / 4; i++) qw[i] = reinterpret_cast<const uint32_t*>(qc)[i];
     SswOut o;
     o.matches = 0; o.others = 0; o.nrun = 0; o.po.clear();
-    const bool aligned = SswLane<NR>::ends(P, ref, b - a, qw, Q, o);
+    bool aligned;
+    if (have_end) {                      // K1 (lsw_affine.cuh) already found the score and the end cell
+        o.score = k_score; o.ref_end = k_ref_end; o.read_end = k_read_end; o.ref_begin = -1; o.read_begin = -1;
+        aligned = k_score > 0 && SswLane<NR>::begin_from_end(P, ref, qw, o);
+        if (k_score > 0 && !aligned) return -1;
+    } else {
+        aligned = SswLane<NR>::ends(P, ref, b - a, qw, Q, o);
+    }
     int rc = 1;
     if (aligned) {
         // find_all: a hit needs matches >= thr * Q, and matches <= query_end - query_begin + 1 <= span of the box; skip the
@@ -430,12 +451,15 @@ k_ssw_round(const SswParams P, uint8_t* scratch) {
         s_tasks = 0; s_cells = 0;
     }
     __syncthreads();
-    const long long total = P.fb_in ? (long long)*P.fb_in_cnt : s_cum[P.n_class_seqs];
+    const long long total = P.fb_in ? (long long)*P.fb_in_cnt : P.cand_rec ? (long long)*P.ncand : s_cum[P.n_class_seqs];
     unsigned long long tasks = 0, cells = 0;
     uint8_t local_dir[BWMAX <= 16 ? SswBand<BWMAX>::DIR_BYTES : 1];
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
         int t;
+        bool have_end = false;
+        int k_score = 0, k_ref_end = 0, k_read_end = 0;
         if (P.fb_in) t = (int)P.fb_in[k];
+        else if (P.cand_rec) t = P.cand_rec[k].t;        // the candidates K1 queued (any order)
         else {
             int lo = 0, hi = P.n_class_seqs;                        // sequence of the class that owns the k-th task
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_cum[mid] <= k) lo = mid; else hi = mid; }
@@ -443,12 +467,18 @@ k_ssw_round(const SswParams P, uint8_t* scratch) {
         }
         uint8_t* dir = BWMAX <= 16 ? local_dir
                                    : scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)SswBand<BWMAX>::DIR_BYTES;
-        const int rc = ssw_task<NR, BWMAX>(P, t, dir);
+        if (P.res) {                                        // K1's result of the task: score | (end row + 1) << 16, end column + 1
+            const int2 rs = P.res[t];
+            have_end = true; k_score = rs.x & 0xFFFF; k_read_end = (rs.x >> 16) - 1; k_ref_end = rs.y - 1;
+        }
+        const int rc = ssw_task<NR, BWMAX>(P, t, dir, have_end, k_score, k_ref_end, k_read_end);
         if (rc == 0) { const unsigned long long j = atomicAdd(P.nfallback, 1ull); P.fallback[j] = (uint32_t)t; }
         else {
             if (rc < 0) *P.errflag = 1;
-            tasks += 1;
-            cells += (unsigned long long)(P.t.b[t] - P.t.a[t]) * (unsigned long long)P.qlen[P.t.seq[t]];
+            if (!P.res) {                                   // (with K1 in front the tasks and cells are counted there)
+                tasks += 1;
+                cells += (unsigned long long)(P.t.b[t] - P.t.a[t]) * (unsigned long long)P.qlen[P.t.seq[t]];
+            }
         }
     }
     atomicAdd(&s_tasks, tasks); atomicAdd(&s_cells, cells);

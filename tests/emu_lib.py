@@ -59,7 +59,7 @@ def align_tasks(reads, seqs, tasks, match=2, mismatch=-1, gap=-1, force_full=Fal
     return out, cig[:used.value]
 
 
-def ssw_find_all(reads, seqs, thr, match=2, mismatch=-3, gap_open=5, gap_extend=2):
+def ssw_find_all(reads, seqs, thr, match=2, mismatch=-3, gap_open=5, gap_extend=2, packed=True):
     """The default (skbio / SSW) seeding path through the host emulation of lsw_ssw.cuh."""
     rc_, ro = concat_sequences(reads)
     qc, qo = concat_sequences(seqs)
@@ -71,13 +71,13 @@ def ssw_find_all(reads, seqs, thr, match=2, mismatch=-3, gap_open=5, gap_extend=
     lib().lsw_emu_ssw_find_all.restype = ctypes.c_int
     rc = lib().lsw_emu_ssw_find_all(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc), _ptr(qo),
                                     ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap_open), ctypes.c_int(gap_extend),
-                                    ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt))
+                                    ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt), ctypes.c_int(int(packed)))
     if rc:
         raise RuntimeError("lsw_emu_ssw_find_all rc=%d" % rc)
     return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), rounds=int(cnt[2]), tier2=int(cnt[3]))
 
 
-def ssw_align_tasks(reads, seqs, tasks, match=2, mismatch=-3, gap_open=5, gap_extend=2):
+def ssw_align_tasks(reads, seqs, tasks, match=2, mismatch=-3, gap_open=5, gap_extend=2, packed=True):
     rc_, ro = concat_sequences(reads)
     qc, qo = concat_sequences(seqs)
     qo = qo.astype(np.int32)
@@ -89,7 +89,8 @@ def ssw_align_tasks(reads, seqs, tasks, match=2, mismatch=-3, gap_open=5, gap_ex
     lib().lsw_emu_ssw_align_tasks.restype = ctypes.c_int
     rc = lib().lsw_emu_ssw_align_tasks(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc), _ptr(qo),
                                        ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap_open), ctypes.c_int(gap_extend),
-                                       ctypes.c_int64(len(tasks)), _ptr(tasks), _ptr(out), _ptr(cig), ctypes.c_int64(cap), ctypes.byref(used))
+                                       ctypes.c_int64(len(tasks)), _ptr(tasks), _ptr(out), _ptr(cig), ctypes.c_int64(cap), ctypes.byref(used),
+                                       ctypes.c_int(int(packed)))
     if rc:
         raise RuntimeError("lsw_emu_ssw_align_tasks rc=%d" % rc)
     return out, cig[:used.value]

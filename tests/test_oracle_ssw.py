@@ -51,8 +51,8 @@ def test_committed_vectors():
         assert got == want
 
 
-def _check_emu_tasks(reads, seqs, tasks, p=(2, -3, 5, 2)):
-    res, cig = emu_lib.ssw_align_tasks(reads, seqs, tasks, *p)
+def _check_emu_tasks(reads, seqs, tasks, p=(2, -3, 5, 2), packed=True):
+    res, cig = emu_lib.ssw_align_tasks(reads, seqs, tasks, *p, packed=packed)
     for t, r in zip(tasks, res):
         d = ssw_oracle.align(reads[t["read"]][t["start"]:t["end"]], seqs[t["query"]], *p)
         if d["score"] == 0:
@@ -91,6 +91,7 @@ def test_emu_ssw_align_vs_oracle(seed, alphabet, p):
     tasks = [(i, 0, len(r), q) for i, r in enumerate(reads) for q in range(len(seqs))]
     tasks += [(i, a, b, q) for i, r in enumerate(reads) for q in (1, 4) for a, b in [sorted((rng.randrange(len(r) + 1), rng.randrange(len(r) + 1)))]]
     _check_emu_tasks(reads, seqs, np.array(tasks, dtype=TASK_DT), p)
+    _check_emu_tasks(reads, seqs, np.array(tasks, dtype=TASK_DT), p, packed=False)
 
 
 def test_emu_ssw_wide_band_takes_the_second_tier():
@@ -119,11 +120,13 @@ def ssw_matrix(hits):
     return np.stack([hits[k].astype(np.int32) for k in cols], 1) if len(hits) else np.zeros((0, 9), np.int32)
 
 
-@pytest.mark.parametrize("thr", [0.70, 0.75])
-def test_emu_ssw_find_all_vs_oracle_and_golden(thr):
+@pytest.mark.parametrize("thr,packed", [(0.70, True), (0.75, True), (0.70, False)])
+def test_emu_ssw_find_all_vs_oracle_and_golden(thr, packed):
+    # packed: the forward scan by the s16x2 DPX lanes of lsw_affine.cuh (what the library runs when match * len(primer) <= 127);
+    # otherwise the scalar per-task scan
     reads = load_reads("50")[:12]
     seqs = [s for _, s in seeding_ref.PrimerSet(schema_path("H33")).sequences()]
-    hits, cnt = emu_lib.ssw_find_all(reads, seqs, thr)
+    hits, cnt = emu_lib.ssw_find_all(reads, seqs, thr, packed=packed)
     want, calls, cells = _oracle_rows(reads, seqs, thr)
     assert np.array_equal(ssw_matrix(hits), want) and len(want) > 50
     assert (cnt["tasks"], cnt["cells"]) == (calls, cells)
