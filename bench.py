@@ -326,6 +326,8 @@ def main():
     ap.add_argument("--extra-reads-5kb", type=int, default=400000)
     ap.add_argument("--extra-reads-long", type=int, default=100000)
     ap.add_argument("--skbio-reads", type=int, default=100000, help="reads of the headline batch seeded on the skbio path (extra config)")
+    ap.add_argument("--strong-pieces", type=int, default=1, help="ranges per device in the strong-scaling leg")
+    ap.add_argument("--e2e-pieces", type=int, default=1, help="ranges per device a batch is cut into inside the pool (lsw_pool_set_pieces)")
     ap.add_argument("--e2e-depth", type=int, default=2, help="contexts per device of the pool (batches in flight)")
     args = ap.parse_args()
     # stdout carries the one JSON line and nothing else: libraries that print to fd 1 (NCCL's version
@@ -501,36 +503,39 @@ def main():
     if not args.no_e2e:
         depth = max(1, args.e2e_depth)
         pool = _native.Pool([local_rank], depth)
-        pool.configure(seqs, args.thr, compact=True)
+        pool.configure(seqs, args.thr, compact=True, pieces=args.e2e_pieces)
         cap = int(n_hits * 1.05) + 4096
         outs = [_native.PinnedArray(cap, _native.HIT16_DT) for _ in range(depth)]
 
         def run_steps(total):
-            tickets, last, tms = [], 0, []
+            tickets, last, tms, done_at = [], 0, [], []
             for k in range(total):
                 tickets.append(pool.submit(ascii_np, offs_np, outs[k % depth].array))
                 if len(tickets) >= depth:
                     h, _, tm = pool.wait(tickets.pop(0))
-                    last = len(h); tms.append(tm)
+                    last = len(h); tms.append(tm); done_at.append(time.perf_counter())
             while tickets:
                 h, _, tm = pool.wait(tickets.pop(0))
-                last = len(h); tms.append(tm)
-            return last, tms
+                last = len(h); tms.append(tm); done_at.append(time.perf_counter())
+            return last, tms, done_at
 
         run_steps(max(depth, args.warmup - 1))
         barrier()
         e0.record(stream)
         t0 = time.perf_counter()
-        got, tms = run_steps(args.steps)
+        got, tms, done_at = run_steps(args.steps)
         t_wall = time.perf_counter() - t0          # the pool's contexts run on their own streams: wall clock around the blocking waits
         e1.record(stream)
         barrier()
         t_e2e, reads_e2e = gather_max_and_sum(t_wall, [args.reads * args.steps])
         e2e = {"value": reads_e2e / t_e2e, "unit": "reads/s",
                "h2d_bytes_per_step": int(ascii_np.nbytes + offs_np.nbytes), "d2h_bytes_per_step": int(got * 16),
-               "ms_per_step": 1e3 * t_e2e / args.steps, "contexts": depth, "hits_per_step": int(got),
+               "ms_per_step": 1e3 * t_e2e / args.steps, "contexts": depth, "pieces": args.e2e_pieces, "hits_per_step": int(got),
                "host_ms_per_call": {k: 1e3 * float(np.mean([tm[k + "_s"] for tm in tms])) for k in ("upload", "find", "fetch")},
                "upload_alone_ms": upload_alone_ms,
+               # between consecutive completions the pipeline is full (the timed region above also pays for filling and draining
+               # it: the first upload and the last download of the K steps overlap nothing)
+               "steady_state_ms_per_step": 1e3 * (done_at[-1] - done_at[0]) / (len(done_at) - 1) if len(done_at) > 1 else None,
                "call": "per step: lsw_pool_submit + lsw_pool_wait on a pool of %d contexts of this GPU (the library's worker threads run "
                        "lsw_upload_reads -> lsw_find_all -> lsw_fetch_hits_compact; one batch's copies overlap the next batch's kernels); "
                        "read text and 16-byte hit records in page-locked host buffers" % depth}
@@ -565,7 +570,7 @@ def main():
         if rank == 0:
             ndev = min(world, torch.cuda.device_count())
             pool = _native.Pool(list(range(ndev)), 2)
-            pool.configure(seqs, args.thr, compact=True)
+            pool.configure(seqs, args.thr, compact=True, pieces=args.strong_pieces)
             cap = int(n_hits * 1.05) + 4096
             outs = [_native.PinnedArray(cap, _native.HIT16_DT) for _ in range(2)]
             for k in range(2):
@@ -584,7 +589,7 @@ def main():
                 _, _, tm = pool.wait(tickets.pop(0)); tms.append(tm)
             t_s = time.perf_counter() - t0
             best = min(lat, key=lambda t: t["total_s"])
-            strong = {"scaling": "strong", "n_gpus": ndev, "reads": args.reads, "workload": args.workload,
+            strong = {"scaling": "strong", "n_gpus": ndev, "reads": args.reads, "workload": args.workload, "pieces": args.strong_pieces,
                       "value": args.reads * (args.steps + 1) / t_s, "unit": "reads/s", "ms_per_batch_pipelined": 1e3 * t_s / (args.steps + 1),
                       "ms_per_batch_latency": 1e3 * best["total_s"],
                       "latency_phases_ms": {k: 1e3 * best[k + "_s"] for k in ("upload", "find", "fetch", "gather_wait")},

@@ -240,10 +240,14 @@ const char* lsw_pool_last_error(const lsw_pool* pool);      /* pool may be NULL:
  * lsw_find_all) and the record format of the hit buffers */
 int  lsw_pool_configure(lsw_pool* pool, int match, int mismatch, int gap, int gap_ext, int n_queries, const uint8_t* concat,
                         const int32_t* offs, double identity_threshold, int allowed_overlap, int hit_format);
+/* pieces > 1: every device's share of a batch is cut further into that many ranges, which alternate between the device's contexts:
+ * a single batch then overlaps its own copies with its own kernels (upload of range k+1 and download of range k-1 under the
+ * kernels of range k), and a context only needs room for 1/pieces of the share.  Default 1. */
+int  lsw_pool_set_pieces(lsw_pool* pool, int pieces);
 int  lsw_pool_submit(lsw_pool* pool, int64_t n_reads, const uint8_t* ascii, const int64_t* offs, void* hits_out,
                      int64_t hits_cap, int64_t* ticket);
 /* blocks until the batch is done.  *n_hits = hits of the whole batch (> hits_cap with LSW_E_OVERFLOW: nothing was copied
- * for the ranges that did not fit); counters = sums over the ranges, ms_* = the slowest range's. */
+ * for the ranges that did not fit); counters = sums over the ranges, ms_* = device time per device (mean over devices). */
 int  lsw_pool_wait(lsw_pool* pool, int64_t ticket, int64_t* n_hits, lsw_counters* counters, lsw_pool_times* times);
 
 #ifdef __cplusplus

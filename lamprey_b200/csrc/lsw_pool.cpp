@@ -36,7 +36,7 @@ struct Batch {                       // one lsw_pool_submit
     int64_t ticket = 0;
     const uint8_t* ascii = nullptr;
     const int64_t* offs = nullptr;
-    std::vector<int64_t> cut;        // [n_devices + 1] read ranges
+    std::vector<int64_t> cut;        // [n_ranges + 1] read ranges (n_ranges = devices x pieces; range r runs on device r % devices)
     uint8_t* out = nullptr;
     int64_t cap = 0;
     int item = 32;
@@ -60,6 +60,7 @@ struct Job { std::shared_ptr<Batch> b; int range = 0; };
 struct lsw_pool {
     std::vector<int> devices;
     int per_dev = 1;
+    int pieces = 1;                                        // ranges per device and batch (lsw_pool_set_pieces)
     struct Worker {
         lsw_ctx* ctx = nullptr;
         int dev_index = 0;
@@ -245,6 +246,14 @@ int lsw_pool_configure(lsw_pool* p, int match, int mismatch, int gap, int gap_ex
     return LSW_OK;
 }
 
+int lsw_pool_set_pieces(lsw_pool* p, int pieces) {
+    if (!p) return LSW_E_ARG;
+    std::lock_guard<std::mutex> g(p->mu);
+    if (pieces < 1 || pieces > 64) { p->err = "lsw_pool_set_pieces: 1..64 pieces per device"; return LSW_E_ARG; }
+    p->pieces = pieces;
+    return LSW_OK;
+}
+
 int lsw_pool_submit(lsw_pool* p, int64_t n, const uint8_t* ascii, const int64_t* offs, void* hits_out, int64_t hits_cap, int64_t* ticket) {
     if (!p) return LSW_E_ARG;
     if (n < 0 || !offs || !ticket || hits_cap < 0 || (hits_cap > 0 && !hits_out) || (n > 0 && !ascii && offs[n] > offs[0])) {
@@ -254,11 +263,17 @@ int lsw_pool_submit(lsw_pool* p, int64_t n, const uint8_t* ascii, const int64_t*
     }
     std::shared_ptr<Batch> b(new Batch());
     const int D = (int)p->devices.size();
+    int S;
+    {
+        std::lock_guard<std::mutex> g(p->mu);
+        S = p->pieces;
+    }
+    const int R = D * S;
     b->ascii = ascii; b->offs = offs; b->out = static_cast<uint8_t*>(hits_out); b->cap = hits_cap;
-    b->cut = shard_by_bases(offs, n, D);
-    b->nhits.assign(D, -1); b->done.assign(D, 0); b->cnt.resize(D);
-    b->t_up.assign(D, 0); b->t_find.assign(D, 0); b->t_fetch.assign(D, 0); b->t_wait.assign(D, 0);
-    b->left = D;
+    b->cut = shard_by_bases(offs, n, R);
+    b->nhits.assign(R, -1); b->done.assign(R, 0); b->cnt.resize(R);
+    b->t_up.assign(R, 0); b->t_find.assign(R, 0); b->t_fetch.assign(R, 0); b->t_wait.assign(R, 0);
+    b->left = R;
     b->t_submit = now_s();
     {
         std::lock_guard<std::mutex> g(p->mu);
@@ -266,9 +281,12 @@ int lsw_pool_submit(lsw_pool* p, int64_t n, const uint8_t* ascii, const int64_t*
         b->item = p->hit_format == LSW_HITS_COMPACT ? (int)sizeof(lsw_hit16) : (int)sizeof(lsw_hit);
         b->ticket = p->next_ticket++;
         p->live[b->ticket] = b;
-        const int slot = (int)((b->ticket - 1) % p->per_dev);
-        for (int d = 0; d < D; d++) {
-            Job j; j.b = b; j.range = d;
+        // range r runs on device r % D: the first D ranges (one per device) finish first, so the hit counts a later range waits
+        // for in the gather are those of earlier waves; on a device, consecutive ranges alternate between its contexts, so that one
+        // range's copies overlap the next range's kernels even within a single batch
+        for (int r = 0; r < R; r++) {
+            Job j; j.b = b; j.range = r;
+            const int d = r % D, slot = (int)(((b->ticket - 1) + r / D) % p->per_dev);
             p->workers[(size_t)d * p->per_dev + slot]->q.push_back(j);
         }
         *ticket = b->ticket;
@@ -286,19 +304,20 @@ int lsw_pool_wait(lsw_pool* p, int64_t ticket, int64_t* n_hits, lsw_counters* co
     p->cv_done.wait(g, [&] { return b->left == 0; });
     p->live.erase(ticket);
     const int D = (int)p->devices.size();
+    const int R = (int)b->nhits.size();
     int64_t total = 0;
-    for (int d = 0; d < D; d++) total += b->nhits[d];
+    for (int r = 0; r < R; r++) total += b->nhits[r];
     if (n_hits) *n_hits = total;
     if (counters) {
         lsw_counters c;
         std::memset(&c, 0, sizeof c);
-        for (int d = 0; d < D; d++) {
+        for (int d = 0; d < R; d++) {
             const lsw_counters& s = b->cnt[d];
             c.tasks += s.tasks; c.cells += s.cells; c.top_tasks += s.top_tasks; c.top_cells += s.top_cells; c.traced += s.traced;
             c.hits += s.hits; c.rounds = std::max(c.rounds, s.rounds);
-            c.ms_score = std::max(c.ms_score, s.ms_score); c.ms_trace = std::max(c.ms_trace, s.ms_trace);
-            c.ms_other = std::max(c.ms_other, s.ms_other); c.ms_total = std::max(c.ms_total, s.ms_total);
-            c.ms_score_round0 = std::max(c.ms_score_round0, s.ms_score_round0);
+            c.ms_score += s.ms_score / D; c.ms_trace += s.ms_trace / D;          // device time per device (mean over the devices)
+            c.ms_other += s.ms_other / D; c.ms_total += s.ms_total / D;
+            c.ms_score_round0 += s.ms_score_round0 / D;
             c.score_launches += s.score_launches; c.trace_launches += s.trace_launches; c.other_launches += s.other_launches;
             c.steps += s.steps; c.fallbacks += s.fallbacks; c.computed_cells += s.computed_cells;
             c.computed_cells_round0 += s.computed_cells_round0;
@@ -308,10 +327,16 @@ int lsw_pool_wait(lsw_pool* p, int64_t ticket, int64_t* n_hits, lsw_counters* co
     }
     if (times) {
         std::memset(times, 0, sizeof *times);
+        std::vector<double> up(D, 0.0), fd(D, 0.0), ft(D, 0.0);
+        for (int r = 0; r < R; r++) {
+            const int d = r % D;
+            up[d] += b->t_up[r]; fd[d] += b->t_find[r]; ft[d] += b->t_fetch[r];        // per device: the sum over its ranges
+            times->gather_wait_s = std::max(times->gather_wait_s, b->t_wait[r]);
+            if (d < 8) { times->reads[d] += b->cut[r + 1] - b->cut[r]; times->hits[d] += b->nhits[r]; }
+        }
         for (int d = 0; d < D; d++) {
-            times->upload_s = std::max(times->upload_s, b->t_up[d]); times->find_s = std::max(times->find_s, b->t_find[d]);
-            times->fetch_s = std::max(times->fetch_s, b->t_fetch[d]); times->gather_wait_s = std::max(times->gather_wait_s, b->t_wait[d]);
-            if (d < 8) { times->reads[d] = b->cut[d + 1] - b->cut[d]; times->hits[d] = b->nhits[d]; }
+            times->upload_s = std::max(times->upload_s, up[d]); times->find_s = std::max(times->find_s, fd[d]);
+            times->fetch_s = std::max(times->fetch_s, ft[d]);
         }
         times->total_s = b->t_done - b->t_submit;
     }

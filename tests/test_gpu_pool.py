@@ -37,8 +37,8 @@ def test_compact_hits_equal_wide_hits(engine):
     assert 0 < c["computed_cells_round0"] <= c["computed_cells"]
 
 
-@pytest.mark.parametrize("compact", [False, True])
-def test_pool_split_over_contexts_equals_one_context(compact):
+@pytest.mark.parametrize("compact,pieces", [(False, 1), (True, 1), (True, 3)])
+def test_pool_split_over_contexts_equals_one_context(compact, pieces):
     # ONE batch dealt over several contexts (every visible GPU; on a single-GPU box two contexts of GPU 0 stand in for two
     # devices) with the host-side gather == the same batch on one context, byte for byte
     devices = list(range(_n_gpus())) if _n_gpus() > 1 else [0, 0]
@@ -50,8 +50,8 @@ def test_pool_split_over_contexts_equals_one_context(compact):
     want = one.find_all(0.7)
     want_cnt = one.last_counters
     one.close()
-    pool = _native.Pool(devices)
-    pool.configure(seqs, 0.7, allowed_overlap=4, compact=compact)
+    pool = _native.Pool(devices, 2 if pieces > 1 else 1)
+    pool.configure(seqs, 0.7, allowed_overlap=4, compact=compact, pieces=pieces)      # pieces: ranges per device, alternating contexts
     out = np.zeros(len(want) + 10, pool.hit_dtype)
     hits, cnt, times = pool.wait(pool.submit(concat, offs, out))
     if compact:
