@@ -15,6 +15,7 @@
 #include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -77,6 +78,7 @@ struct TaskBuf {
 
 struct Timed { cudaEvent_t e0, e1; int kind; };
 
+constexpr int64_t REUSE_MIN_TASKS = 1 << 16;          // recursion rounds with fewer tasks align whole slices (no block-best reuse)
 constexpr int64_t UPLOAD_CHUNK = 64ll << 20;          // bytes of read text per staged host -> device copy (lsw_upload_reads)
 
 }  // namespace
@@ -121,7 +123,10 @@ struct lsw_ctx {
     DevBuf d_blockbest, d_bb_off, d_bb1, d_bb1_off, d_nseg, d_segpos, d_res_s, d_seg_s, d_class_of, d_kt;
     int32_t allowed_overlap = -1;
     int64_t n_hits = 0;
-    bool hits_pruned = false;        // the sorted hits carry the survivor flag of lsw_set_overlap (lsw_chain_subreads needs it)
+    bool hits_pruned = false;
+    // environment switches, read once in lsw_create
+    int env_k2_blocks = 0, env_k2_debug = 0;
+    bool env_debug = false, env_no_reuse = false, env_ssw_scalar = false;        // the sorted hits carry the survivor flag of lsw_set_overlap (lsw_chain_subreads needs it)
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -166,6 +171,16 @@ int64_t device_bytes(lsw_ctx* ctx) {
     } while (0)
 
 int fail(lsw_ctx* ctx, int code, const char* msg) { ctx->err = msg; return code; }
+
+// the environment switches, once per call of an entry point (not per launch: tests flip them between calls on one context)
+void read_env(lsw_ctx* ctx) {
+    const char* e;
+    ctx->env_k2_blocks = (e = getenv("LSW_K2_BLOCKS_PER_SM")) ? atoi(e) : 0;
+    ctx->env_k2_debug = (e = getenv("LSW_K2_DEBUG")) ? atoi(e) : 0;
+    ctx->env_debug = getenv("LSW_DEBUG") != nullptr;
+    ctx->env_no_reuse = getenv("LSW_NO_REUSE") != nullptr;
+    ctx->env_ssw_scalar = getenv("LSW_SSW_SCALAR") != nullptr;
+}
 
 // ---- small kernels ----------------------------------------------------------------------
 
@@ -426,12 +441,34 @@ struct Span {      // times a region of the stream into one of the lsw_counters 
     ~Span() { if (t.e1) { cudaEventRecord(t.e1, ctx->stream); ctx->timed.push_back(t); } }
 };
 
+// Launch configuration of one kernel instantiation (dynamic shared memory attribute + resident blocks per SM), looked up once per
+// process and device: a step launches ~560 kernels, most of them in the late, tiny recursion rounds where the GPU waits for the
+// host -- two runtime calls per launch were a measurable part of a step there.
+struct LaunchCfg {
+    std::atomic<int> occ[16];
+    LaunchCfg() { for (auto& o : occ) o.store(-1); }
+    template <class K>
+    cudaError_t get(int device, K kernel, int threads, size_t smem, int& out) {
+        const int d = device & 15;
+        int v = occ[d].load(std::memory_order_acquire);
+        if (v < 0) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem);
+            if (e != cudaSuccess) return e;
+            occ[d].store(v, std::memory_order_release);
+        }
+        out = v;
+        return cudaSuccess;
+    }
+};
+
 template <int NR>
 int launch_score(lsw_ctx* ctx, const ScoreParams& P, int64_t n_class_tasks) {
     const size_t smem = score_smem_bytes<NR>();
-    CK(cudaFuncSetAttribute(k_score<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static LaunchCfg cfg;
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score<NR>, SCORE_WARPS * 32, smem));
+    CK(cfg.get(ctx->device, k_score<NR>, SCORE_WARPS * 32, smem, occ));
     if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "score kernel does not fit on an SM");
     const int64_t lanes_needed = (n_class_tasks + 1) / 2;
     const int blocks = grid_for(lanes_needed, SCORE_WARPS * 32, ctx->num_sms * occ);
@@ -465,23 +502,24 @@ int launch_trace(lsw_ctx* ctx, TraceParams P, int64_t n_class_tasks, int qmax) {
     const size_t smem = BandSmem<NR, BW>::total;
     // find_all never needs the op list of a path, align_tasks (CIGAR output) does
     auto kernel = P.mode == 1 ? k_trace_band<NR, BW, true> : k_trace_band<NR, BW, false>;
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static LaunchCfg cfg_band[2], cfg_fast[2], cfg_full;
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TRACE_THREADS, smem));
+    CK(cfg_band[P.mode == 1].get(ctx->device, kernel, TRACE_THREADS, smem, occ));
     if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
-    if (getenv("LSW_K2_BLOCKS_PER_SM")) occ = std::max(1, std::min(occ, atoi(getenv("LSW_K2_BLOCKS_PER_SM"))));
+    if (ctx->env_k2_blocks > 0) occ = std::max(1, std::min(occ, ctx->env_k2_blocks));
     const int blocks = grid_for((n_class_tasks + 1) / 2, TRACE_THREADS, ctx->num_sms * occ);
     // tier 2, the ~1 % whose walk left the band: the whole window in a global scratch (k_trace_fast); a small grid, the list is short
     const size_t smem1 = trace_smem_bytes<NR>();
     auto kernel1 = P.mode == 1 ? k_trace_fast<NR, true> : k_trace_fast<NR, false>;
-    CK(cudaFuncSetAttribute(kernel1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    int occ1 = 0;
+    CK(cfg_fast[P.mode == 1].get(ctx->device, kernel1, TRACE_THREADS, smem1, occ1));
     const int blocks1 = grid_for((n_class_tasks + 1) / 2, TRACE_THREADS, ctx->num_sms * 2);
     const int64_t threads1 = (int64_t)blocks1 * TRACE_THREADS;
     const int64_t Wf = trace_window_fast_max(qmax, ctx->match, ctx->g);
     constexpr int UNITS = TraceLane<NR>::UPAIRS;         // 16 bytes per (window column, unit pair, lane): both tasks of the lane
     // tier 3, what even that could not prove: one thread per task, 2-bit ops of a window that is exact a priori
     int occ2 = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_trace_full<NR2>, TRACE_THREADS, 0));
+    CK(cfg_full.get(ctx->device, k_trace_full<NR2>, TRACE_THREADS, 0, occ2));
     if (occ2 < 1) return fail(ctx, LSW_E_INTERNAL, "trace kernel does not fit on an SM");
     const int blocks2 = grid_for(n_class_tasks, TRACE_THREADS, ctx->num_sms * std::min(occ2, 2));
     const int64_t threads2 = (int64_t)blocks2 * TRACE_THREADS;
@@ -550,7 +588,7 @@ void fill_trace_params(lsw_ctx* ctx, TraceParams& T, const TaskBuf& cur) {
     T.match = ctx->match; T.mismatch = ctx->mismatch; T.g = ctx->g;
     T.errflag = ctx->d_err.as<int32_t>();
     T.all_fallback = nibble_walk_ok(ctx->match, ctx->mismatch, ctx->g) ? 0 : 1;
-    T.debug = getenv("LSW_K2_DEBUG") ? atoi(getenv("LSW_K2_DEBUG")) : 0;
+    T.debug = ctx->env_k2_debug;
 }
 
 // Runs K1 then K2 for every class over the task list `cur` (segments h_seg on the host).
@@ -692,9 +730,9 @@ int launch_ssw(lsw_ctx* ctx, SswParams P, int64_t n_class_tasks, const ScorePara
         // K1: the forward scan of every task of the class with packed DPX instructions (lsw_affine.cuh); it queues the tasks
         // that need the rest (reverse scan, banded traceback) as candidates
         const size_t smem = score_smem_bytes<NR>();
-        CK(cudaFuncSetAttribute(k_score_affine<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static LaunchCfg cfg;
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_affine<NR>, SCORE_WARPS * 32, smem));
+        CK(cfg.get(ctx->device, k_score_affine<NR>, SCORE_WARPS * 32, smem, occ));
         if (occ < 1) return fail(ctx, LSW_E_INTERNAL, "affine score kernel does not fit on an SM");
         const int blocks1 = grid_for((n_class_tasks + 1) / 2, SCORE_WARPS * 32, ctx->num_sms * occ);
         k_score_affine<NR><<<blocks1, SCORE_WARPS * 32, smem, ctx->stream>>>(*K1);
@@ -744,7 +782,7 @@ int run_round_ssw(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<
     P.match = ctx->ssw_match; P.mismatch = ctx->ssw_mismatch; P.gap_open = ctx->ssw_open; P.gap_extend = ctx->ssw_extend;
     P.counters = ctx->d_counters.as<unsigned long long>();
     P.errflag = ctx->d_err.as<int32_t>();
-    bool packed = !getenv("LSW_SSW_SCALAR");
+    bool packed = !ctx->env_ssw_scalar;
     for (int s = 0; s < ctx->nseq; s++) if (ctx->ssw_match * ctx->qlen[s] > 127) packed = false;
     ScoreParams K1;
     if (packed) {
@@ -838,6 +876,7 @@ int lsw_create(int device, lsw_ctx** out) {
         g_create_error = cudaGetErrorString(e); delete ctx; return LSW_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    read_env(ctx);
     *out = ctx;
     return LSW_OK;
 }
@@ -1072,6 +1111,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     if (ctx->nseq <= 0) return fail(ctx, LSW_E_STATE, "lsw_set_queries has not been called");
     if (int rc = check_scoring_fits(ctx)) return rc;
     CK(cudaSetDevice(ctx->device));
+    read_env(ctx);
     lsw_counters cnt;
     memset(&cnt, 0, sizeof cnt);
     ctx->timed.clear(); ctx->ev_used = 0;
@@ -1117,7 +1157,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     }
 
     // block bests of round 0 for the child tasks: 4 B per BB_BLOCK columns per (read, sequence)
-    bool reuse = ctx->reuse && !getenv("LSW_NO_REUSE") && !ctx->ssw;    // (SSW's "first maximum wins" end rule has no block-best merge yet)
+    bool reuse = ctx->reuse && !ctx->env_no_reuse && !ctx->ssw;    // (SSW's "first maximum wins" end rule has no block-best merge yet)
     // the block bests are an optimisation (4 B per 32 columns per sequence): without room for them every round simply
     // aligns whole slices -- same results, more cells
     if (reuse && ctx->d_blockbest.ensure((size_t)std::max<int64_t>(1, ctx->bb_total) * ctx->nseq * 4) != cudaSuccess) {
@@ -1156,7 +1196,10 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
             S.child_flag = T.child_flag; S.child = T.child;
             rc = run_round_ssw(ctx, ctx->tb[cur], cur, h_seg, n, S, &cnt);
         } else {
-            rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse ? (round == 0 ? 1 : 2) : 0);
+            // late rounds hold a few thousand tasks: there the four extra launches of the reuse path (plan, scan, fill, merge) cost
+            // more than the cells they save, and the GPU waits for the host between launches (both paths are exact)
+            const bool reuse_round = reuse && (round == 0 || n >= REUSE_MIN_TASKS);
+            rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse_round ? (round == 0 ? 1 : 2) : 0);
         }
         if (rc) break;
         if (reuse && round == 0 && ctx->use_bb1 && ctx->bb1_total > 0) {
@@ -1201,7 +1244,7 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
         CK(cudaMemcpyAsync(h_nf, ctx->d_nfallback.p, NCLASS * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         for (int c = 0; c < NCLASS; c++) { cnt.traced += (int64_t)h_nc[c]; cnt.fallbacks += (int64_t)h_nf[c]; }
-        if (getenv("LSW_DEBUG")) {
+        if (ctx->env_debug) {
             float ms[3] = {0.f, 0.f, 0.f};
             for (size_t k = dbg_from; k < ctx->timed.size(); k++) {
                 float m = 0.f;
@@ -1469,6 +1512,7 @@ int lsw_align_tasks(lsw_ctx* ctx, int64_t n, const lsw_task* tasks, lsw_result* 
     if (cigar_used) *cigar_used = 0;
     if (n == 0) return LSW_OK;
     CK(cudaSetDevice(ctx->device));
+    read_env(ctx);
     ctx->timed.clear(); ctx->ev_used = 0;
 
     // group by sequence (K1 serves one sequence per warp): counting sort on the host
