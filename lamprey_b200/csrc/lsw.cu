@@ -78,7 +78,6 @@ struct TaskBuf {
 
 struct Timed { cudaEvent_t e0, e1; int kind; };
 
-constexpr int64_t REUSE_MIN_TASKS = 1 << 16;          // recursion rounds with fewer tasks align whole slices (no block-best reuse)
 constexpr int64_t UPLOAD_CHUNK = 64ll << 20;          // bytes of read text per staged host -> device copy (lsw_upload_reads)
 
 }  // namespace
@@ -1196,10 +1195,9 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
             S.child_flag = T.child_flag; S.child = T.child;
             rc = run_round_ssw(ctx, ctx->tb[cur], cur, h_seg, n, S, &cnt);
         } else {
-            // late rounds hold a few thousand tasks: there the four extra launches of the reuse path (plan, scan, fill, merge) cost
-            // more than the cells they save, and the GPU waits for the host between launches (both paths are exact)
-            const bool reuse_round = reuse && (round == 0 || n >= REUSE_MIN_TASKS);
-            rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse_round ? (round == 0 ? 1 : 2) : 0);
+            // (the reuse path stays on in the late, tiny rounds as well: it also bounds the SERIAL work of a lane -- a 10 kb child
+            // slice is a 100-column head and tail there, but milliseconds of one lane's time when aligned whole; measured)
+            rc = run_round(ctx, ctx->tb[cur], cur, h_seg, n, T, &cnt, reuse ? (round == 0 ? 1 : 2) : 0);
         }
         if (rc) break;
         if (reuse && round == 0 && ctx->use_bb1 && ctx->bb1_total > 0) {
