@@ -2,7 +2,7 @@
 # ncu launch list + full captures of the hot kernels AT THE 10^6-READ CONFIG (run under gpurun): tools/profile_1M.sh <tag>
 # gpurun copies back at most 64 MiB: the reports are turned into CSV pages on the box and dropped if they are too large.
 tag=${1:-r02}
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extra --no-strong"
 O=gpurun_out
 if [ -z "$NO_LAUNCH_LIST" ]; then
 $CMD > $O/${tag}_plain.log 2>&1 &&
@@ -22,5 +22,8 @@ cap() {   # cap <name> <kernel base name> <launches of that kernel to skip>
 cap score24 k_score 2
 cap band24 k_trace_band 2
 cap band16 k_trace_band 0
+# the skbio path: round 0 of the packed affine K1, 24-row class, 10^5 reads
+CMD="python tools/dbg_ssw.py 100000"
+cap affine24 k_score_affine 2
 for f in $O/${tag}_ncu_*.log; do echo "== $f"; tail -n 3 $f; done
 du -sh $O; ls -la $O
