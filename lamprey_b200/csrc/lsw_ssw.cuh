@@ -78,7 +78,11 @@ template <int NR>
 struct SswLane {
     static_assert(NR % 4 == 0 && NR <= 64, "rows in registers");
 
-    LSW_HD static int sub(int qb, int bc, int match, int mismatch) { return bc >= CODE_OTHER ? 0 : (qb == bc ? match : mismatch); }
+    // skbio's matrix: "N" (any non-ACGT base) scores 0 against everything, in the target and -- stage 2, where the query is a
+    // sub-read -- in the query.  (A padding row of the register kernels carries 0xFF: never equal, plain mismatch.)
+    LSW_HD static int sub(int qb, int bc, int match, int mismatch) {
+        return (bc >= CODE_OTHER || qb == CODE_OTHER) ? 0 : (qb == bc ? match : mismatch);
+    }
 
     // steps 1 and 2.  ref[c]: code of slice column c.  false: nothing aligned (score 0).
     LSW_HD static bool ends(const SswParams& P, const uint8_t* ref, int len, const uint32_t* qw, int Q, SswOut& o) {

@@ -164,6 +164,8 @@ def test_emu_stage2_subreads_vs_oracle():
     for fn in ("H3F3A.fa", "HIST1H3B.fa"):
         refs[fn] = open(os.path.join(GOLD, fn)).read().split("\n", 1)[1].replace("\n", "").upper()
     reads = load_reads("50")[:16] + ["ACGT" * 30, "A" * 50, "", "NNNNACGTTGCANNN"]
+    r0 = reads[0]
+    reads.append(r0[:120] + "N" + r0[121:260] + "RY" + r0[262:400])        # non-ACGT bases INSIDE an alignment: they score 0, not a mismatch
     pairs = []
     for i, r in enumerate(reads):
         pairs.append((i, 0, len(r), 0))
