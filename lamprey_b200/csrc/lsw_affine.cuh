@@ -10,7 +10,7 @@
 //                     carries the arg-max tag) but NOT biased: every packed add is a true two-lane DPX add, so a negative
 //                     substitution score cannot borrow across the halves.  Per two cells:
 //                         t  = VIADDMNMX.RELU(D, w, E)      h  = VIMNMX(t, F)
-//                         hg = VIADDMNMX.RELU(h, -gapO, 0)  E' = VIADDMNMX(E, -gapE, hg)   F' = VIADDMNMX(F, -gapE, hg)
+//                         hg = VIADDMNMX.RELU(h, -gapO, -gapO)  E' = VIADDMNMX(E, -gapE, hg)   F' = VIADDMNMX(F, -gapE, hg)
 //   first maximum     ssw.c moves its best score only when a column's maximum is STRICTLY greater than everything before it,
 //                     and takes the SMALLEST read index of that column: the arg-max is the lexicographic maximum of
 //                     (H, -column, -row).  The tag in the low byte is 2 * (63 - step) + (1 - row parity), the fold orders row
@@ -134,11 +134,11 @@ struct AffineLane {
             {                                                             \
                 const uint32_t mold = M[R];                               \
                 const uint32_t h1 = max2_2(addmax2_relu(dOld, SA, E[R]), fA);      /* column A */ \
-                const uint32_t g1 = addmax2_relu(h1, NGO2, 0u);           \
+                const uint32_t g1 = addmax2_relu(h1, NGO2, NGO2);      /* max(h - go, -go, 0): a zero operand would be re-made (PRMT) every time */           \
                 const uint32_t e1 = addmax2(E[R], NGE2, g1);              \
                 fA = addmax2(fA, NGE2, g1);                               \
                 const uint32_t h2 = max2_2(addmax2_relu(uA, SB, e1), fB);          /* column B */ \
-                const uint32_t g2 = addmax2_relu(h2, NGO2, 0u);           \
+                const uint32_t g2 = addmax2_relu(h2, NGO2, NGO2);           \
                 E[R] = addmax2(e1, NGE2, g2);                             \
                 fB = addmax2(fB, NGE2, g2);                               \
                 K[(R) >> 1] = max3_2(K[(R) >> 1], h1 + (tagA + (1 - ((R) & 1)) * 0x00010001u), \
