@@ -532,7 +532,7 @@ def main():
                "h2d_bytes_per_step": int(ascii_np.nbytes + offs_np.nbytes), "d2h_bytes_per_step": int(got * 16),
                "ms_per_step": 1e3 * t_e2e / args.steps, "contexts": depth, "pieces": args.e2e_pieces, "hits_per_step": int(got),
                "host_ms_per_call": {k: 1e3 * float(np.mean([tm[k + "_s"] for tm in tms])) for k in ("upload", "find", "fetch")},
-               "upload_alone_ms": upload_alone_ms,
+               "first_upload_ms": upload_alone_ms,      # first lsw_upload_reads of the context: includes its device allocations
                # between consecutive completions the pipeline is full (the timed region above also pays for filling and draining
                # it: the first upload and the last download of the K steps overlap nothing)
                "steady_state_ms_per_step": 1e3 * (done_at[-1] - done_at[0]) / (len(done_at) - 1) if len(done_at) > 1 else None,
