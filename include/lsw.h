@@ -240,6 +240,11 @@ const char* lsw_pool_last_error(const lsw_pool* pool);      /* pool may be NULL:
  * lsw_find_all) and the record format of the hit buffers */
 int  lsw_pool_configure(lsw_pool* pool, int match, int mismatch, int gap, int gap_ext, int n_queries, const uint8_t* concat,
                         const int32_t* offs, double identity_threshold, int allowed_overlap, int hit_format);
+/* the same for the default (scikit-bio StripedSmithWaterman) seeding branch: lsw_set_ssw instead of lsw_set_scoring.  In the 16-byte
+ * records of this branch `mismatches` holds the CIGAR columns that are not matches, and the score is not re-derivable: use the wide
+ * records when the score is needed. */
+int  lsw_pool_configure_ssw(lsw_pool* pool, int match, int mismatch, int gap_open, int gap_extend, int n_queries, const uint8_t* concat,
+                            const int32_t* offs, double identity_threshold, int allowed_overlap, int hit_format);
 /* pieces > 1: every device's share of a batch is cut further into that many ranges, which alternate between the device's contexts:
  * a single batch then overlaps its own copies with its own kernels (upload of range k+1 and download of range k-1 under the
  * kernels of range k), and a context only needs room for 1/pieces of the share.  Default 1. */

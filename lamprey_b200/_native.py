@@ -38,7 +38,7 @@ assert HIT16_DT.itemsize == 16
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",
            "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_overlap", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
            "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_set_ssw", "lsw_chain_subreads", "lsw_ssw_subreads", "lsw_host_alloc", "lsw_host_free",
-           "lsw_pool_create", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_pool_configure", "lsw_pool_set_pieces", "lsw_pool_submit", "lsw_pool_wait")
+           "lsw_pool_create", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_pool_configure", "lsw_pool_configure_ssw", "lsw_pool_set_pieces", "lsw_pool_submit", "lsw_pool_wait")
 PAIR_DT = np.dtype([("read", "<i4"), ("start", "<i4"), ("end", "<i4"), ("revcomp", "<i4")])
 SUBREAD_DT = np.dtype([("read", "<i4"), ("start", "<i4"), ("end", "<i4"), ("target_idx", "<i4"), ("direction", "<i4"), ("hit", "<i4")])
 HITS_WIDE, HITS_COMPACT = 0, 1
@@ -87,6 +87,7 @@ def load():
     lib.lsw_pool_last_error.argtypes = [vp]
     lib.lsw_pool_last_error.restype = ctypes.c_char_p
     lib.lsw_pool_configure.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, dbl, i32, i32]
+    lib.lsw_pool_configure_ssw.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, dbl, i32, i32]
     lib.lsw_pool_set_pieces.argtypes = [vp, i32]
     lib.lsw_pool_submit.argtypes = [vp, i64, vp, vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_pool_wait.argtypes = [vp, i64, ctypes.POINTER(i64), vp, vp]
@@ -190,13 +191,19 @@ class Pool(object):
             raise OverflowError(msg)
         raise RuntimeError(msg)
 
-    def configure(self, seqs, threshold, match=2, mismatch=-1, gap=-1, gap_ext=-1, allowed_overlap=None, compact=False, pieces=1):
+    def configure(self, seqs, threshold, match=2, mismatch=-1, gap=-1, gap_ext=-1, allowed_overlap=None, compact=False, pieces=1,
+                  ssw=None):
+        """ssw=(match, mismatch, gap_open, gap_extend): the default (skbio) seeding branch instead of the swalign one."""
         concat, offs = concat_sequences(seqs)
         offs32 = offs.astype(np.int32)
         fmt = HITS_COMPACT if compact else HITS_WIDE
-        self._check(self._lib.lsw_pool_configure(self._h, int(match), int(mismatch), int(gap), int(gap_ext), len(seqs), _ptr(concat),
-                                                 _ptr(offs32), float(threshold), -1 if allowed_overlap is None else int(allowed_overlap),
-                                                 fmt), "lsw_pool_configure")
+        ov = -1 if allowed_overlap is None else int(allowed_overlap)
+        if ssw is not None:
+            self._check(self._lib.lsw_pool_configure_ssw(self._h, int(ssw[0]), int(ssw[1]), int(ssw[2]), int(ssw[3]), len(seqs), _ptr(concat),
+                                                         _ptr(offs32), float(threshold), ov, fmt), "lsw_pool_configure_ssw")
+        else:
+            self._check(self._lib.lsw_pool_configure(self._h, int(match), int(mismatch), int(gap), int(gap_ext), len(seqs), _ptr(concat),
+                                                     _ptr(offs32), float(threshold), ov, fmt), "lsw_pool_configure")
         self._check(self._lib.lsw_pool_set_pieces(self._h, int(pieces)), "lsw_pool_set_pieces")
         self.hit_format = fmt
         self.scoring = (int(match), int(mismatch), int(gap))

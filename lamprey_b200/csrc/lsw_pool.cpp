@@ -226,8 +226,8 @@ void lsw_pool_destroy(lsw_pool* p) {
     delete p;
 }
 
-int lsw_pool_configure(lsw_pool* p, int match, int mismatch, int gap, int gap_ext, int n_queries, const uint8_t* concat,
-                       const int32_t* offs, double thr, int allowed_overlap, int hit_format) {
+static int pool_configure(lsw_pool* p, bool ssw, int match, int mismatch, int gap_a, int gap_b, int n_queries, const uint8_t* concat,
+                          const int32_t* offs, double thr, int allowed_overlap, int hit_format) {
     if (!p) return LSW_E_ARG;
     std::unique_lock<std::mutex> g(p->mu);
     if (!p->live.empty()) { p->err = "lsw_pool_configure: batches are in flight (wait for every ticket first)"; return LSW_E_STATE; }
@@ -235,7 +235,7 @@ int lsw_pool_configure(lsw_pool* p, int match, int mismatch, int gap, int gap_ex
     if (!(thr > 0.0)) { p->err = "identity_threshold must be > 0 (the reference recurses forever otherwise)"; return LSW_E_ARG; }
     p->configured = false;
     for (auto& w : p->workers) {
-        int rc = lsw_set_scoring(w->ctx, match, mismatch, gap, gap_ext);
+        int rc = ssw ? lsw_set_ssw(w->ctx, match, mismatch, gap_a, gap_b) : lsw_set_scoring(w->ctx, match, mismatch, gap_a, gap_b);
         if (rc == LSW_OK) rc = lsw_set_queries(w->ctx, n_queries, concat, offs);
         if (rc == LSW_OK) rc = lsw_set_overlap(w->ctx, allowed_overlap);
         if (rc != LSW_OK) { p->err = lsw_last_error(w->ctx); return rc; }
@@ -244,6 +244,16 @@ int lsw_pool_configure(lsw_pool* p, int match, int mismatch, int gap, int gap_ex
     p->hit_format = hit_format;
     p->configured = true;
     return LSW_OK;
+}
+
+int lsw_pool_configure(lsw_pool* p, int match, int mismatch, int gap, int gap_ext, int n_queries, const uint8_t* concat,
+                       const int32_t* offs, double thr, int allowed_overlap, int hit_format) {
+    return pool_configure(p, false, match, mismatch, gap, gap_ext, n_queries, concat, offs, thr, allowed_overlap, hit_format);
+}
+
+int lsw_pool_configure_ssw(lsw_pool* p, int match, int mismatch, int gap_open, int gap_extend, int n_queries, const uint8_t* concat,
+                           const int32_t* offs, double thr, int allowed_overlap, int hit_format) {
+    return pool_configure(p, true, match, mismatch, gap_open, gap_extend, n_queries, concat, offs, thr, allowed_overlap, hit_format);
 }
 
 int lsw_pool_set_pieces(lsw_pool* p, int pieces) {

@@ -234,9 +234,14 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
     pairs = primer_set.sequences()
     names = [n for n, _ in pairs]
     skbio = _use_skbio(args, method)
+    if skbio and devices is not None:
+        if subreads:
+            raise ValueError("subreads=True needs a single device")
+        pool = get_pool(devices)
+        pool.configure([s for _, s in pairs], threshold, allowed_overlap=allowed_overlap, compact=False, ssw=SKBIO_DEFAULTS)
+        hits, counters = _seed_on_pool(pool, concat, offs)
+        return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, counters, qlen=np.array([len(s) for _, s in pairs], np.int64))
     if skbio:
-        if devices is not None:
-            raise NotImplementedError("the skbio seeding path runs on one context (devices= is for the swalign path)")
         eng = engine or _sw.get_engine(device)
         eng.set_ssw(*SKBIO_DEFAULTS)
         eng.set_queries([s for _, s in pairs])

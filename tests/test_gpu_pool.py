@@ -130,3 +130,18 @@ def test_device_subreads_and_processLamplicon_seed_stage():
     with pytest.raises(ValueError):                       # the hits carry no survivor flags
         eng.chain_subreads([0, 1], [1, 0], 0, 1)
     eng.close()
+
+
+def test_skbio_path_over_several_contexts_equals_golden():
+    # the default (StripedSmithWaterman) seeding branch through the pool: one batch split over contexts, gathered in read order
+    devices = list(range(_n_gpus())) if _n_gpus() > 1 else [0, 0]
+    reads = load_reads("1k")
+    ps = seeding.PrimerSet(schema_path("H33"))
+    gold = np.load(__import__("os").path.join(__import__("conftest").GOLD, "seed_1k_H33_70_skbio.npz"))
+    batch = seeding.seed_reads(reads, ps, 0.70, devices=devices, method="skbio")
+    cols = ("read", "query", "start", "end", "matches", "score", "q_pos", "q_end", "depth")
+    got = np.stack([batch.hits[k].astype(np.int32) for k in cols], 1)
+    assert np.array_equal(got, gold["hits"])
+    assert (batch.counters["tasks"], batch.counters["cells"]) == (int(gold["calls"]), int(gold["cells"]))
+    one = seeding.seed_reads(reads, ps, 0.70, method="skbio")
+    assert batch.hits.tobytes() == one.hits.tobytes() and np.array_equal(batch.identity, one.identity)
