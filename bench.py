@@ -237,6 +237,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = 3 * max(cores, 8)        # a few reads per core, so one long read does not set the step time
     kw = dict(synth.CONFIGS[args.workload])
+    kw.pop("chunk", None)
     concat, offs = synth.generate(sample * (args.steps + args.warmup), chunk=sample, **kw)
     reads = synth.reads_as_strings(concat, offs)
     import multiprocessing as mp

@@ -101,9 +101,12 @@ def generate(n_reads, seed=3, mean_len=2000, error=0.08, schema="H33", length_ki
     jobs = [(min(chunk, n_reads - c0), seed, ci, mean_len, error, schema, length_kind, min_len, max_len, adapter_p,
              heads) for ci, c0 in enumerate(range(0, n_reads, chunk))]
     if workers > 1 and len(jobs) > 1:
+        # a ProcessPoolExecutor, not a multiprocessing.Pool: if the kernel's OOM killer takes a worker, the executor raises
+        # BrokenProcessPool, where Pool.map would wait for ever
         import multiprocessing as mp
-        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
-            parts = pool.map(_chunk, jobs)
+        from concurrent.futures import ProcessPoolExecutor
+        with ProcessPoolExecutor(min(workers, len(jobs)), mp_context=mp.get_context("fork")) as pool:
+            parts = list(pool.map(_chunk, jobs))
     else:
         parts = [_chunk(j) for j in jobs]
     concat = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, np.uint8)
@@ -120,10 +123,12 @@ _BARCODES = ["AAGAAAGTTGTCGGTGTCTTTGTG", "TCGATTCCGTTTGTAGTCGTCTGT", "GAGTCTTGTG
 CONFIGS = {
     # BASELINE.json configs[2..4] / SURVEY.md section 8d
     "synth_2kb_8pct": dict(mean_len=2000, error=0.08, min_len=200, max_len=20000, seed=3, schema="H33"),
-    "synth_5kb_12pct": dict(mean_len=5000, error=0.12, min_len=500, max_len=50000, seed=4, schema="H33"),
+    # (chunk: reads per generator job.  A job holds ~50 bytes per base while it runs: 16384 reads of 35 kb were 27 GB per worker
+    # process, and a dozen workers per rank on a multi-GPU box ran the host out of memory)
+    "synth_5kb_12pct": dict(mean_len=5000, error=0.12, min_len=500, max_len=50000, seed=4, schema="H33", chunk=4096),
     # long-read stress: dense concatemers, one adapter + random barcode at the read head
     "synth_20_50kb_12pct": dict(length_kind="uniform", min_len=20000, max_len=50000, error=0.12, seed=5,
-                                schema="H33", adapter_p=1.0,
+                                schema="H33", adapter_p=1.0, chunk=2048,
                                 heads=[(ONT_RAP_TOP + b).encode() for b in _BARCODES]),
 }
 # schema used with a workload: number of NAMED sequences taken from the schema file (None = all)
