@@ -8,6 +8,11 @@
  *   /root/reference/lamprey.py:563       aligner.align(str(seq), primer)          (ref = read slice, query = primer)
  *   /root/reference/lamprey.py:596-645   findPrimerAlignments   (greedy left/right recursion around the best hit)
  *   /root/reference/lamprey.py:699-733   findAllPrimerAlignments (T, Tc, every schema entry fwd + rc; stable sort)
+ * and, for the rows next to it:
+ *   /root/reference/lamprey.py:17, 572-593   from skbio.alignment import StripedSmithWaterman; alignSequence_skbio (default branch)
+ *   /root/reference/lamprey.py:859-998       removeOverlappingPrimerAlignments, extractAmpliconAroundTarget
+ *   /root/reference/lamprey.py:1566-1669     processLamplicon stage 1 (sub-reads) and stage 2 (sub-read vs target reference)
+ *   /root/reference/lamprey.py:2182-2207     reads dealt over worker processes, results collected from a queue
  *
  * so the entry points below are what a replacement `swalign` module (lib/swalign.py in this
  * repo; binding stub in INTEGRATION.md) binds through ctypes.  Plain pointers and sizes only;

@@ -1,8 +1,13 @@
-"""lamprey_b200 -- B200-native batched Smith-Waterman seeding engine for LAMPrey's seed stage.
+"""lamprey_b200 -- B200-native batched Smith-Waterman engine for LAMPrey's seed stage and the rows next to it.
 
 swalign   : drop-in for the third-party `swalign` module (LocalAlignment.align + batched forms)
-seeding   : mirror of lamprey.py's PrimerSet / rc / findPrimerAlignments / findAllPrimerAlignments
-_native   : ctypes binding of liblsw.so (C ABI in include/lsw.h)
+skbio_ssw : drop-in for `skbio.alignment.StripedSmithWaterman` as LAMPrey uses it (default seeding branch, stage 2)
+seeding   : mirrors of lamprey.py's PrimerSet / rc / alignSequence_* / findPrimerAlignments / findAllPrimerAlignments,
+            and the batched seed_reads (one or several GPUs), seed_stream, seed_fastq
+chain     : host mirrors of removeOverlappingPrimerAlignments / extractAmpliconAroundTarget
+pipeline  : processLamplicon's seed stage and stage 2 as batched calls
+fastq     : FASTQ -> (bases, offsets) without Biopython
+_native   : ctypes binding of liblsw.so (C ABI in include/lsw.h): Engine (one context), Pool (several contexts / GPUs)
 synth     : synthetic ONT-like concatemer reads for tests and bench
 """
-__all__ = ["swalign", "seeding", "synth"]
+__all__ = ["swalign", "skbio_ssw", "seeding", "chain", "pipeline", "fastq", "synth"]
