@@ -51,9 +51,19 @@ struct Batch {                       // one lsw_pool_submit
     int left = 0;
 };
 
-struct DeviceLocks { std::mutex h2d, gpu, d2h; };
+// Per device: uploads and lsw_find_all calls run one at a time AND in submission order (a turnstile each: a job takes its number at
+// submit).  Plain mutexes let the second of two batches submitted back to back overtake the first at the very first lock, after
+// which the caller -- who waits for tickets in order -- sat on a finished batch while the pipeline ran dry.
+struct DeviceLocks {
+    std::mutex m;
+    std::condition_variable cv;
+    int64_t issued = 0, next_h2d = 0, next_gpu = 0;
+    std::mutex d2h;
+    void enter(int64_t& turn, int64_t seq) { std::unique_lock<std::mutex> g(m); cv.wait(g, [&] { return turn == seq; }); }
+    void leave(int64_t& turn) { { std::lock_guard<std::mutex> g(m); turn++; } cv.notify_all(); }
+};
 
-struct Job { std::shared_ptr<Batch> b; int range = 0; };
+struct Job { std::shared_ptr<Batch> b; int range = 0; int64_t seq = 0; };
 
 }  // namespace
 
@@ -96,25 +106,25 @@ void run_job(lsw_pool* p, lsw_pool::Worker* w, const Job& job) {
     lsw_counters cnt;
     std::memset(&cnt, 0, sizeof cnt);
     double t_up = 0, t_find = 0, t_fetch = 0, t_wait = 0;
+    L.enter(L.next_h2d, job.seq);
     if (hi > lo) {
-        {
-            std::lock_guard<std::mutex> g(L.h2d);
-            const double t0 = now_s();
-            rc = lsw_set_read_base(w->ctx, lo);
-            if (rc == LSW_OK) rc = lsw_upload_reads(w->ctx, hi - lo, b.ascii, b.offs + lo);
-            t_up = now_s() - t0;
-        }
-        if (rc == LSW_OK) {
-            std::lock_guard<std::mutex> g(L.gpu);
-            const double t0 = now_s();
-            rc = lsw_find_all(w->ctx, p->thr, &nh, &cnt);
-            if (rc == LSW_E_OVERFLOW) {              // the device-side hit buffer was too small: once more with room for the count
-                if (lsw_set_hit_capacity(w->ctx, nh + 1024) == LSW_OK) rc = lsw_find_all(w->ctx, p->thr, &nh, &cnt);
-                lsw_set_hit_capacity(w->ctx, 0);
-            }
-            t_find = now_s() - t0;
-        }
+        const double t0 = now_s();
+        rc = lsw_set_read_base(w->ctx, lo);
+        if (rc == LSW_OK) rc = lsw_upload_reads(w->ctx, hi - lo, b.ascii, b.offs + lo);
+        t_up = now_s() - t0;
     }
+    L.leave(L.next_h2d);
+    L.enter(L.next_gpu, job.seq);
+    if (hi > lo && rc == LSW_OK) {
+        const double t0 = now_s();
+        rc = lsw_find_all(w->ctx, p->thr, &nh, &cnt);
+        if (rc == LSW_E_OVERFLOW) {              // the device-side hit buffer was too small: once more with room for the count
+            if (lsw_set_hit_capacity(w->ctx, nh + 1024) == LSW_OK) rc = lsw_find_all(w->ctx, p->thr, &nh, &cnt);
+            lsw_set_hit_capacity(w->ctx, 0);
+        }
+        t_find = now_s() - t0;
+    }
+    L.leave(L.next_gpu);
     int64_t before = 0;
     {
         // the gather: this range's hits start where the ranges before it end
@@ -297,6 +307,7 @@ int lsw_pool_submit(lsw_pool* p, int64_t n, const uint8_t* ascii, const int64_t*
         for (int r = 0; r < R; r++) {
             Job j; j.b = b; j.range = r;
             const int d = r % D, slot = (int)(((b->ticket - 1) + r / D) % p->per_dev);
+            j.seq = p->locks[d]->issued++;           // (under p->mu: the order of submission)
             p->workers[(size_t)d * p->per_dev + slot]->q.push_back(j);
         }
         *ticket = b->ticket;
