@@ -222,11 +222,12 @@ def ncu_capture():
         return None
 
 
-def workload_reads(workload, n_reads, rank, workers):
+def workload_reads(workload, n_reads, rank, workers, world=1):
     from lamprey_b200 import synth
     kw = dict(synth.CONFIGS[workload])
     kw["seed"] = kw["seed"] + 1000 * rank            # every rank seeds its own batch (weak scaling)
-    return synth.generate(n_reads, workers=workers, **kw)
+    # all ranks of a box generate at the same time: each keeps its jobs in flight within its share of half the free host memory
+    return synth.generate(n_reads, workers=workers, mem_share=0.5 / max(1, world), **kw)
 
 
 def run_reference(args):
@@ -346,9 +347,9 @@ def main():
     from lamprey_b200 import synth
 
     # ---- everything that forks happens before CUDA is touched -------------------------------
-    concat, offs = workload_reads(args.workload, args.reads, rank, workers)
+    concat, offs = workload_reads(args.workload, args.reads, rank, workers, world)
     extra_specs = [] if args.no_extra else [("synth_5kb_12pct", args.extra_reads_5kb), ("synth_20_50kb_12pct", args.extra_reads_long)]
-    extra_reads = [(wl, n) + workload_reads(wl, n, rank, workers) for wl, n in extra_specs]
+    extra_reads = [(wl, n) + workload_reads(wl, n, rank, workers, world) for wl, n in extra_specs]
     from lamprey_b200 import seeding
     ps = seeding.PrimerSet(SCHEMA)
     seqs = [s for _, s in synth.schema_sequences(ps, args.workload)]

@@ -90,14 +90,41 @@ def _chunk(args):
     return out, new_len
 
 
+def _mem_available():
+    try:
+        with open("/proc/meminfo") as fp:
+            for line in fp:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return None
+
+
+JOB_BYTES_PER_BASE = 56        # peak of _chunk: int32 read ids, three int64 index arrays, float32 draws, masks, the two texts
+
+
+def workers_that_fit(workers, chunk, mean_read_len, mem_share):
+    """The worker count capped so that the jobs in flight stay within `mem_share` of the host's available memory."""
+    avail = _mem_available()
+    if avail is None or not mem_share:
+        return workers
+    per_job = JOB_BYTES_PER_BASE * chunk * mean_read_len
+    return int(max(1, min(workers, (avail * mem_share) // max(1, per_job))))
+
+
 def generate(n_reads, seed=3, mean_len=2000, error=0.08, schema="H33", length_kind="gamma", min_len=200,
-             max_len=20000, adapter_p=0.5, heads=None, chunk=16384, workers=1):
+             max_len=20000, adapter_p=0.5, heads=None, chunk=16384, workers=1, mem_share=None):
     """-> (uint8 ASCII concat, int64 offsets[n+1]).  heads: optional list of byte strings, one of which
     (uniformly) replaces the ONT adapter at the read head (config 5 injects barcode + adapter).
     Each chunk of reads has its own PCG64 stream seeded by (seed, chunk index), so the result does
-    not depend on `workers`.  workers > 1 forks a pool: call it BEFORE initialising CUDA."""
+    not depend on `workers`.  workers > 1 forks a pool: call it BEFORE initialising CUDA.  mem_share: fraction of the host's
+    available memory the jobs in flight may take (several ranks generate at once on a multi-GPU box); fewer workers run if more
+    would not fit."""
     if heads is None:
         heads = [ONT_RAP_TOP.encode()]
+    if workers > 1 and mem_share:
+        workers = workers_that_fit(workers, min(chunk, n_reads), mean_len if length_kind == "gamma" else (min_len + max_len) / 2.0, mem_share)
     jobs = [(min(chunk, n_reads - c0), seed, ci, mean_len, error, schema, length_kind, min_len, max_len, adapter_p,
              heads) for ci, c0 in enumerate(range(0, n_reads, chunk))]
     if workers > 1 and len(jobs) > 1:
