@@ -260,6 +260,28 @@ int  lsw_pool_submit(lsw_pool* pool, int64_t n_reads, const uint8_t* ascii, cons
  * for the ranges that did not fit); counters = sums over the ranges, ms_* = device time per device (mean over devices). */
 int  lsw_pool_wait(lsw_pool* pool, int64_t ticket, int64_t* n_hits, lsw_counters* counters, lsw_pool_times* times);
 
+/* ---- Host side: FASTQ ingest and the per-read view of a hit list (no CUDA; lsw_hostops.cpp) ---------------------------
+ * The reference reads its input with Biopython -- SeqIO.parse(fn, "fastq"), /root/reference/lamprey.py:2145-2155; one delivered
+ * file at a time in online mode, lamprey.py:451-507 -- and hands str(record.seq) to every align() call.  lsw_fastq_index scans
+ * the bytes of a FASTQ file (4-line records; LF or CRLF; final newline optional; `threads` <= 0: one per core, at most 32) and
+ * lsw_fastq_extract writes exactly what lsw_upload_reads / lsw_pool_submit take: the concatenated read text and n + 1 offsets.
+ * name_spans (may be NULL) receives [n][2] byte ranges of `data` holding each record's id (the title after '@' up to the first
+ * white space: Biopython's record.id).  `data` must stay valid until lsw_fastq_free.  A malformed file (line count not a multiple
+ * of 4, no '@' / '+', quality and sequence of different length -- what Biopython raises ValueError for) is LSW_E_ARG with the
+ * line or record number in lsw_host_last_error(). */
+typedef struct lsw_fastq lsw_fastq;
+int  lsw_fastq_index(const uint8_t* data, int64_t size, int threads, lsw_fastq** out, int64_t* n_reads, int64_t* n_bases);
+int  lsw_fastq_extract(const lsw_fastq* fq, uint8_t* ascii_out, int64_t* offs_out /* n + 1 */, int64_t* name_spans);
+void lsw_fastq_free(lsw_fastq* fq);
+/* 16-byte hit records -> 32-byte records (end, score and the survivor flag re-derived as described at lsw_hit16). */
+int  lsw_expand_hits(const lsw_hit16* in, int64_t n, int match, int mismatch, int gap, lsw_hit* out, int threads);
+/* What findAllPrimerAlignments returns per read next to its hits (lamprey.py:722-731), for a whole sorted hit list of either
+ * record format: offsets[r] .. offsets[r + 1] are the hits of read read_base + r (n_reads + 1 entries), covered[r] (may be NULL)
+ * is the sum of (end - start) over them -- the numerator of the read's alignment coverage. */
+int  lsw_hits_index(const void* hits, int64_t n, int hit_format, int64_t n_reads, int64_t read_base, int64_t* offsets,
+                    int64_t* covered, int threads);
+const char* lsw_host_last_error(void);                  /* of the calling thread's last failed call of this group */
+
 #ifdef __cplusplus
 }
 #endif

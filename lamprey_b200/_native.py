@@ -38,7 +38,8 @@ assert HIT16_DT.itemsize == 16
 SYMBOLS = ("lsw_create", "lsw_destroy", "lsw_last_error", "lsw_set_stream", "lsw_set_scoring", "lsw_set_queries",
            "lsw_upload_reads", "lsw_align_tasks", "lsw_set_read_base", "lsw_set_overlap", "lsw_set_hit_capacity", "lsw_find_all", "lsw_fetch_hits",
            "lsw_measure_int_peak", "lsw_version", "lsw_fetch_hits_compact", "lsw_set_ssw", "lsw_chain_subreads", "lsw_ssw_subreads", "lsw_host_alloc", "lsw_host_free",
-           "lsw_pool_create", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_pool_configure", "lsw_pool_configure_ssw", "lsw_pool_set_pieces", "lsw_pool_submit", "lsw_pool_wait")
+           "lsw_pool_create", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_pool_configure", "lsw_pool_configure_ssw", "lsw_pool_set_pieces", "lsw_pool_submit", "lsw_pool_wait",
+           "lsw_fastq_index", "lsw_fastq_extract", "lsw_fastq_free", "lsw_expand_hits", "lsw_hits_index", "lsw_host_last_error")
 PAIR_DT = np.dtype([("read", "<i4"), ("start", "<i4"), ("end", "<i4"), ("revcomp", "<i4")])
 SUBREAD_DT = np.dtype([("read", "<i4"), ("start", "<i4"), ("end", "<i4"), ("target_idx", "<i4"), ("direction", "<i4"), ("hit", "<i4")])
 HITS_WIDE, HITS_COMPACT = 0, 1
@@ -91,8 +92,17 @@ def load():
     lib.lsw_pool_set_pieces.argtypes = [vp, i32]
     lib.lsw_pool_submit.argtypes = [vp, i64, vp, vp, vp, i64, ctypes.POINTER(i64)]
     lib.lsw_pool_wait.argtypes = [vp, i64, ctypes.POINTER(i64), vp, vp]
+    lib.lsw_fastq_index.argtypes = [vp, i64, i32, ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.lsw_fastq_extract.argtypes = [vp, vp, vp, vp]
+    lib.lsw_fastq_free.argtypes = [vp]
+    lib.lsw_fastq_free.restype = None
+    lib.lsw_expand_hits.argtypes = [vp, i64, i32, i32, i32, vp, i32]
+    lib.lsw_hits_index.argtypes = [vp, i64, i32, i64, i64, vp, vp, i32]
+    lib.lsw_host_last_error.argtypes = []
+    lib.lsw_host_last_error.restype = ctypes.c_char_p
     for name in SYMBOLS:
-        if name not in ("lsw_destroy", "lsw_last_error", "lsw_host_free", "lsw_pool_destroy", "lsw_pool_last_error"):
+        if name not in ("lsw_destroy", "lsw_last_error", "lsw_host_free", "lsw_pool_destroy", "lsw_pool_last_error", "lsw_fastq_free",
+                        "lsw_host_last_error"):
             getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -112,21 +122,37 @@ def concat_sequences(seqs):
     return concat, offs
 
 
-def expand_hits(h16, match=2, mismatch=-1, gap=-1):
-    """lsw_hit16 records -> HIT_DT records (end, score and the survivor flag are re-derived: see include/lsw.h)."""
-    out = np.zeros(len(h16), HIT_DT)
-    m = (h16["matches"] & 0x7F).astype(np.int32)
-    x = h16["mismatches"].astype(np.int32)
-    span = h16["span"].astype(np.int32)
-    qspan = h16["q_end"].astype(np.int32) - h16["q_pos"]
-    a = span + qspan - m - x                      # aligned (M) columns
-    out["read"] = h16["read"]; out["start"] = h16["start"]; out["end"] = h16["start"].astype(np.int64) + span
-    out["query"] = h16["query"]; out["depth"] = np.minimum(h16["depth"], 32767)
-    out["matches"] = m; out["mismatches"] = x
-    out["score"] = match * m + mismatch * (a - m) + gap * ((span - a) + (qspan - a))
-    out["q_pos"] = h16["q_pos"]; out["q_end"] = h16["q_end"]
-    out["reserved"] = h16["matches"] >> 7
+def _host_check(lib, rc, what):
+    if rc != LSW_OK:
+        raise ValueError("%s failed (%d): %s" % (what, rc, lib.lsw_host_last_error().decode()))
+
+
+def expand_hits(h16, match=2, mismatch=-1, gap=-1, threads=0):
+    """lsw_hit16 records -> HIT_DT records (end, score and the survivor flag are re-derived: see include/lsw.h); lsw_expand_hits,
+    all host cores."""
+    lib = load()
+    h16 = np.ascontiguousarray(h16, HIT16_DT)
+    out = np.empty(len(h16), HIT_DT)
+    _host_check(lib, lib.lsw_expand_hits(_ptr(h16), len(h16), int(match), int(mismatch), int(gap), _ptr(out), int(threads)), "lsw_expand_hits")
     return out
+
+
+def hits_index(hits, n_reads, read_base=0, threads=0):
+    """-> (offsets int64[n_reads + 1], covered int64[n_reads]) of a hit list sorted by read, in either record format
+    (lsw_hits_index): read r's hits are hits[offsets[r]:offsets[r + 1]], covered[r] = sum of (end - start) over them."""
+    lib = load()
+    if hits.dtype == HIT16_DT:
+        fmt = HITS_COMPACT
+    elif hits.dtype == HIT_DT:
+        fmt = HITS_WIDE
+    else:
+        raise TypeError("hits must be HIT_DT or HIT16_DT records")
+    hits = np.ascontiguousarray(hits)
+    offsets = np.empty(int(n_reads) + 1, np.int64)
+    covered = np.empty(int(n_reads), np.int64)
+    _host_check(lib, lib.lsw_hits_index(_ptr(hits), len(hits), fmt, int(n_reads), int(read_base), ctypes.c_void_p(offsets.ctypes.data),
+                                        _ptr(covered), int(threads)), "lsw_hits_index")
+    return offsets, covered
 
 
 class PinnedArray(object):

@@ -108,16 +108,24 @@ class SeedBatch(object):
         self.names = names
         self.counters = counters
         self.read_lengths = read_lengths
-        self.offsets = np.searchsorted(hits["read"], np.arange(n_reads + 1)).astype(np.int64)
-        if qlen is not None:          # skbio path: float(matches)/float(len(primer)), lamprey.py:585
-            self.identity = hits["matches"] / qlen[hits["query"]].astype(np.float64)
-        else:
-            tot = (hits["matches"].astype(np.int64) + hits["mismatches"])
-            self.identity = hits["matches"] / np.maximum(tot, 1)        # tot > 0 for every hit
-        covered = np.zeros(n_reads, np.int64)
-        np.add.at(covered, hits["read"], (hits["end"] - hits["start"]).astype(np.int64))
+        self._qlen = qlen
+        self._identity = None
+        # where every read's hits start, and the bases they cover: one multi-threaded pass in the library (lsw_hits_index)
+        self.offsets, covered = _native.hits_index(hits, n_reads)
         with np.errstate(divide="ignore", invalid="ignore"):
             self.coverage = covered / read_lengths.astype(np.float64)
+
+    @property
+    def identity(self):
+        """Per hit, in Python doubles as the reference computes it (computed on first use)."""
+        if self._identity is None:
+            hits = self.hits
+            if self._qlen is not None:    # skbio path: float(matches)/float(len(primer)), lamprey.py:585
+                self._identity = hits["matches"] / self._qlen[hits["query"]].astype(np.float64)
+            else:
+                tot = (hits["matches"].astype(np.int64) + hits["mismatches"])
+                self._identity = hits["matches"] / np.maximum(tot, 1)        # tot > 0 for every hit
+        return self._identity
 
     def __len__(self):
         return len(self.offsets) - 1
@@ -147,8 +155,15 @@ class SeedBatch(object):
     def alignments(self, i, pruned=False):
         lo, hi = self.offsets[i], self.offsets[i + 1]
         h = self.hits[lo:hi]
-        return [Alignment(int(x["start"]), int(x["end"]), float(self.identity[lo + k]), self.names[x["query"]])
-                for k, x in enumerate(h) if not pruned or x["reserved"] == 1]
+        if self._identity is not None:
+            ident = self._identity[lo:hi]
+        elif self._qlen is not None:
+            ident = h["matches"] / self._qlen[h["query"]].astype(np.float64)
+        else:
+            ident = h["matches"] / np.maximum(h["matches"].astype(np.int64) + h["mismatches"], 1)
+        start, end, query, keep = h["start"].tolist(), h["end"].tolist(), h["query"].tolist(), h["reserved"].tolist()
+        names = self.names
+        return [Alignment(start[k], end[k], float(ident[k]), names[query[k]]) for k in range(hi - lo) if not pruned or keep[k] == 1]
 
     def __getitem__(self, i):
         """(sorted alignment list, coverage) -- findAllPrimerAlignments' return value for read i."""
