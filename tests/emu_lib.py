@@ -22,17 +22,19 @@ def lib():
     return _lib
 
 
-def find_all(reads, seqs, thr, match=2, mismatch=-1, gap=-1, force_full=False, allowed_overlap=-1, reuse=True):
+def find_all(reads, seqs, thr, match=2, mismatch=-1, gap=-1, force_full=False, allowed_overlap=-1, reuse=True, cap=None):
     rc_, ro = concat_sequences(reads)
     qc, qo = concat_sequences(seqs)
     qo = qo.astype(np.int32)
-    cap = max(1024, int(ro[-1]) // 4)
+    cap = max(1024, int(ro[-1]) // 4) if cap is None else cap
     out = np.zeros(cap, HIT_DT)
     n = ctypes.c_int64(0)
     cnt = np.zeros(8, np.int64)
     rc = lib().lsw_emu_find_all(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc),
                                 _ptr(qo), ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap),
                                 ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt), ctypes.c_int(int(force_full)), ctypes.c_int(int(allowed_overlap)), ctypes.c_int(int(reuse)))
+    if rc == -4 and n.value > cap:       # LSW_E_OVERFLOW: short sequences on low-complexity reads give more than a hit per 4 bases
+        return find_all(reads, seqs, thr, match, mismatch, gap, force_full, allowed_overlap, reuse, cap=n.value + 16)
     if rc:
         raise RuntimeError("lsw_emu_find_all rc=%d" % rc)
     return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), steps=int(cnt[2]), rounds=int(cnt[3]), traced=int(cnt[4]), fallbacks=int(cnt[5]), computed_cells=int(cnt[6]), tier2=int(cnt[7]))
@@ -59,12 +61,12 @@ def align_tasks(reads, seqs, tasks, match=2, mismatch=-1, gap=-1, force_full=Fal
     return out, cig[:used.value]
 
 
-def ssw_find_all(reads, seqs, thr, match=2, mismatch=-3, gap_open=5, gap_extend=2, packed=True):
+def ssw_find_all(reads, seqs, thr, match=2, mismatch=-3, gap_open=5, gap_extend=2, packed=True, cap=None):
     """The default (skbio / SSW) seeding path through the host emulation of lsw_ssw.cuh."""
     rc_, ro = concat_sequences(reads)
     qc, qo = concat_sequences(seqs)
     qo = qo.astype(np.int32)
-    cap = max(1024, int(ro[-1]) // 4)
+    cap = max(1024, int(ro[-1]) // 4) if cap is None else cap
     out = np.zeros(cap, HIT_DT)
     n = ctypes.c_int64(0)
     cnt = np.zeros(4, np.int64)
@@ -72,6 +74,8 @@ def ssw_find_all(reads, seqs, thr, match=2, mismatch=-3, gap_open=5, gap_extend=
     rc = lib().lsw_emu_ssw_find_all(ctypes.c_int64(len(reads)), _ptr(rc_), _ptr(ro), ctypes.c_int(len(seqs)), _ptr(qc), _ptr(qo),
                                     ctypes.c_int(match), ctypes.c_int(mismatch), ctypes.c_int(gap_open), ctypes.c_int(gap_extend),
                                     ctypes.c_double(thr), _ptr(out), ctypes.c_int64(cap), ctypes.byref(n), _ptr(cnt), ctypes.c_int(int(packed)))
+    if rc == -4 and n.value > cap:
+        return ssw_find_all(reads, seqs, thr, match, mismatch, gap_open, gap_extend, packed, cap=n.value + 16)
     if rc:
         raise RuntimeError("lsw_emu_ssw_find_all rc=%d" % rc)
     return out[:n.value], dict(tasks=int(cnt[0]), cells=int(cnt[1]), rounds=int(cnt[2]), tier2=int(cnt[3]))
