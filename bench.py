@@ -20,6 +20,7 @@ Printed JSON line (rank 0): metric reads/s (whole job), plus
                 submit/wait loop, H2D and D2H inside the timed region;
   strong_scaling ONE fixed batch (rank 0's) split over all N GPUs by the pool of rank 0, host-side gather included;
   extra_configs BASELINE.json configs[3] and [4] (5 kb / 12 %; 20-50 kb, 40-sequence schema) with their own timing;
+  host_side     FASTQ scanner / hit-record expansion / per-read index rates of the library's host threads on this box (no GPU work);
   clocks.
 """
 import argparse
@@ -380,7 +381,18 @@ def main():
             cpu_ref = {"n": sample, "py_hits": None, "calls": None, "cells": None}
         cpu_ref["c_rows"] = c_oracle_rows(reads, seqs, args.thr, workers if world > 1 else cores)
 
-    log("inputs generated, CPU legs done")
+    # host side of a FASTQ -> hits run (FASTQ scanner, record expansion, per-read index: lsw_hostops.cpp) on this box's cores
+    host_side = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_host
+            n_hs = min(len(offs) - 1, 200000)
+            host_side = bench_host.measure(concat[:offs[n_hs]], offs[:n_hs + 1], with_numpy=False)
+        except Exception as e:                      # a side figure: never the reason a bench run fails
+            host_side = {"error": repr(e)}
+
+    log("inputs generated, CPU legs done" + ("; host side: %r" % (host_side.get("fastq") or host_side) if host_side else ""))
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -650,7 +662,7 @@ def main():
                 "gpu_launches": acc["launches"],
                 "breakdown_ms_per_step": {k: acc[k] / args.steps for k in ("ms_score", "ms_trace", "ms_other", "ms_total")},
                 "device_bytes": cnt["device_bytes"], "reuse_dropped": cnt["reuse_dropped"],
-                "parity_vs_cpu_sample": parity, "strong_scaling": strong, "extra_configs": extra}
+                "parity_vs_cpu_sample": parity, "strong_scaling": strong, "host_side": host_side, "extra_configs": extra}
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -50,38 +50,49 @@ def numpy_index(h, n_reads):
     return offs, cov
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
-    concat, offs = synth.generate(n, workers=os.cpu_count(), **synth.CONFIGS["synth_2kb_8pct"])
-    path = os.path.join(tempfile.gettempdir(), "bench_host.fastq")
+def measure(concat, offs, with_numpy=True, per=128):
+    """-> dict of timings for the reads (concat, offs): FASTQ scan, record expansion, hit-list index.  per: synthetic hits per read
+    (128 = what a 2 kb concatemer read of the headline workload yields)."""
+    n = len(offs) - 1
+    path = os.path.join(tempfile.gettempdir(), "bench_host_%d.fastq" % os.getpid())
     b = concat.tobytes()
     with open(path, "wb") as fp:
         for i in range(n):
             L = offs[i + 1] - offs[i]
             fp.write(b"@read%d runid=abc ch=%d\n" % (i, i)); fp.write(b[offs[i]:offs[i + 1]]); fp.write(b"\n+\n"); fp.write(b"I" * L); fp.write(b"\n")
-    size = os.path.getsize(path)
-    got = fastq.read_fastq(path)
-    assert (got[0] == concat).all() and (got[1] == offs).all()
-    t_new, t_old = best(lambda: fastq.read_fastq(path)), best(lambda: numpy_fastq(path), 1)
-    per = 128                         # hits per 2 kb concatemer read on the headline workload
+    try:
+        size = os.path.getsize(path)
+        got = fastq.read_fastq(path)
+        assert (got[0] == concat).all() and (got[1] == offs).all()
+        t_new = best(lambda: fastq.read_fastq(path))
+        t_old = best(lambda: numpy_fastq(path), 1) if with_numpy else None
+    finally:
+        os.remove(path)
     N = n * per
     rng = np.random.default_rng(0)
     h = np.zeros(N, _native.HIT16_DT)
     h["read"] = np.repeat(np.arange(n, dtype=np.uint32), per); h["start"] = np.tile(np.arange(per, dtype=np.uint32) * 15, n)
     h["span"] = 24; h["query"] = rng.integers(0, 46, N); h["matches"] = 20; h["mismatches"] = 3; h["q_end"] = 23
     w = _native.expand_hits(h)
-    assert w.tobytes() == numpy_expand(h).tobytes()
-    e_new, e_old = best(lambda: _native.expand_hits(h)), best(lambda: numpy_expand(h), 1)
-    i_new, i_old = best(lambda: _native.hits_index(h, n)), best(lambda: numpy_index(w, n), 1)
+    if with_numpy:
+        assert w.tobytes() == numpy_expand(h).tobytes()
+    e_new, e_old = best(lambda: _native.expand_hits(h)), (best(lambda: numpy_expand(h), 1) if with_numpy else None)
+    i_new, i_old = best(lambda: _native.hits_index(h, n)), (best(lambda: numpy_index(w, n), 1) if with_numpy else None)
     names = ["q%d" % i for i in range(46)]
     sb = best(lambda: seeding.SeedBatch(w, n, np.diff(offs), names, {}))
-    os.remove(path)
-    print(json.dumps({"cores": os.cpu_count(), "reads": n, "fastq_bytes": size, "hits": N,
-                      "fastq": {"native_s": t_new, "numpy_s": t_old, "native_reads_per_s": n / t_new, "native_gb_per_s": size / t_new / 1e9,
-                                "speedup": t_old / t_new},
-                      "expand_hits": {"native_s": e_new, "numpy_s": e_old, "native_mhits_per_s": N / e_new / 1e6, "speedup": e_old / e_new},
-                      "hits_index": {"native_s": i_new, "numpy_s": i_old, "native_mhits_per_s": N / i_new / 1e6, "speedup": i_old / i_new},
-                      "seedbatch_construct_s": sb}))
+    sp = (lambda old, new: old / new if old else None)
+    return {"cores": os.cpu_count(), "reads": n, "fastq_bytes": size, "hits": N,
+            "fastq": {"native_s": t_new, "numpy_s": t_old, "native_reads_per_s": n / t_new, "native_gb_per_s": size / t_new / 1e9,
+                      "speedup": sp(t_old, t_new)},
+            "expand_hits": {"native_s": e_new, "numpy_s": e_old, "native_mhits_per_s": N / e_new / 1e6, "speedup": sp(e_old, e_new)},
+            "hits_index": {"native_s": i_new, "numpy_s": i_old, "native_mhits_per_s": N / i_new / 1e6, "speedup": sp(i_old, i_new)},
+            "seedbatch_construct_s": sb}
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+    concat, offs = synth.generate(n, workers=os.cpu_count(), **synth.CONFIGS["synth_2kb_8pct"])
+    print(json.dumps(measure(concat, offs)))
 
 
 if __name__ == "__main__":
