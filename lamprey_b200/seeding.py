@@ -217,15 +217,21 @@ def get_pool(devices, contexts_per_device=1):
     return pool
 
 
-def _seed_on_pool(pool, concat, offs, hit_cap=None):
-    """One batch through a configured pool: submit, wait, enlarge the hit buffer once if it was too small."""
+def _seed_on_pool(pool, concat, offs, hit_cap=None, hit_buffer=None):
+    """One batch through a configured pool: submit, wait, enlarge the hit buffer once if it was too small.
+    hit_buffer: a caller-owned array of pool.hit_dtype records the hits are downloaded into (page-locked memory --
+    _native.PinnedArray -- makes the download run at PCIe speed); the returned compact hits are expanded into new memory,
+    wide ones are a view of it."""
     cap = int(hit_cap or (len(concat) // 8 + 4096))
+    if hit_buffer is not None and (hit_buffer.dtype != pool.hit_dtype or hit_buffer.ndim != 1 or not hit_buffer.flags["C_CONTIGUOUS"]):
+        raise ValueError("hit_buffer must be a contiguous 1-d array of %d-byte hit records (%s)" % (pool.hit_dtype.itemsize, pool.hit_dtype.names,))
     while True:
-        out = np.zeros(cap, pool.hit_dtype)
+        out = hit_buffer if hit_buffer is not None and len(hit_buffer) >= 1 else np.zeros(cap, pool.hit_dtype)
         try:
             hits, counters, times = pool.wait(pool.submit(concat, offs, out))
         except OverflowError as e:
             cap = e.needed + 1024
+            hit_buffer = None                            # the caller's buffer was too small for this batch: a pageable one of the right size
             continue
         if pool.hit_format == _native.HITS_COMPACT:
             hits = _native.expand_hits(hits, *pool.scoring)
@@ -234,7 +240,7 @@ def _seed_on_pool(pool, concat, offs, hit_cap=None):
 
 
 def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None, devices=None,
-               compact=True, method=None, args=None, subreads=False):
+               compact=True, method=None, args=None, subreads=False, hit_buffer=None):
     """findAllPrimerAlignments for every read of a batch in one device pass.  allowed_overlap (LAMPrey uses 4,
     lamprey.py:1536) also runs removeOverlappingPrimerAlignments on the device: see SeedBatch.kept.
 
@@ -243,7 +249,11 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
     worker processes (lamprey.py:2182-2207).  The result is identical to the single-device one.
 
     method="skbio" (or an `args` whose .swalign is False, the reference's default) seeds with scikit-bio's
-    StripedSmithWaterman semantics instead of swalign's (lamprey.py:572-593): hits then carry identity = matches / len(primer)."""
+    StripedSmithWaterman semantics instead of swalign's (lamprey.py:572-593): hits then carry identity = matches / len(primer).
+
+    With `devices`, the PCIe copies run at full speed when the read arrays and `hit_buffer` (records of _native.HIT16_DT with
+    compact=True, the default, else _native.HIT_DT) lie in page-locked memory: fastq.read_fastq(path, pinned=True) and
+    _native.PinnedArray(n, dtype).array provide both."""
     from . import swalign as _sw
     concat, offs = _read_arrays(reads)
     pairs = primer_set.sequences()
@@ -254,7 +264,7 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
             raise ValueError("subreads=True needs a single device")
         pool = get_pool(devices)
         pool.configure([s for _, s in pairs], threshold, allowed_overlap=allowed_overlap, compact=False, ssw=SKBIO_DEFAULTS)
-        hits, counters = _seed_on_pool(pool, concat, offs)
+        hits, counters = _seed_on_pool(pool, concat, offs, hit_buffer=hit_buffer)
         return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, counters, qlen=np.array([len(s) for _, s in pairs], np.int64))
     if skbio:
         eng = engine or _sw.get_engine(device)
@@ -278,7 +288,7 @@ def seed_reads(reads, primer_set, threshold, aligner=None, device=0, engine=None
         pool = get_pool(devices)
         sc = _scoring_of(aligner)
         pool.configure([s for _, s in pairs], threshold, *sc, allowed_overlap=allowed_overlap, compact=compact)
-        hits, counters = _seed_on_pool(pool, concat, offs)
+        hits, counters = _seed_on_pool(pool, concat, offs, hit_buffer=hit_buffer)
         return SeedBatch(hits, len(offs) - 1, np.diff(offs), names, counters)
     eng = engine or _sw.get_engine(device)
     if aligner is not None:
@@ -332,15 +342,53 @@ def seed_stream(batches, primer_set, threshold, aligner=None, devices=(0,), allo
         yield finish(inflight.pop(0))
 
 
-def seed_fastq(path, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None, with_names=False):
+def _unpin(got):
+    """(PinnedArray, PinnedArray, ...) of fastq.read_fastq(pinned=True) -> the arrays, plus the objects that keep them alive."""
+    return (got[0].array, got[1].array), (got[0], got[1])
+
+
+def seed_fastq(path, primer_set, threshold, aligner=None, device=0, engine=None, allowed_overlap=None, with_names=False,
+               devices=None, method=None, args=None, pinned=False, hit_buffer=None):
     """Seed one FASTQ file as one batch -- what the online FastqHandler.process_file does per file
-    (/root/reference/lamprey.py:451-507) and the offline loader per run (lamprey.py:2145-2155), without Biopython.
-    -> SeedBatch [, read names]."""
+    (/root/reference/lamprey.py:451-507) and the offline loader per run (lamprey.py:2145-2155), without Biopython: the
+    library's scanner cuts the file's bytes into the (text, offsets) pair the upload takes (fastq.read_fastq).
+    pinned=True parses straight into page-locked memory.  -> SeedBatch [, read names]."""
     from . import fastq as _fastq
-    got = _fastq.read_fastq(path, with_names=with_names)
-    batch = seed_reads((got[0], got[1]), primer_set, threshold, aligner=aligner, device=device, engine=engine,
-                       allowed_overlap=allowed_overlap)
+    got = _fastq.read_fastq(path, with_names=with_names, pinned=pinned)
+    arrays, keep = _unpin(got) if pinned else ((got[0], got[1]), None)
+    batch = seed_reads(arrays, primer_set, threshold, aligner=aligner, device=device, engine=engine,
+                       allowed_overlap=allowed_overlap, devices=devices, method=method, args=args, hit_buffer=hit_buffer)
+    if keep is not None:
+        batch.read_lengths = np.array(batch.read_lengths)          # (np.diff made a copy already; nothing else refers to the pinned arrays)
+        for k in keep:
+            k.close()
     return (batch, got[2]) if with_names else batch
+
+
+def seed_fastq_files(paths, primer_set, threshold, aligner=None, devices=(0,), allowed_overlap=None, compact=True, depth=2,
+                     pinned=False):
+    """A run of FASTQ files, one batch per file, in order -- the online mode's stream of delivered files (lamprey.py:451-507):
+    file k + 1 is parsed (all host cores) and uploaded while file k is being seeded.  Yields (path, SeedBatch)."""
+    from . import fastq as _fastq
+    paths = list(paths)
+    keep = []
+
+    def batches():
+        for p in paths:
+            got = _fastq.read_fastq(p, pinned=pinned)
+            if pinned:
+                arrays, objs = _unpin(got)
+                keep.append(objs)
+                yield arrays
+            else:
+                yield got
+    for k, batch in enumerate(seed_stream(batches(), primer_set, threshold, aligner=aligner, devices=devices,
+                                          allowed_overlap=allowed_overlap, compact=compact, depth=depth)):
+        if pinned:                                       # batch k is done: nothing reads its page-locked text any more
+            for o in keep[k]:
+                o.close()
+            keep[k] = None
+        yield paths[k], batch
 
 
 def alignSequence_swalign(aligner, seq, primer, primer_name):

@@ -145,3 +145,45 @@ def test_skbio_path_over_several_contexts_equals_golden():
     assert (batch.counters["tasks"], batch.counters["cells"]) == (int(gold["calls"]), int(gold["cells"]))
     one = seeding.seed_reads(reads, ps, 0.70, method="skbio")
     assert batch.hits.tobytes() == one.hits.tobytes() and np.array_equal(batch.identity, one.identity)
+
+
+def test_fastq_files_to_hits_through_the_library(tmp_path):
+    # FASTQ files -> hits with nothing but library code in between: the multi-threaded scanner (lsw_fastq_*), page-locked text and
+    # hit buffers, the pool's double buffering, the per-read index (lsw_hits_index); against the golden seeding result
+    reads = load_reads("1k")
+    ps = seeding.PrimerSet(schema_path("H33"))
+    gold = load_seed_golden("1k", "H33", 0.75)
+    cuts = [0, 1, 400, 400, 1000]                          # one file holds a single read, one is empty
+    paths = []
+    for k in range(len(cuts) - 1):
+        p = tmp_path / ("f%d.fastq" % k)
+        with open(p, "w") as fp:
+            for i in range(cuts[k], cuts[k + 1]):
+                fp.write("@read%d ch=%d\n%s\n+\n%s\n" % (i, i, reads[i], "I" * len(reads[i])))
+        paths.append(str(p))
+    G = hits_matrix_gold = gold["hits"]
+    for pinned in (False, True):
+        got = list(seeding.seed_fastq_files(paths, ps, 0.75, devices=[0], pinned=pinned))
+        assert [p for p, _ in got] == paths
+        for k, (_, b) in enumerate(got):
+            want = G[(G[:, 0] >= cuts[k]) & (G[:, 0] < cuts[k + 1])].copy()
+            want[:, 0] -= cuts[k]
+            assert len(b) == cuts[k + 1] - cuts[k] and np.array_equal(hits_matrix(b.hits), want)
+            assert np.array_equal(b.coverage, gold["coverage"][cuts[k]:cuts[k + 1]])
+    # one file as one batch, parsed into page-locked memory, hits downloaded into a caller-owned page-locked buffer
+    whole = tmp_path / "all.fastq"
+    with open(whole, "w") as fp:
+        for i, r in enumerate(reads):
+            fp.write("@read%d\n%s\n+\n%s\n" % (i, r, "#" * len(r)))
+    buf = _native.PinnedArray(len(G) + 100, _native.HIT16_DT)
+    batch, names = seeding.seed_fastq(str(whole), ps, 0.75, devices=[0], pinned=True, hit_buffer=buf.array, with_names=True)
+    assert np.array_equal(hits_matrix(batch.hits), G) and np.array_equal(batch.coverage, gold["coverage"])
+    assert names[999] == "read999" and len(names) == 1000
+    assert batch[3][1] == float(gold["coverage"][3]) and len(batch[3][0]) == int((G[:, 0] == 3).sum())
+    # a caller's buffer that is too small is replaced for that batch, not an error
+    tiny = _native.PinnedArray(10, _native.HIT16_DT)
+    again = seeding.seed_fastq(str(whole), ps, 0.75, devices=[0], hit_buffer=tiny.array)
+    assert again.hits.tobytes() == batch.hits.tobytes()
+    with pytest.raises(ValueError):
+        seeding.seed_fastq(str(whole), ps, 0.75, devices=[0], hit_buffer=np.zeros(10, np.int32))
+    buf.close(); tiny.close()
