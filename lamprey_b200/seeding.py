@@ -152,6 +152,24 @@ class SeedBatch(object):
         """Mask of the hits that survive removeOverlappingPrimerAlignments (needs seed_reads(allowed_overlap=...))."""
         return self.hits["reserved"] == 1
 
+    def target_depth(self, pruned=True):
+        """result.target_depth of processLamplicon for EVERY read of the batch at once (lamprey.py:1547-1549): the number of
+        'T' / 'Tc' hits, after removeOverlappingPrimerAlignments when pruned (needs seed_reads(allowed_overlap=...))."""
+        is_t = np.isin(np.arange(len(self.names)), [k for k, n in enumerate(self.names) if n in ('T', 'Tc')])
+        m = is_t[self.hits["query"]]
+        if pruned:
+            m &= self.kept
+        return np.bincount(self.hits["read"][m], minlength=len(self)).astype(np.int64)
+
+    def num_ont_seqs(self, threshold, pruned=True):
+        """num_ont_seqs of processLamplicon for every read at once (lamprey.py:1551-1553): hits of sequences whose name starts with
+        'ont' and whose identity reaches the threshold."""
+        is_ont = np.array([n.startswith('ont') for n in self.names], bool)
+        m = is_ont[self.hits["query"]] & (self.identity >= threshold)
+        if pruned:
+            m &= self.kept
+        return np.bincount(self.hits["read"][m], minlength=len(self)).astype(np.int64)
+
     def alignments(self, i, pruned=False):
         lo, hi = self.offsets[i], self.offsets[i + 1]
         h = self.hits[lo:hi]

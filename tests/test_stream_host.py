@@ -126,6 +126,13 @@ def test_seed_reads_devices_overlap_flag_and_stream_overflow(emu_device):
             from lamprey_b200 import chain
             want = chain.removeOverlappingPrimerAlignments(False, b.alignments(i), 4)
             assert [(a.start, a.end, a.primer_name) for a in al] == [(a.start, a.end, a.primer_name) for a in want]
+        if compact:                                        # the per-read counts of processLamplicon for the whole batch at once
+            td, no = b.target_depth(), b.num_ont_seqs(0.70)
+            for i in range(len(reads)):
+                al = b.alignments(i, pruned=True)
+                assert td[i] == sum(1 for a in al if a.primer_name in ('T', 'Tc'))
+                assert no[i] == sum(1 for a in al if a.primer_name.startswith('ont') and a.identity >= 0.70)
+            assert td.sum() > 50 and (b.target_depth(pruned=False) >= td).all()
     # seed_stream: a batch whose hits do not fit the default buffer (bases / 8 + 4096 records) is seeded again with room
     dense = ["ACGTA" * 1000] * 14                          # a five-base sequence on its own tandem repeat: a hit every five bases
     class P(object):
