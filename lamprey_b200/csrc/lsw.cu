@@ -100,7 +100,7 @@ struct lsw_ctx {
     std::vector<uint8_t> qcodes;
     std::vector<int32_t> class_of;
     std::vector<int32_t> class_seqs[NCLASS];
-    DevBuf d_qcodes, d_qlen, d_class_seqs[NCLASS], d_cand_ok;
+    DevBuf d_qcodes, d_qlen, d_class_seqs[NCLASS], d_cand_ok, d_wx;
 
     int64_t n_reads = 0, total_bases = 0, codes_bytes = 0;
     std::vector<int32_t> h_rlen;
@@ -125,7 +125,7 @@ struct lsw_ctx {
     bool hits_pruned = false;
     // environment switches, read once in lsw_create
     int env_k2_blocks = 0, env_k2_debug = 0;
-    bool env_debug = false, env_no_reuse = false, env_ssw_scalar = false;        // the sorted hits carry the survivor flag of lsw_set_overlap (lsw_chain_subreads needs it)
+    bool env_debug = false, env_no_reuse = false, env_ssw_scalar = false, env_full_head = false;        // the sorted hits carry the survivor flag of lsw_set_overlap (lsw_chain_subreads needs it)
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -135,7 +135,7 @@ namespace {
 
 // every device buffer of a context (lsw_destroy releases them; lsw_counters.device_bytes sums their capacities)
 std::vector<DevBuf*> all_bufs(lsw_ctx* ctx) {
-    std::vector<DevBuf*> v = {&ctx->d_qcodes, &ctx->d_qlen, &ctx->d_cand_ok, &ctx->d_ascii, &ctx->d_offs_in, &ctx->d_codes,
+    std::vector<DevBuf*> v = {&ctx->d_qcodes, &ctx->d_qlen, &ctx->d_cand_ok, &ctx->d_wx, &ctx->d_ascii, &ctx->d_offs_in, &ctx->d_codes,
                               &ctx->d_roff, &ctx->d_rlen, &ctx->d_order, &ctx->d_order_tmp, &ctx->d_len_tmp[0], &ctx->d_len_tmp[1],
                               &ctx->d_res, &ctx->d_seg[0], &ctx->d_seg[1], &ctx->d_head, &ctx->d_ncand, &ctx->d_counters,
                               &ctx->d_child_flag, &ctx->d_pos, &ctx->d_cubtemp, &ctx->d_scratch, &ctx->d_hits, &ctx->d_hits_sorted,
@@ -179,6 +179,7 @@ void read_env(lsw_ctx* ctx) {
     ctx->env_debug = getenv("LSW_DEBUG") != nullptr;
     ctx->env_no_reuse = getenv("LSW_NO_REUSE") != nullptr;
     ctx->env_ssw_scalar = getenv("LSW_SSW_SCALAR") != nullptr;
+    ctx->env_full_head = getenv("LSW_REUSE_FULL_HEAD") != nullptr;
 }
 
 // ---- small kernels ----------------------------------------------------------------------
@@ -636,6 +637,7 @@ int run_round(lsw_ctx* ctx, const TaskBuf& cur, int segi, const std::vector<int6
         // child tasks: K1 runs on the segment list (own head + warm-started tail), the whole-read blocks in between are looked up
         Span sp(ctx, 2);
         R.t = cur.view(); R.n = n; R.qlen = ctx->d_qlen.as<int32_t>(); R.match = ctx->match; R.g = ctx->g; R.enable = 1;
+        R.wx = ctx->d_wx.as<int32_t>();
         R.blockbest = ctx->d_blockbest.as<uint32_t>(); R.bb_off = ctx->d_bb_off.as<int64_t>(); R.bb_total = ctx->bb_total;
         if (ctx->use_bb1) { R.bb1 = ctx->d_bb1.as<uint32_t>(); R.bb1_off = ctx->d_bb1_off.as<int64_t>(); R.bb1_total = ctx->bb1_total; }
         CK(ctx->d_nseg.ensure((size_t)(n + 1) * 4)); CK(ctx->d_segpos.ensure((size_t)(n + 1) * 4));
@@ -1128,6 +1130,11 @@ int lsw_find_all(lsw_ctx* ctx, double thr, int64_t* n_hits, lsw_counters* counte
     build_cand_ok(ctx->nseq, ctx->qlen.data(), ctx->match, ctx->mismatch, ctx->g, thr, false, tab);
     CK(ctx->d_cand_ok.ensure(tab.size()));
     CK(cudaMemcpyAsync(ctx->d_cand_ok.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+    // head / warm-up length of child slices (lsw_reuse.cuh): only cells that could pass the hit test must be the whole read's cells
+    std::vector<int32_t> wx;
+    build_reuse_wx(ctx->nseq, ctx->qlen.data(), ctx->match, ctx->g, tab, ctx->env_full_head || ctx->ssw, wx);
+    CK(ctx->d_wx.ensure(wx.size() * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(ctx->d_wx.p, wx.data(), wx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
 
     int64_t hit_cap = ctx->hit_cap_user > 0 ? ctx->hit_cap_user : ctx->total_bases / 8 + 4096;
     CK(ctx->d_hits.ensure((size_t)hit_cap * sizeof(lsw_hit)));

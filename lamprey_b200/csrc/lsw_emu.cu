@@ -8,6 +8,7 @@
 // It is built into its own library (liblsw_emu.so) and is never loaded by the product path:
 // lamprey_b200 only opens liblsw.so and fails loudly without a CUDA device.
 #include <cstring>
+#include <cstdlib>
 #include <cstdio>
 #include <vector>
 #include <algorithm>
@@ -248,6 +249,9 @@ void emu_round(Emu& E, TraceParams T) {
     memset(&R, 0, sizeof R);
     R.t = view(E); R.n = n; R.qlen = E.qlen.data(); R.match = E.match; R.g = E.g; R.enable = 1;
     R.blockbest = E.blockbest.data(); R.bb_off = E.bb_off.data(); R.bb_total = E.bb_total;
+    std::vector<int32_t> wx;
+    build_reuse_wx(E.nseq, E.qlen.data(), E.match, E.g, E.cand_ok, getenv("LSW_REUSE_FULL_HEAD") != nullptr, wx);
+    R.wx = wx.data();
     if (E.round == 1 && E.bb1_total > 0) {           // built once, after round 0
         E.bb1.assign((size_t)E.bb1_total * E.nseq, 0u);
         const int64_t nr = (int64_t)E.bb_off.size() - 1;

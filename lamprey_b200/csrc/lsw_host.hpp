@@ -46,5 +46,27 @@ inline void build_cand_ok(int nseq, const int32_t* qlen, int match, int mismatch
     }
 }
 
+// Head / warm-up length of a child slice per sequence (lsw_reuse.cuh, `Wx`).  A child slice [a, b) may take the whole read's
+// values for read columns >= a + Wx if every cell there that MATTERS is the same in both matrices.  Cells that matter are those
+// whose value could pass the hit test, H >= minpass = the smallest score with cand_ok != 0: an alignment with score s >= minpass
+// has at most (match * Q - s) / g deleted read bases (s <= match * Q - g * D), so it spans at most Q + (match * Q - minpass) / g
+// read columns and lies inside the slice once its end is that far from `a` -- the cell then holds the same value, at the same
+// place, in both matrices.  Cells below minpass may differ (the whole read's value can be larger, a warm-started tail's smaller),
+// but they stay below minpass in both, and a task whose best cell is below minpass yields no hit and no children whatever that
+// cell is.  With minpass = 1 this is the a-priori bound Q + match * Q / g (every positive cell exact).
+inline void build_reuse_wx(int nseq, const int32_t* qlen, int match, int g, const std::vector<uint8_t>& cand_ok, bool full,
+                           std::vector<int32_t>& wx) {
+    wx.assign((size_t)nseq, 0);
+    for (int s = 0; s < nseq; s++) {
+        const int Q = qlen[s], top = match * Q;
+        int minpass = top > 0 ? top : 1;                    // nothing can pass: any bound will do
+        for (int score = 1; score < 128 && score <= top; score++)
+            if (cand_ok[(size_t)s * 128 + score]) { minpass = score; break; }
+        if (full) minpass = 1;
+        const int apriori = Q + top / g;
+        const int w = Q + (top - minpass) / g + 1;
+        wx[(size_t)s] = w < apriori ? w : apriori;
+    }
+}
 
 }  // namespace lsw

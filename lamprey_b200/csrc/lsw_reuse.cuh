@@ -12,7 +12,9 @@
 //     TAIL   [te - Wxa, b)      a DP that warms up for Wxa >= Wx columns (not counted) and counts (te, b];
 //                               Wxa is a multiple of the 32-column lane block the segment launches use
 // and the three bests are merged with swalign's tie rule (value, then row, then the LAST column).
-// Everything here is exact; nothing is approximated.  Slices too short to profit are computed directly.
+// In lsw_find_all only cells that could pass the hit test have to be the same cells: Wx shrinks to Q + (M*Q - minpass)/g + 1
+// (lsw_host.hpp build_reuse_wx, with the argument), about 1.9 Q instead of 3 Q for LAMPrey's scoring and thresholds.
+// Everything here is exact for every hit and every child; nothing is approximated.  Slices too short to profit are computed directly.
 #pragma once
 #include "lsw_common.cuh"
 
@@ -35,11 +37,11 @@ struct SegPlan {
 // The last, partial block [te, b) needs no DP when the whole block's best cell lies before b -- it is then also the best
 // of [te, b), last-column tie rule included -- or when the block holds no positive cell at all.
 LSW_HD SegPlan plan_task(int a, int b, int Q, int match, int g, bool enable, const uint32_t* bbrow = nullptr,
-                         int tb = SEG_BLOCK /* lane block of the segment launch */) {
+                         int tb = SEG_BLOCK /* lane block of the segment launch */, int wx = 0 /* head length (build_reuse_wx); 0: a priori */) {
     SegPlan p;
     p.nseg = 1; p.split = false; p.hb = b; p.te = b; p.mid_end = 0; p.ts = 0; p.skip = 0; p.tail = false;
     if (!enable) return p;
-    const int Wx = Q + (match * Q) / g;
+    const int Wx = wx > 0 ? wx : Q + (match * Q) / g;
     const int hb = ((a + Wx + BB_BLOCK - 1) / BB_BLOCK) * BB_BLOCK;
     const int te = (b / BB_BLOCK) * BB_BLOCK;
     if (hb > te) return p;
@@ -79,6 +81,7 @@ struct ReuseParams {
     const int64_t* bb1_off;      // [n_reads + 1] first group of each read
     int64_t bb1_total;
     const uint8_t* cand_ok;      // [n_seq][128]
+    const int32_t* wx;           // [n_seq] head / warm-up length of a child slice (lsw_host.hpp build_reuse_wx); null: the a-priori bound
     const int32_t* class_of;     // [n_seq] register-row class
     uint32_t* cand[16];          // per class: candidate list / sort key
     uint16_t* cand_key[16];
@@ -90,7 +93,8 @@ struct ReuseParams {
 LSW_HD SegPlan plan_of(const ReuseParams& R, int64_t t) {
     const int q = R.t.seq[t];
     return plan_task(R.t.a[t], R.t.b[t], R.qlen[q], R.match, R.g, R.enable != 0,
-                     R.blockbest ? R.blockbest + (size_t)q * R.bb_total + R.bb_off[R.t.read[t]] : nullptr);
+                     R.blockbest ? R.blockbest + (size_t)q * R.bb_total + R.bb_off[R.t.read[t]] : nullptr, SEG_BLOCK,
+                     R.wx ? R.wx[q] : 0);
 }
 
 // K1 needs nothing but the start descriptor of a segment (its results go to res_s[segment], the task list is not read
