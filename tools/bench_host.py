@@ -56,18 +56,19 @@ def measure(concat, offs, with_numpy=True, per=128):
     n = len(offs) - 1
     path = os.path.join(tempfile.gettempdir(), "bench_host_%d.fastq" % os.getpid())
     b = concat.tobytes()
-    with open(path, "wb") as fp:
-        for i in range(n):
-            L = offs[i + 1] - offs[i]
-            fp.write(b"@read%d runid=abc ch=%d\n" % (i, i)); fp.write(b[offs[i]:offs[i + 1]]); fp.write(b"\n+\n"); fp.write(b"I" * L); fp.write(b"\n")
     try:
+        with open(path, "wb") as fp:
+            for i in range(n):
+                L = offs[i + 1] - offs[i]
+                fp.write(b"@read%d runid=abc ch=%d\n" % (i, i)); fp.write(b[offs[i]:offs[i + 1]]); fp.write(b"\n+\n"); fp.write(b"I" * L); fp.write(b"\n")
         size = os.path.getsize(path)
         got = fastq.read_fastq(path)
         assert (got[0] == concat).all() and (got[1] == offs).all()
         t_new = best(lambda: fastq.read_fastq(path))
         t_old = best(lambda: numpy_fastq(path), 1) if with_numpy else None
     finally:
-        os.remove(path)
+        if os.path.exists(path):
+            os.remove(path)
     N = n * per
     rng = np.random.default_rng(0)
     h = np.zeros(N, _native.HIT16_DT)
