@@ -63,15 +63,21 @@ def parse_fastq(data, with_names=False, threads=0, pinned=False):
     return out + ((ReadNames(raw, spans),) if with_names else ())
 
 
-def read_fastq(path, with_names=False, threads=0, pinned=False):
-    """-> (concat uint8, offsets int64[n+1]) [, names].  The FASTQ must use 4-line records; ``.gz`` files are inflated first."""
+def read_fastq(path, with_names=False, threads=0, pinned=False, mmap=True):
+    """-> (concat uint8, offsets int64[n+1]) [, names].  The FASTQ must use 4-line records; ``.gz`` files are inflated first.
+    mmap=False reads the file into memory first instead of mapping it (slower by the copy; use it for a file another process may
+    still truncate or rewrite -- a mapped page that disappears is a bus error, not an exception)."""
+    import os
     if str(path).endswith(".gz"):
         with gzip.open(path, "rb") as fp:
             data = fp.read()
-    else:
-        import os
+    elif not os.path.getsize(path):
+        data = np.zeros(0, np.uint8)
+    elif mmap:
         # mapped, not read: the scanner's threads pull the pages straight from the page cache (np.fromfile costs as much as the parse)
-        data = np.memmap(path, dtype=np.uint8, mode="r") if os.path.getsize(path) else np.zeros(0, np.uint8)
+        data = np.memmap(path, dtype=np.uint8, mode="r")
+    else:
+        data = np.fromfile(path, dtype=np.uint8)
     try:
         return parse_fastq(data, with_names=with_names, threads=threads, pinned=pinned)
     except ValueError as e:

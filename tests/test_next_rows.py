@@ -61,6 +61,8 @@ def test_read_fastq(tmp_path):
         for i, r in enumerate(reads):
             fp.write("@read%d runid=abc ch=%d start_time=2021-02-08T02:45:38Z\n%s\n+\n%s\n" % (i, i, r, "#" * len(r)))
     concat, offs, names = fastq.read_fastq(str(p), with_names=True)
+    c2, o2 = fastq.read_fastq(str(p), mmap=False, threads=2)
+    assert (c2 == concat).all() and (o2 == offs).all()
     assert names[:2] == ["read0", "read1"] and len(offs) == len(reads) + 1
     got = [concat[offs[i]:offs[i + 1]].tobytes().decode() for i in range(len(reads))]
     assert got == reads
