@@ -42,9 +42,14 @@ def make_case(rng):
         seqs.append("".join(COMP[c] for c in reversed(seqs[0])))
     thr = rng.choice([0.5, 0.6, 0.7, 0.7, 0.75, 0.8, 0.9, 0.95])
     reads = []
-    for _ in range(rng.randrange(1, 14)):
+    long_case = rng.random() < 0.08          # a few long reads: slices that span whole groups of blocks (second-level block bests)
+    for _ in range(rng.randrange(1, 14) if not long_case else rng.randrange(1, 3)):
         n = rng.choice([0, 1, 5, 31, 32, 33, 63, 64, 65, 127, 128, 129, 200, 449, 700, 1024, 1500, 3000])
+        if long_case:
+            n = rng.choice([5000, 9000, 20000, 40000])
         kind = rng.random()
+        if long_case and kind >= 0.6:
+            kind = rng.random() * 0.6        # (random reads hold nothing to find)
         if kind < 0.4:                       # concatemer of noisy copies of the sequences
             r, rate = "", rng.choice([0.0, 0.03, 0.08, 0.12, 0.2])
             while len(r) < n:
