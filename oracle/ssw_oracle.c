@@ -284,12 +284,15 @@ typedef struct {
     sswo_stats* st;
     int match, mismatch, gapO, gapE;
     double thr;
+    uint32_t cig[512];      /* CIGAR scratch of the call in progress: nothing reads it after sswo_align() returns, and a frame without
+                               it is ~100 bytes -- exact tandem repeats of a short primer recurse once per copy (thousands deep on a
+                               40 kb read; the reference's Python would have hit its recursion limit long before) */
 } rec_ctx;
 
 static int rec(rec_ctx* cx, const uint8_t* seq, int len, int shift, const uint8_t* primer, int Q, int seq_idx, int depth)
 {
     sswo_result r;
-    uint32_t cig[512];
+    uint32_t* cig = cx->cig;
     if (cx->st) {
         cx->st->calls++; cx->st->cells += (int64_t)len * Q;
         if (depth > cx->st->max_depth) cx->st->max_depth = depth;
@@ -318,7 +321,7 @@ static int rec(rec_ctx* cx, const uint8_t* seq, int len, int shift, const uint8_
 int sswo_find_all(const uint8_t* read, int len, int n_seq, const uint8_t* concat, const int32_t* offs, int match, int mismatch,
                   int gapO, int gapE, double thr, sswo_hit* hits, int64_t cap, int64_t* n_out, sswo_stats* st)
 {
-    rec_ctx cx = { hits, cap, 0, st, match, mismatch, gapO, gapE, thr };
+    rec_ctx cx = { hits, cap, 0, st, match, mismatch, gapO, gapE, thr, {0} };
     for (int s = 0; s < n_seq; s++)
         if (rec(&cx, read, len, 0, concat + offs[s], offs[s + 1] - offs[s], s, 0)) return -1;
     *n_out = cx.n;
