@@ -247,3 +247,23 @@ def test_emu_long_sparse_reads_use_second_level_block_bests():
         assert np.array_equal(hits_matrix(hits), want), reuse
         assert (cnt["tasks"], cnt["cells"]) == (calls, cells)
     assert len(want) > 20
+
+
+def test_emu_recursion_deeper_than_pythons_limit():
+    # exact tandem repeats of a short sequence: the greedy recursion finds one copy per level (swalign keeps the LAST maximum, so
+    # everything else is in the left child; SSW keeps the FIRST, so it is in the right child) -- 1500 levels, where the
+    # reference's Python would raise RecursionError at ~1000.  Both paths, against the C oracles.
+    from oracle import ssw_oracle
+    read, seqs = "ACGTA" * 1500, ["ACGTA", "TACGT"]
+    want, st = c_oracle.find_all(read, seqs, 0.7)
+    want = want[np.argsort(want["start"], kind="stable")]
+    hits, cnt = emu_lib.find_all([read], seqs, 0.7)
+    assert len(hits) == len(want) >= 2000 and cnt["tasks"] == st["calls"] and st["max_depth"] == 1499
+    for a, b in (("query", "seq"), ("start", "start"), ("end", "end"), ("depth", "depth"), ("matches", "matches")):
+        assert (hits[a] == want[b]).all()
+    want, st = ssw_oracle.find_all(read, seqs, 0.7)
+    want = want[np.argsort(want["start"], kind="stable")]
+    hits, cnt = emu_lib.ssw_find_all([read], seqs, 0.7)
+    assert len(hits) == len(want) and cnt["tasks"] == st["calls"] and st["max_depth"] >= 1499
+    for a, b in (("query", "seq"), ("start", "start"), ("end", "end"), ("depth", "depth"), ("matches", "matches")):
+        assert (hits[a] == want[b]).all()
