@@ -353,6 +353,7 @@ int lsw_emu_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* offs,
             if (flag[j]) { nr.push_back(c_read[j]); na.push_back(c_a[j]); nb.push_back(c_b[j]); ns.push_back(c_seq[j]); }
         E.t_read.swap(nr); E.t_a.swap(na); E.t_b.swap(nb); E.t_seq.swap(ns); E.seg.swap(nseg);
         round++;
+        if (round > 30000) return LSW_E_INTERNAL;      // as lsw_find_all: "recursion did not terminate" (lsw_hit.depth is 16 bits)
     }
 #if defined(LSW_EMU_STATS)
     fprintf(stderr, "[emu] mean window columns %.1f; columns touched beyond max_row (histogram -20..40):", (double)g_ncols_sum / (double)(g_walks ? g_walks : 1));
@@ -557,6 +558,7 @@ int lsw_emu_ssw_find_all(int64_t n_reads, const uint8_t* ascii, const int64_t* o
             if (flag[j]) { nr.push_back(c_read[j]); na.push_back(c_a[j]); nb.push_back(c_b[j]); ns.push_back(c_seq[j]); }
         E.t_read.swap(nr); E.t_a.swap(na); E.t_b.swap(nb); E.t_seq.swap(ns); E.seg.swap(nseg);
         round++;
+        if (round > 30000) return LSW_E_INTERNAL;      // as lsw_find_all: "recursion did not terminate" (lsw_hit.depth is 16 bits)
     }
     if (errflag) return LSW_E_INTERNAL;
     if (n_out) *n_out = (int64_t)nhits;

@@ -267,3 +267,10 @@ def test_emu_recursion_deeper_than_pythons_limit():
     assert len(hits) == len(want) and cnt["tasks"] == st["calls"] and st["max_depth"] >= 1499
     for a, b in (("query", "seq"), ("start", "start"), ("end", "end"), ("depth", "depth"), ("matches", "matches")):
         assert (hits[a] == want[b]).all()
+
+
+def test_emu_stops_at_the_librarys_round_limit():
+    # a 1-base sequence on a homopolymer recurses once per base; past 30 000 levels the library (and its emulation) report an
+    # internal error instead of wrapping the 16-bit depth field (limits)
+    with pytest.raises(RuntimeError, match="rc=-6"):
+        emu_lib.find_all(["A" * 30500], ["A"], 0.7)
