@@ -90,7 +90,7 @@ def oracle_rows(find_all, reads, seqs, thr, *scoring):
 
 
 t_end = time.time() + budget
-it = bad = too_deep = 0
+it = bad = too_deep = limited = 0
 n_hits = 0
 while time.time() < t_end:
     rng = random.Random(seed0 + it)
@@ -138,9 +138,43 @@ while time.time() < t_end:
             got = hits_matrix(hits)[:, [0, 1, 2, 3, 4, 6, 7, 8, 9]]       # (the oracle's hit record has no mismatch count)
             if not (np.array_equal(got, want) and (cnt["tasks"], cnt["cells"]) == (calls, cells)):
                 what.append("ssw_find_all packed=%r" % packed)
+    # stage 2 (lamprey.py:1637-1658): random sub-reads of the batch (reverse-complemented or not) against one read as the reference
+    refs = [r for r in reads if 50 <= len(r) <= 700]
+    if it % 4 == 1 and refs:
+        from lamprey_b200._native import PAIR_DT
+        ref = refs[0].upper()
+        pairs = []
+        for _ in range(12):
+            i = rng.randrange(len(reads))
+            if reads[i]:
+                a = rng.randrange(len(reads[i]))
+                pairs.append((i, a, min(len(reads[i]), a + rng.randrange(1, 600)), rng.randrange(2)))
+        if pairs:
+            try:
+                res, cig = emu_lib.ssw_subreads(reads, np.array(pairs, PAIR_DT), ref)
+            except RuntimeError:                     # the band limit of the stage-2 kernel (reported, not guessed): counted
+                res, cig, pairs = [], [], []
+                limited += 1
+            for (i, a, b, rcf), r in zip(pairs, res):
+                q = reads[i][a:b].upper()
+                if rcf:
+                    q = "".join(COMP.get(ch, ch) for ch in reversed(q))
+                d = ssw_oracle.align(ref, q)
+                if d["score"] == 0:
+                    ok = r["score"] == 0
+                else:
+                    runs = [(int(x >> 2), " MID"[int(x & 3)]) for x in cig[r["cigar_off"]:r["cigar_off"] + r["n_cigar"]]]
+                    # (matches: the engine never counts a non-ACGT character as a match, the restated wrapper compares raw characters --
+                    # they differ only when the REFERENCE holds the same non-ACGT character; LAMPrey's references are ACGT and its
+                    # stage 2 does not read the match count)
+                    pure = set(ref) <= set("ACGT")
+                    ok = (r["score"], r["r_pos"], r["r_end"] - 1, r["q_pos"], r["q_end"] - 1, r["matches"] if pure else 0, runs) == \
+                        (d["score"], d["ref_begin"], d["ref_end"], d["read_begin"], d["read_end"], d["matches"] if pure else 0, d["cigar"])
+                if not ok:
+                    what.append("stage 2 pair %r" % ((i, a, b, rcf),))
     if what:
         bad += 1
         print("MISMATCH seed", seed0 + it, (M, X, gap), thr, [len(s) for s in seqs], [len(r) for r in reads], what, flush=True)
     it += 1
-print("fuzz_emu: %d cases (seeds %d..%d), %d oracle hits, %d mismatching cases, %d skipped (recursion deeper than 30000)" % (it, seed0, seed0 + it - 1, n_hits, bad, too_deep))
+print("fuzz_emu: %d cases (seeds %d..%d), %d oracle hits, %d mismatching cases, %d skipped (recursion deeper than 30000), %d stage-2 batches beyond the band limit" % (it, seed0, seed0 + it - 1, n_hits, bad, too_deep, limited))
 sys.exit(1 if bad else 0)
